@@ -1,0 +1,333 @@
+// 3x3x3 stride-1 Conv3d as a tcgen05 implicit GEMM for sm_100a.
+//
+// Replaces the cuDNN call behind `nn.Conv3d` of dynamic_network_architectures' ConvDropoutNormReLU, invoked at
+// _external/nnunetv2/inference/predict_from_raw_data.py:543.
+//
+// Design (measured basis: profiles/r01_probe_tcgen05.log):
+//   * SS-mode tcgen05.mma M=128,K=16 costs max(N/2, 32 + N/4) cycles - the A operand (4 KB/MMA) saturates the
+//     128 B/cycle shared-memory port, so N = C_out = 32 would cap at 40 % of the tensor peak.  We therefore FOLD the
+//     three dz taps into N: one MMA computes, for one input z-plane ("slab"), the contributions to the three output
+//     planes z-1, z, z+1 at once (N = 3*NC: 86 % at NC=32, 100 % at NC=64).  The three N-blocks land in three
+//     consecutive TMEM column slots (slot = output plane), so the tap sum happens by accumulation in TMEM.
+//   * A operand: a TMA 5-D box (8ch, 10x, 18y, zt+2 planes, 2 channel groups) of the C8 activation tensor, zero
+//     filled out of bounds (= conv padding).  The (dy,dx) taps are 16-byte address offsets of the same smem tile
+//     (no-swizzle K-major descriptors; M rows = 8 x-voxels x 16 y-rows, SBO = one halo row).
+//   * B operand: weights pre-packed on the host into the exact smem image, one bulk copy per K chunk.
+//   * Persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2-5
+//     epilogue (TMEM -> regs, +bias, InstanceNorm sum / sum^2, fp16 C8 store).  2-stage smem ring over K chunks of
+//     16 input channels; TMEM accumulators double-buffered when zt*NC <= 256.
+#include <vector>
+#include "net_kernels.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace boa {
+
+constexpr int MMA_THREADS = 192;
+constexpr int TILE_X = 8, TILE_Y = 16;
+constexpr int XB = TILE_X + 2, YB = TILE_Y + 2, SLAB = XB * YB;  // 180 halo positions per z-plane
+
+struct ConvMmaParams {
+  const __half* bpacked;
+  const float* bias;
+  __half* out;
+  double* stats;
+  int B, kc_count, Cout, D, H, W, zt;
+  int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
+  int in_groups_total, in_group_off;
+};
+
+__device__ __forceinline__ void decode_tile(int t, const ConvMmaParams& p, int& nt, int& b, int& tz, int& ty,
+                                            int& tx) {
+  tx = t % p.tiles_x; t /= p.tiles_x;
+  ty = t % p.tiles_y; t /= p.tiles_y;
+  tz = t % p.tiles_z; t /= p.tiles_z;
+  b = t % p.B;
+  nt = t / p.B;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(MMA_THREADS, 1)
+conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int zb = p.zt + 2;
+  const uint32_t a_bytes = 2u * zb * SLAB * 16u;
+  constexpr uint32_t b_group = 96u * NC;  // [2 kchunks][3*NC rows][16 B]
+  constexpr uint32_t b_bytes = 9u * b_group;
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
+  uint64_t* full = bars;        // [2] TMA -> MMA
+  uint64_t* empty = bars + 2;   // [2] MMA -> TMA
+  uint64_t* tfull = bars + 4;   // [2] MMA -> epilogue
+  uint64_t* tempty = bars + 6;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nbuf = (p.zt * NC <= 256) ? 2 : 1;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmapA);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int nt, b, tz, ty, tx;
+      decode_tile(tile, p, nt, b, tz, ty, tx);
+      for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
+        const int st = it & 1;
+        mbar_wait(&empty[st], ((it >> 1) & 1) ^ 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + st * stage_bytes;
+          mbar_arrive_expect_tx(&full[st], stage_bytes);
+          tma_load_5d(sa, &tmapA, &full[st], 0, tx * TILE_X - 1, ty * TILE_Y - 1, tz * p.zt - 1,
+                      b * p.in_groups_total + p.in_group_off + 2 * kc);
+          bulk_load(sa + a_bytes,
+                    reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)(nt * p.kc_count + kc) * b_bytes, b_bytes,
+                    &full[st]);
+        }
+        __syncwarp();
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    uint32_t it = 0, tcount = 0;
+    const uint32_t a_lbo = (uint32_t)zb * SLAB * 16u;  // next channel group (K chunk of 8)
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0;
+      const uint32_t tph = nbuf == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
+      mbar_wait(&tempty[buf], tph ^ 1);
+      tc_fence_after();
+      const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
+      for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
+        const int st = it & 1;
+        mbar_wait(&full[st], (it >> 1) & 1);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + st * stage_bytes);
+        const uint32_t b0 = a0 + a_bytes;
+        for (int i = 0; i < zb; ++i) {          // input z-plane (slab) i feeds output slots i-2 .. i
+          const int lo = max(0, i - 2), hi = min(p.zt - 1, i);
+          const int jlo = lo - (i - 2);         // first valid dz block (blocks are ordered dz = 2,1,0)
+          const bool fresh = (kc == 0) && (i <= p.zt - 1);  // slot i receives its first contribution now
+#pragma unroll
+          for (int g = 0; g < 9; ++g) {
+            const int dy = g / 3, dx = g % 3;
+            const uint64_t ad = umma_desc(a0 + (uint32_t)(i * SLAB + dy * XB + dx) * 16u, a_lbo, XB * 16u);
+            const uint32_t bg = b0 + g * b_group + (uint32_t)jlo * NC * 16u;
+            if (g == 0 && fresh) {
+              const int nprev = hi - lo;        // already-touched slots below slot hi
+              if (nprev > 0) {
+                const uint64_t bd = umma_desc(bg, 3u * NC * 16u, 128u);
+                if (elect_one()) umma_f16(dcol0 + lo * NC, ad, bd, umma_idesc_f16(128, nprev * NC), 1u);
+              }
+              const uint64_t bd2 = umma_desc(bg + (uint32_t)nprev * NC * 16u, 3u * NC * 16u, 128u);
+              if (elect_one()) umma_f16(dcol0 + hi * NC, ad, bd2, umma_idesc_f16(128, NC), 0u);
+            } else {
+              const uint64_t bd = umma_desc(bg, 3u * NC * 16u, 128u);
+              if (elect_one()) umma_f16(dcol0 + lo * NC, ad, bd, umma_idesc_f16(128, (hi - lo + 1) * NC), 1u);
+            }
+          }
+        }
+        if (elect_one()) umma_commit(&empty[st]);   // smem stage reusable once these MMAs retire
+        __syncwarp();
+      }
+      if (elect_one()) umma_commit(&tfull[buf]);     // accumulators of this tile complete
+      __syncwarp();
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;                  // TMEM lane quadrant this warp may read
+    const int row = q * 32 + lane;
+    uint32_t tcount = 0;
+    const int out_groups = p.Cout / 8;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      int nt, b, tz, ty, tx;
+      decode_tile(tile, p, nt, b, tz, ty, tx);
+      const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0;
+      const uint32_t tph = nbuf == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
+      mbar_wait(&tfull[buf], tph);
+      tc_fence_after();
+      const int x = tx * TILE_X + (row & 7), y = ty * TILE_Y + (row >> 3);
+      const bool rowvalid = (x < p.W) && (y < p.H);
+      const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(p.zt * NC);
+#pragma unroll 1
+      for (int chunk = 0; chunk < NC / 32; ++chunk) {
+        const int cbase = nt * NC + chunk * 32;
+        float s1[32], s2[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+        float bs[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) bs[c] = __ldg(p.bias + cbase + c);
+#pragma unroll 1
+        for (int slot = 0; slot < p.zt; ++slot) {
+          const int z = tz * p.zt + slot;
+          uint32_t v[32];
+          tmem_ld32(tlane + slot * NC + chunk * 32, v);
+          tmem_ld_wait();
+          if (z < p.D && rowvalid) {
+            float f[32];
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              f[c] = __uint_as_float(v[c]) + bs[c];
+              s1[c] += f[c];
+              s2[c] = fmaf(f[c], f[c], s2[c]);
+            }
+            uint4* dst = reinterpret_cast<uint4*>(p.out) +
+                         ((((size_t)b * out_groups + (cbase >> 3)) * p.D + z) * p.H + y) * p.W + x;
+            const size_t gstride = (size_t)p.D * p.H * p.W;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              uint4 o;
+              __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+              dst[j * gstride] = o;
+            }
+          }
+        }
+        // transpose-reduce over the 32 lanes: afterwards lane l holds the warp total of channel cbase + l
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+          const bool upper = (lane & off) != 0;
+#pragma unroll
+          for (int k = 0; k < off; ++k) {
+            const float send1 = upper ? s1[k] : s1[k + off];
+            const float send2 = upper ? s2[k] : s2[k + off];
+            const float r1 = __shfl_xor_sync(0xffffffffu, send1, off);
+            const float r2 = __shfl_xor_sync(0xffffffffu, send2, off);
+            s1[k] = (upper ? s1[k + off] : s1[k]) + r1;
+            s2[k] = (upper ? s2[k + off] : s2[k]) + r2;
+          }
+        }
+        if (p.stats) {
+          double* st = p.stats + ((size_t)b * p.Cout + cbase + lane) * 2;
+          atomicAdd(st, (double)s1[0]);
+          atomicAdd(st + 1, (double)s2[0]);
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+// ================================================================================================ host side
+struct ConvMmaPlan {
+  CUtensorMap tmap;
+  ConvMmaParams prm;
+  __half* d_bpacked = nullptr;
+  float* d_bias = nullptr;
+  int nc = 32;
+  size_t smem = 0;
+  int grid = 0;
+  double macs = 0;
+};
+
+ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin_w, int cin_padded, int Cout,
+                                  const ActView& src, int B, __half* d_raw_out, double* d_stats) {
+  if (cin_padded % 16 || Cout % 32 || cin_padded > src.groups * 8) {
+    set_error("conv_mma: unsupported channels cin=%d(padded %d) cout=%d src groups=%d", cin_w, cin_padded, Cout,
+              src.groups);
+    return nullptr;
+  }
+  ConvMmaPlan* pl = new ConvMmaPlan();
+  const int NC = (Cout % 64 == 0) ? 64 : 32;
+  pl->nc = NC;
+  const int zt = 8;
+  ConvMmaParams& p = pl->prm;
+  p.B = B; p.kc_count = cin_padded / 16; p.Cout = Cout; p.D = src.D; p.H = src.H; p.W = src.W; p.zt = zt;
+  p.tiles_x = (src.W + TILE_X - 1) / TILE_X;
+  p.tiles_y = (src.H + TILE_Y - 1) / TILE_Y;
+  p.tiles_z = (src.D + zt - 1) / zt;
+  p.n_ntiles = Cout / NC;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_z * B * p.n_ntiles;
+  p.in_groups_total = src.groups_total; p.in_group_off = src.group_off;
+  p.out = d_raw_out; p.stats = d_stats;
+  pl->macs = 27.0 * cin_w * Cout * (double)src.voxels() * B;
+
+  // pack weights: [nt][kc][g=(dy,dx)][kchunk][n = j*NC + co, j <-> dz = 2-j][8 cin]
+  const size_t b_group = 96 * (size_t)NC / 2;  // halves
+  std::vector<__half> hb((size_t)p.n_ntiles * p.kc_count * 9 * b_group);
+  for (int nt = 0; nt < p.n_ntiles; ++nt)
+    for (int kc = 0; kc < p.kc_count; ++kc)
+      for (int g = 0; g < 9; ++g) {
+        const int dy = g / 3, dx = g % 3;
+        __half* blk = hb.data() + (((size_t)nt * p.kc_count + kc) * 9 + g) * b_group;
+        for (int kch = 0; kch < 2; ++kch)
+          for (int j = 0; j < 3; ++j)
+            for (int co = 0; co < NC; ++co)
+              for (int e = 0; e < 8; ++e) {
+                const int ci = kc * 16 + kch * 8 + e;
+                const int dz = 2 - j;
+                float v = 0.f;
+                if (ci < cin_w) v = h_w[((size_t)(nt * NC + co) * cin_w + ci) * 27 + dz * 9 + dy * 3 + dx];
+                blk[((size_t)kch * 3 * NC + j * NC + co) * 8 + e] = __float2half_rn(v);
+              }
+      }
+  if (cudaMalloc(&pl->d_bpacked, hb.size() * 2) != cudaSuccess ||
+      cudaMalloc(&pl->d_bias, Cout * sizeof(float)) != cudaSuccess) {
+    set_error("conv_mma: cudaMalloc failed");
+    conv_mma_plan_destroy(pl);
+    return nullptr;
+  }
+  cudaMemcpy(pl->d_bpacked, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(pl->d_bias, h_bias, Cout * sizeof(float), cudaMemcpyHostToDevice);
+  p.bpacked = pl->d_bpacked; p.bias = pl->d_bias;
+
+  if (make_c8_tmap(&pl->tmap, src.base, B * src.groups_total, src.D, src.H, src.W, XB, YB, zt + 2, 2)) {
+    set_error("conv_mma: tensor map creation failed");
+    conv_mma_plan_destroy(pl);
+    return nullptr;
+  }
+  const size_t stage = 2 * (size_t)(zt + 2) * SLAB * 16 + 9 * 96 * (size_t)NC;
+  pl->smem = 2 * stage + 128;
+  cudaError_t e = NC == 64 ? cudaFuncSetAttribute(conv3_fold_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)
+                           : cudaFuncSetAttribute(conv3_fold_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  if (e != cudaSuccess) {
+    set_error("conv_mma: cannot opt in to %zu bytes of shared memory: %s", pl->smem, cudaGetErrorString(e));
+    conv_mma_plan_destroy(pl);
+    return nullptr;
+  }
+  pl->grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  return pl;
+}
+
+void conv_mma_plan_destroy(ConvMmaPlan* p) {
+  if (!p) return;
+  if (p->d_bpacked) cudaFree(p->d_bpacked);
+  if (p->d_bias) cudaFree(p->d_bias);
+  delete p;
+}
+
+double conv_mma_plan_macs(const ConvMmaPlan* p) { return p->macs; }
+
+int conv_mma_launch(ConvMmaPlan* pl, cudaStream_t s) {
+  if (pl->nc == 64)
+    conv3_fold_kernel<64><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
+  else
+    conv3_fold_kernel<32><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+}  // namespace boa

@@ -1,0 +1,432 @@
+// tcgen05 implicit GEMM over an explicit per-K-chunk tap list, for sm_100a.
+//
+// Covers the convolution shapes of PlainConvUNet that the dz-folded kernel (conv_mma.cu) does not:
+//   * 3x3x3 STRIDE-2 convs (first conv of encoder stages 1..n): run as a stride-1 gather over the space-to-depth copy
+//     of the input ([B][8 phases][C/8][D/2][H/2][W/2][8], written by the producer's normalise pass).  Output voxel o
+//     reads input 2o-1, 2o, 2o+1 per axis = (odd phase, o-1), (even phase, o), (odd phase, o): a K chunk of 16
+//     channels belongs to one phase and only carries the 1, 2, 4 or 8 taps that phase can serve - 27 in total, no
+//     wasted MACs.
+//   * ConvTranspose3d k=2,s=2 (decoder up-sampling): a single tap, the 8 output phases sit on N
+//     (n = phase * Cout + co) and the epilogue scatters them into the concat buffer.
+//   * plain 3x3x3 stride 1 (27 taps per chunk) as an independent cross-check of the folded kernel.
+// Replaces the cuDNN calls behind nn.Conv3d / nn.ConvTranspose3d of dynamic_network_architectures' PlainConvEncoder /
+// UNetDecoder, invoked at _external/nnunetv2/inference/predict_from_raw_data.py:543.
+//
+// Structure: persistent CTAs, warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue; A = TMA 5-D halo box
+// of the C8 tensor (zero filled out of bounds = conv padding), taps are 16-byte address offsets into it; B = weights
+// pre-packed on the host into the smem operand image, one bulk copy per chunk; accumulators: one TMEM slot of NC
+// columns per output z-plane of the tile, double buffered.
+#include <vector>
+#include "net_kernels.cuh"
+#include "ptx.cuh"
+#include "tmap.cuh"
+
+namespace boa {
+
+constexpr int TAPS_THREADS = 192;
+constexpr int TT_X = 8, TT_Y = 16;
+constexpr int TAPS_MAX_OPS = 27;
+constexpr int TAB_STRIDE = 32;  // ints per chunk-table entry: [0] n_ops, [1] b_off (16-byte units), [2..] a_off
+
+struct TapsParams {
+  const __half* bpacked;
+  const float* bias;
+  __half* out;
+  double* stats;
+  const int32_t* table;  // [kc_count][TAB_STRIDE]
+  int kind;
+  int B, kc_count, Ntotal, D, H, W, zt;
+  int box_x, box_y, box_z, org;
+  int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
+  int in_groups_total, in_group_off;
+  int out_groups_total, out_group_off, Cout;
+  int stages;
+  uint32_t a_bytes, a_tx_bytes, b_stage_bytes, b_nt_bytes;  // a_bytes: smem placement (128 B multiple), a_tx: TMA box
+};
+
+__device__ __forceinline__ void taps_decode_tile(int t, const TapsParams& p, int& nt, int& b, int& tz, int& ty,
+                                                 int& tx) {
+  tx = t % p.tiles_x; t /= p.tiles_x;
+  ty = t % p.tiles_y; t /= p.tiles_y;
+  tz = t % p.tiles_z; t /= p.tiles_z;
+  b = t % p.B;
+  nt = t / p.B;
+}
+
+template <int NC>
+__global__ void __launch_bounds__(TAPS_THREADS, 1)
+conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const uint32_t stage_bytes = p.a_bytes + p.b_stage_bytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
+  uint64_t* full = bars;         // [4] TMA -> MMA
+  uint64_t* empty = bars + 4;    // [4] MMA -> TMA
+  uint64_t* tfull = bars + 8;    // [2] MMA -> epilogue
+  uint64_t* tempty = bars + 10;  // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nstage = p.stages;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full[i], 1);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    fence_barrier_init();
+    tma_prefetch_desc(&tmapA);
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+  const uint32_t buf_cols = (uint32_t)(p.zt * NC);  // <= 256: two accumulator buffers
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    uint32_t it = 0;
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int nt, b, tz, ty, tx;
+      taps_decode_tile(tile, p, nt, b, tz, ty, tx);
+      for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
+        mbar_wait(&empty[st], ph ^ 1);
+        const int n_ops = __ldg(p.table + kc * TAB_STRIDE);
+        const int b_off = __ldg(p.table + kc * TAB_STRIDE + 1);
+        if (elect_one()) {
+          uint8_t* sa = smem + (size_t)st * stage_bytes;
+          const uint32_t bbytes = (uint32_t)n_ops * NC * 32u;
+          mbar_arrive_expect_tx(&full[st], p.a_tx_bytes + bbytes);
+          tma_load_5d(sa, &tmapA, &full[st], 0, tx * TT_X + p.org, ty * TT_Y + p.org, tz * p.zt + p.org,
+                      b * p.in_groups_total + p.in_group_off + 2 * kc);
+          bulk_load(sa + p.a_bytes,
+                    reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)nt * p.b_nt_bytes + (size_t)b_off * 16u,
+                    bbytes, &full[st]);
+        }
+        __syncwarp();
+        if (++st == nstage) { st = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    uint32_t tcount = 0;
+    int st = 0;
+    uint32_t ph = 0;
+    const uint32_t slab16 = (uint32_t)(p.box_x * p.box_y);           // 16-byte units per z-plane of the box
+    const uint32_t a_lbo = (uint32_t)p.box_z * slab16 * 16u;         // next channel group (8 channels of K)
+    const uint32_t a_sbo = (uint32_t)p.box_x * 16u;                  // next y row (8 rows of M)
+    const uint32_t idesc = umma_idesc_f16(128, NC);
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      const uint32_t buf = tcount & 1;
+      mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
+      tc_fence_after();
+      const uint32_t dcol0 = tbase + buf * buf_cols;
+      int tab_next = __ldg(p.table + lane);
+      for (int kc = 0; kc < p.kc_count; ++kc) {
+        const int tab = tab_next;
+        if (kc + 1 < p.kc_count) tab_next = __ldg(p.table + (kc + 1) * TAB_STRIDE + lane);  // hide the fetch
+        const int n_ops = __shfl_sync(0xffffffffu, tab, 0);
+        mbar_wait(&full[st], ph);
+        tc_fence_after();
+        const uint32_t a0 = smem_u32(smem + (size_t)st * stage_bytes);
+        const uint32_t b0 = a0 + p.a_bytes;
+        for (int z = 0; z < p.zt; ++z) {
+          for (int op = 0; op < n_ops; ++op) {
+            const uint32_t a_off = (uint32_t)__shfl_sync(0xffffffffu, tab, 2 + op);
+            const uint64_t ad = umma_desc(a0 + ((uint32_t)z * slab16 + a_off) * 16u, a_lbo, a_sbo);
+            const uint64_t bd = umma_desc(b0 + (uint32_t)op * NC * 32u, NC * 16u, 128u);
+            if (elect_one()) umma_f16(dcol0 + (uint32_t)z * NC, ad, bd, idesc, (kc | op) ? 1u : 0u);
+          }
+        }
+        if (elect_one()) umma_commit(&empty[st]);
+        __syncwarp();
+        if (++st == nstage) { st = 0; ph ^= 1; }
+      }
+      if (elect_one()) umma_commit(&tfull[buf]);
+      __syncwarp();
+    }
+  } else {
+    // ===================================================================== epilogue (warps 2..5)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t tcount = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      int nt, b, tz, ty, tx;
+      taps_decode_tile(tile, p, nt, b, tz, ty, tx);
+      const uint32_t buf = tcount & 1;
+      mbar_wait(&tfull[buf], (tcount >> 1) & 1);
+      tc_fence_after();
+      const int x = tx * TT_X + (row & 7), y = ty * TT_Y + (row >> 3);
+      const bool rowvalid = (x < p.W) && (y < p.H);
+      const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + buf * buf_cols;
+#pragma unroll 1
+      for (int chunk = 0; chunk < NC / 32; ++chunk) {
+        const int nbase = nt * NC + chunk * 32;  // first GEMM column of this 32-wide strip
+        float bs[32];
+#pragma unroll
+        for (int c = 0; c < 32; ++c) bs[c] = __ldg(p.bias + (nbase + c) % p.Cout);
+        if (p.kind != TAPS_TCONV2) {
+          float s1[32], s2[32];
+#pragma unroll
+          for (int c = 0; c < 32; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+          const int out_groups = p.Cout / 8;
+          const size_t gstride = (size_t)p.D * p.H * p.W;
+#pragma unroll 1
+          for (int slot = 0; slot < p.zt; ++slot) {
+            const int z = tz * p.zt + slot;
+            uint32_t v[32];
+            tmem_ld32(tlane + slot * NC + chunk * 32, v);
+            tmem_ld_wait();
+            if (z < p.D && rowvalid) {
+              float f[32];
+#pragma unroll
+              for (int c = 0; c < 32; ++c) {
+                f[c] = __uint_as_float(v[c]) + bs[c];
+                s1[c] += f[c];
+                s2[c] = fmaf(f[c], f[c], s2[c]);
+              }
+              uint4* dst = reinterpret_cast<uint4*>(p.out) +
+                           ((((size_t)b * out_groups + (nbase >> 3)) * p.D + z) * p.H + y) * p.W + x;
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                uint4 o;
+                __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
+                dst[j * gstride] = o;
+              }
+            }
+          }
+#pragma unroll
+          for (int off = 16; off >= 1; off >>= 1) {
+            const bool upper = (lane & off) != 0;
+#pragma unroll
+            for (int k = 0; k < off; ++k) {
+              const float send1 = upper ? s1[k] : s1[k + off];
+              const float send2 = upper ? s2[k] : s2[k + off];
+              const float r1 = __shfl_xor_sync(0xffffffffu, send1, off);
+              const float r2 = __shfl_xor_sync(0xffffffffu, send2, off);
+              s1[k] = (upper ? s1[k + off] : s1[k]) + r1;
+              s2[k] = (upper ? s2[k + off] : s2[k]) + r2;
+            }
+          }
+          if (p.stats) {
+            double* st = p.stats + ((size_t)b * p.Cout + nbase + lane) * 2;
+            atomicAdd(st, (double)s1[0]);
+            atomicAdd(st + 1, (double)s2[0]);
+          }
+        } else {
+          // transposed conv: column n = phase * Cout + co ; scatter to (2z+pz, 2y+py, 2x+px)
+          const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
+#pragma unroll 1
+          for (int slot = 0; slot < p.zt; ++slot) {
+            const int z = tz * p.zt + slot;
+            uint32_t v[32];
+            tmem_ld32(tlane + slot * NC + chunk * 32, v);
+            tmem_ld_wait();
+            if (z < p.D && rowvalid) {
+#pragma unroll
+              for (int j = 0; j < 4; ++j) {
+                const int n = nbase + 8 * j;
+                const int phs = n / p.Cout, co = n % p.Cout;
+                const int zo = 2 * z + (phs >> 2), yo = 2 * y + ((phs >> 1) & 1), xo = 2 * x + (phs & 1);
+                uint4 o;
+                __half2* h = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+                for (int e = 0; e < 4; ++e)
+                  h[e] = __floats2half2_rn(__uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e],
+                                           __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1]);
+                reinterpret_cast<uint4*>(p.out)[((((size_t)b * p.out_groups_total + p.out_group_off + (co >> 3)) * Do +
+                                                  zo) * Ho + yo) * Wo + xo] = o;
+              }
+            }
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tbase, 512);
+}
+
+// ================================================================================================ host side
+struct ConvTapsPlan {
+  CUtensorMap tmap;
+  TapsParams prm;
+  __half* d_bpacked = nullptr;
+  float* d_bias = nullptr;
+  int32_t* d_table = nullptr;
+  int nc = 64;
+  size_t smem = 0;
+  int grid = 0;
+};
+
+static inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
+
+ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float* h_bias, int cin_w, int Cout,
+                                    const ActView& src, int B, const ActView& dst, double* d_stats) {
+  const int cin_padded = (cin_w + 15) / 16 * 16;
+  const int Ntotal = kind == TAPS_TCONV2 ? 8 * Cout : Cout;
+  const int src_cin_groups = kind == TAPS_CONV3_S2 ? src.groups / 8 : src.groups;  // groups per phase for s2d
+  if (Cout % 8 || Ntotal % 64 || cin_padded / 8 > src_cin_groups || (kind == TAPS_CONV3_S2 && cin_w % 16)) {
+    set_error("conv_taps: unsupported channels kind=%d cin=%d cout=%d src groups=%d", (int)kind, cin_w, Cout,
+              src.groups);
+    return nullptr;
+  }
+  ConvTapsPlan* pl = new ConvTapsPlan();
+  const int NC = (kind != TAPS_CONV3_S1 && Ntotal % 128 == 0) ? 128 : 64;
+  pl->nc = NC;
+  TapsParams& p = pl->prm;
+  p.kind = (int)kind;
+  p.zt = 256 / NC;  // two TMEM accumulator buffers of zt*NC <= 256 columns
+  p.B = B; p.Ntotal = Ntotal; p.Cout = Cout; p.D = src.D; p.H = src.H; p.W = src.W;
+  const int halo = kind == TAPS_CONV3_S1 ? 2 : (kind == TAPS_CONV3_S2 ? 1 : 0);
+  p.org = kind == TAPS_TCONV2 ? 0 : -1;
+  p.box_x = TT_X + halo; p.box_y = TT_Y + halo; p.box_z = p.zt + halo;
+  p.tiles_x = (src.W + TT_X - 1) / TT_X;
+  p.tiles_y = (src.H + TT_Y - 1) / TT_Y;
+  p.tiles_z = (src.D + p.zt - 1) / p.zt;
+  p.n_ntiles = Ntotal / NC;
+  p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_z * B * p.n_ntiles;
+  p.in_groups_total = src.groups_total; p.in_group_off = src.group_off;
+  p.out = kind == TAPS_TCONV2 ? dst.base : dst.base;
+  p.out_groups_total = dst.groups_total; p.out_group_off = dst.group_off;
+  p.stats = kind == TAPS_TCONV2 ? nullptr : d_stats;
+
+  // ---- chunk table + packed weights
+  const int cpp = cin_padded / 16;                                   // K chunks per phase (or per tensor)
+  p.kc_count = kind == TAPS_CONV3_S2 ? 8 * cpp : cpp;
+  std::vector<int32_t> table((size_t)p.kc_count * TAB_STRIDE, 0);
+  struct Op { int a_off, tap; };
+  std::vector<std::vector<Op>> ops(p.kc_count);
+  int max_ops = 0;
+  size_t total_ops = 0;
+  for (int kc = 0; kc < p.kc_count; ++kc) {
+    std::vector<Op>& o = ops[kc];
+    if (kind == TAPS_CONV3_S1) {
+      for (int t = 0; t < 27; ++t) {
+        const int dz = t / 9, dy = (t / 3) % 3, dx = t % 3;
+        o.push_back({(dz * p.box_y + dy) * p.box_x + dx, t});
+      }
+    } else if (kind == TAPS_CONV3_S2) {
+      const int phs = kc / cpp, pz = phs >> 2, py = (phs >> 1) & 1, px = phs & 1;
+      // per axis: even phase serves tap d=1 at box offset 1; odd phase serves d=0 at offset 0 and d=2 at offset 1
+      auto opts = [](int bit, int (&off)[2], int (&d)[2]) {
+        if (bit) { off[0] = 0; d[0] = 0; off[1] = 1; d[1] = 2; return 2; }
+        off[0] = 1; d[0] = 1; return 1;
+      };
+      int oz[2], dzv[2], oy[2], dyv[2], ox[2], dxv[2];
+      const int nz = opts(pz, oz, dzv), ny = opts(py, oy, dyv), nx = opts(px, ox, dxv);
+      for (int a = 0; a < nz; ++a)
+        for (int bq = 0; bq < ny; ++bq)
+          for (int c = 0; c < nx; ++c)
+            o.push_back({(oz[a] * p.box_y + oy[bq]) * p.box_x + ox[c], dzv[a] * 9 + dyv[bq] * 3 + dxv[c]});
+    } else {
+      o.push_back({0, 0});
+    }
+    table[(size_t)kc * TAB_STRIDE] = (int)o.size();
+    table[(size_t)kc * TAB_STRIDE + 1] = (int)(total_ops * NC * 2);  // 16-byte units: NC*32 bytes per op
+    for (size_t i = 0; i < o.size(); ++i) table[(size_t)kc * TAB_STRIDE + 2 + i] = o[i].a_off;
+    max_ops = std::max(max_ops, (int)o.size());
+    total_ops += o.size();
+  }
+  const size_t nt_halves = total_ops * NC * 16;  // [op][kchunk 2][NC rows][8]
+  p.b_nt_bytes = (uint32_t)(nt_halves * 2);
+  std::vector<__half> hb((size_t)p.n_ntiles * nt_halves);
+  for (int nt = 0; nt < p.n_ntiles; ++nt) {
+    size_t opi = 0;
+    for (int kc = 0; kc < p.kc_count; ++kc)
+      for (const Op& op : ops[kc]) {
+        __half* blk = hb.data() + (size_t)nt * nt_halves + opi * NC * 16;
+        ++opi;
+        const int cc = kind == TAPS_CONV3_S2 ? kc % cpp : kc;
+        for (int kch = 0; kch < 2; ++kch)
+          for (int n = 0; n < NC; ++n)
+            for (int e = 0; e < 8; ++e) {
+              const int ci = cc * 16 + kch * 8 + e;
+              const int ng = nt * NC + n;
+              float v = 0.f;
+              if (ci < cin_w) {
+                if (kind == TAPS_TCONV2) {
+                  const int phs = ng / Cout, co = ng % Cout;
+                  v = h_w[((size_t)ci * Cout + co) * 8 + phs];
+                } else {
+                  v = h_w[((size_t)ng * cin_w + ci) * 27 + op.tap];
+                }
+              }
+              blk[((size_t)kch * NC + n) * 8 + e] = __float2half_rn(v);
+            }
+      }
+  }
+  if (cudaMalloc(&pl->d_bpacked, hb.size() * 2) != cudaSuccess ||
+      cudaMalloc(&pl->d_bias, Cout * sizeof(float)) != cudaSuccess ||
+      cudaMalloc(&pl->d_table, table.size() * sizeof(int32_t)) != cudaSuccess) {
+    set_error("conv_taps: cudaMalloc failed");
+    conv_taps_plan_destroy(pl);
+    return nullptr;
+  }
+  cudaMemcpy(pl->d_bpacked, hb.data(), hb.size() * 2, cudaMemcpyHostToDevice);
+  cudaMemcpy(pl->d_bias, h_bias, Cout * sizeof(float), cudaMemcpyHostToDevice);
+  cudaMemcpy(pl->d_table, table.data(), table.size() * sizeof(int32_t), cudaMemcpyHostToDevice);
+  p.bpacked = pl->d_bpacked; p.bias = pl->d_bias; p.table = pl->d_table;
+
+  if (make_c8_tmap(&pl->tmap, src.base, B * src.groups_total, src.D, src.H, src.W, p.box_x, p.box_y, p.box_z, 2)) {
+    set_error("conv_taps: tensor map creation failed");
+    conv_taps_plan_destroy(pl);
+    return nullptr;
+  }
+  p.a_tx_bytes = 2u * p.box_z * p.box_y * p.box_x * 16u;
+  p.a_bytes = round_up(p.a_tx_bytes, 128u);
+  p.b_stage_bytes = round_up((uint32_t)max_ops * NC * 32u, 128u);
+  const uint32_t stage = p.a_bytes + p.b_stage_bytes;
+  int stages = (int)(200u * 1024u / stage);
+  if (stages > 4) stages = 4;
+  if (stages < 2) {
+    set_error("conv_taps: stage of %u bytes does not fit twice in shared memory", stage);
+    conv_taps_plan_destroy(pl);
+    return nullptr;
+  }
+  p.stages = stages;
+  pl->smem = (size_t)stages * stage + 256;
+  // the attribute is per kernel, not per plan: always opt in to the full 227 KB
+  cudaError_t e = NC == 128 ? cudaFuncSetAttribute(conv_taps_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)
+                            : cudaFuncSetAttribute(conv_taps_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  if (e != cudaSuccess) {
+    set_error("conv_taps: cannot opt in to %zu bytes of shared memory: %s", pl->smem, cudaGetErrorString(e));
+    conv_taps_plan_destroy(pl);
+    return nullptr;
+  }
+  pl->grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  return pl;
+}
+
+void conv_taps_plan_destroy(ConvTapsPlan* p) {
+  if (!p) return;
+  if (p->d_bpacked) cudaFree(p->d_bpacked);
+  if (p->d_bias) cudaFree(p->d_bias);
+  if (p->d_table) cudaFree(p->d_table);
+  delete p;
+}
+
+int conv_taps_launch(ConvTapsPlan* pl, cudaStream_t s) {
+  if (pl->nc == 128)
+    conv_taps_kernel<128><<<pl->grid, TAPS_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
+  else
+    conv_taps_kernel<64><<<pl->grid, TAPS_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+}  // namespace boa

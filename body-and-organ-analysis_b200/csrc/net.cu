@@ -1,0 +1,656 @@
+// Network orchestrator of libboa_b200: builds the static launch schedule of one PlainConvUNet forward over a batch
+// of sliding-window patches and runs it (plain launches or a captured CUDA graph).
+//
+// Replaces  nnUNetPredictor.initialize_from_trained_model_folder  (_external/nnunetv2/inference/predict_from_raw_data.py:67-129)
+//           get_network_from_plans -> PlainConvUNet(**kwargs)     (_external/nnunetv2/utilities/get_network_from_plans.py:9-43,
+//                                                                  _external/nnunetv2/utilities/plans_handling/plans_handler.py:36-97)
+//           `self.network(x)` and the per-patch Gaussian accumulation (predict_from_raw_data.py:543,603-616)
+// Network semantics follow dynamic_network_architectures==0.4.3 (PlainConvEncoder / UNetDecoder / StackedConvBlocks /
+// ConvDropoutNormReLU); see oracle/network.py for the restatement this is tested against.
+//
+// Numerics: fp16 operands, fp32 accumulation on the tensor cores; conv outputs are stored once as fp16; InstanceNorm
+// statistics come from the fp32 accumulators (fp64 sums); normalise + LeakyReLU are applied to the stored fp16 values
+// in fp32 and stored as fp16 (the reference's CUDA path runs the same ops under torch.autocast fp16,
+// predict_from_raw_data.py:648).
+#include <map>
+#include <string>
+#include <vector>
+#include "net_kernels.cuh"
+
+namespace boa {
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+};
+
+enum StepKind { STEP_CONV_FOLD, STEP_CONV_TAPS, STEP_CONV_SIMT, STEP_TCONV_TAPS, STEP_TCONV_SIMT };
+
+struct ConvStep {  // conv -> (stats) -> norm + lrelu   |   transposed conv
+  StepKind kind;
+  bool is_tconv = false;
+  ActView src;           // input activation (for CONV_TAPS stride 2: the s2d view)
+  ActView src_plain;     // SIMT stride-2 path reads the plain activation
+  int cin = 0, cout = 0;
+  int ks[3] = {3, 3, 3}, stride[3] = {1, 1, 1};
+  int Do = 0, Ho = 0, Wo = 0;
+  __half* raw = nullptr;       // conv output before normalisation
+  ActView dst;                 // normalised output (conv) or direct output (tconv)
+  __half* s2d = nullptr;       // optional space-to-depth copy of the normalised output
+  float *d_w = nullptr, *d_bias = nullptr, *d_gamma = nullptr, *d_beta = nullptr;  // SIMT operands / norm affine
+  double* d_stats = nullptr;
+  float *d_scale = nullptr, *d_shift = nullptr;
+  ConvMmaPlan* fold = nullptr;
+  ConvTapsPlan* taps = nullptr;
+  double macs = 0;
+  std::string name;
+};
+
+// Scratch memory of one forward (activations, statistics, staging).  Networks of identical geometry run one at a
+// time on a stream and may share it (fold ensembles, the five `total` part models).
+struct Workspace {
+  std::vector<std::pair<void*, size_t>> bufs;
+  int refs = 1;
+};
+
+}  // namespace boa
+
+using namespace boa;
+
+struct boa_net {
+  boa_arch arch;
+  int device = 0, B = 1, mode = 0;
+  bool finalized = false;
+  std::map<std::string, HostTensor> tensors;
+  std::vector<void*> allocs;  // per-network memory (weights)
+  Workspace* ws = nullptr;    // shared scratch
+  size_t ws_cursor = 0;
+  std::vector<ConvStep> steps;
+  // head
+  float *d_head_w = nullptr, *d_head_b = nullptr;
+  ActView head_src;
+  __half* d_patch = nullptr;  // [B][2][P] C8 input
+  FwdCall* d_call = nullptr;
+  FwdCall* h_call = nullptr;  // pinned
+  double* d_stats_all = nullptr;
+  size_t stats_bytes = 0;
+  int64_t macs_per_patch = 0;
+  // timing
+  bool timing = false;
+  std::vector<cudaEvent_t> ev;
+  size_t ev_used = 0;
+  std::vector<std::pair<size_t, size_t>> conv_spans;  // event index pairs around conv kernels
+  std::vector<std::pair<size_t, size_t>> fwd_spans;
+  double ms_convs = 0, ms_total = 0;
+  int64_t n_conv_launches = 0;
+  // graph
+  cudaGraphExec_t graph_accum = nullptr;
+  int use_graph = 1;
+};
+
+namespace {
+
+template <typename T>
+T* dalloc(boa_net* net, size_t n) {
+  void* p = nullptr;
+  if (cudaMalloc(&p, n * sizeof(T)) != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes failed: %s", n * sizeof(T), cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  net->allocs.push_back(p);
+  return static_cast<T*>(p);
+}
+
+// Workspace allocation: buffers are requested in a deterministic order, so a network that shares a donor's workspace
+// walks the donor's list and must find the same sizes.
+template <typename T>
+T* wsalloc(boa_net* net, size_t n) {
+  const size_t bytes = n * sizeof(T);
+  Workspace* ws = net->ws;
+  if (net->ws_cursor < ws->bufs.size()) {
+    auto& b = ws->bufs[net->ws_cursor];
+    if (b.second != bytes) {
+      set_error("shared workspace mismatch at buffer %zu: have %zu bytes, need %zu (different network geometry)",
+                net->ws_cursor, b.second, bytes);
+      return nullptr;
+    }
+    ++net->ws_cursor;
+    return static_cast<T*>(b.first);
+  }
+  void* p = nullptr;
+  if (cudaMalloc(&p, bytes) != cudaSuccess) {
+    set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
+    return nullptr;
+  }
+  ws->bufs.push_back({p, bytes});
+  ++net->ws_cursor;
+  return static_cast<T*>(p);
+}
+
+float* upload(boa_net* net, const std::vector<float>& v) {
+  float* d = dalloc<float>(net, v.size());
+  if (d) cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+  return d;
+}
+
+std::vector<float> round_fp16(const std::vector<float>& v) {
+  std::vector<float> o(v.size());
+  for (size_t i = 0; i < v.size(); ++i) o[i] = __half2float(__float2half_rn(v[i]));
+  return o;
+}
+
+const HostTensor* find(boa_net* net, const std::string& key) {
+  auto it = net->tensors.find(key);
+  return it == net->tensors.end() ? nullptr : &it->second;
+}
+
+bool is3(const int* a, int v) { return a[0] == v && a[1] == v && a[2] == v; }
+
+cudaEvent_t next_event(boa_net* net, size_t* idx) {
+  if (net->ev_used == net->ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    net->ev.push_back(e);
+  }
+  *idx = net->ev_used;
+  return net->ev[net->ev_used++];
+}
+
+int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
+  const boa_arch& a = net->arch;
+  const int B = net->B;
+  size_t e0 = 0, e1 = 0;
+  const bool time_it = net->timing;
+  if (time_it) cudaEventRecord(next_event(net, &e0), s);
+  int r = BOA_OK;
+  if (st.is_tconv) {
+    if (st.kind == STEP_TCONV_TAPS && net->mode == 0) r = conv_taps_launch(st.taps, s);
+    else r = launch_tconv_simt(st.src, B, st.d_w, st.d_bias, st.cin, st.cout, st.stride, st.dst, s);
+    if (time_it) {
+      cudaEventRecord(next_event(net, &e1), s);
+      net->conv_spans.push_back({e0, e1});
+    }
+    return r;
+  }
+  if (net->mode == 0 && st.kind == STEP_CONV_FOLD) r = conv_mma_launch(st.fold, s);
+  else if (net->mode == 0 && st.kind == STEP_CONV_TAPS) r = conv_taps_launch(st.taps, s);
+  else
+    r = launch_conv_simt(st.src_plain, B, st.d_w, st.d_bias, st.cin, st.cout, st.ks, st.stride, st.raw, st.Do, st.Ho,
+                         st.Wo, st.d_stats, s);
+  if (time_it) {
+    cudaEventRecord(next_event(net, &e1), s);
+    net->conv_spans.push_back({e0, e1});
+  }
+  if (r) return r;
+  if ((r = launch_stats_finalize(st.d_stats, st.d_gamma, st.d_beta, B, st.cout, (double)st.Do * st.Ho * st.Wo, a.eps,
+                                 st.d_scale, st.d_shift, s)))
+    return r;
+  return launch_norm_lrelu(st.raw, B, st.cout / 8, st.Do, st.Ho, st.Wo, st.d_scale, st.d_shift, a.leaky_slope, st.dst,
+                           st.s2d, s);
+}
+
+// everything of one forward except the input staging and the head
+int run_body(boa_net* net, cudaStream_t s) {
+  BOA_CUDA(cudaMemsetAsync(net->d_stats_all, 0, net->stats_bytes, s));
+  for (ConvStep& st : net->steps)
+    if (int r = run_step(net, st, s)) return r;
+  return BOA_OK;
+}
+
+int run_accumulate(boa_net* net, cudaStream_t s) {
+  const boa_arch& a = net->arch;
+  if (int r = launch_extract_patches(net->d_call, net->B, a.patch[0], a.patch[1], a.patch[2], net->d_patch, s)) return r;
+  if (int r = run_body(net, s)) return r;
+  for (int b = 0; b < net->B; ++b)
+    if (int r = launch_head(net->head_src, b, net->d_head_w, net->d_head_b, a.features[0], a.num_classes, nullptr,
+                            net->d_call, s))
+      return r;
+  return BOA_OK;
+}
+
+}  // namespace
+
+extern "C" int boa_net_create(const boa_arch* arch, int device, int max_batch, boa_net** out) {
+  BOA_REQUIRE(arch && out, "boa_net_create: null argument");
+  BOA_REQUIRE(arch->n_stages >= 2 && arch->n_stages <= BOA_MAX_STAGES, "boa_net_create: n_stages=%d unsupported",
+              arch->n_stages);
+  BOA_REQUIRE(max_batch >= 1 && max_batch <= MAX_BATCH, "boa_net_create: max_batch must be in [1, %d]", MAX_BATCH);
+  BOA_REQUIRE(arch->in_channels == 1, "boa_net_create: only single-channel (CT) input is implemented");
+  BOA_REQUIRE(arch->num_classes >= 1 && arch->num_classes <= 128, "boa_net_create: num_classes=%d out of range",
+              arch->num_classes);
+  for (int s = 0; s < arch->n_stages; ++s) {
+    BOA_REQUIRE(arch->features[s] % 8 == 0 && arch->features[s] > 0, "boa_net_create: features must be multiples of 8");
+    for (int k = 0; k < 3; ++k) {
+      BOA_REQUIRE(arch->kernels[s][k] == 1 || arch->kernels[s][k] == 3, "boa_net_create: kernel sizes must be 1 or 3");
+      BOA_REQUIRE(arch->strides[s][k] == 1 || arch->strides[s][k] == 2, "boa_net_create: strides must be 1 or 2");
+    }
+  }
+  BOA_REQUIRE(arch->features[0] <= 64, "boa_net_create: features[0] > 64 is not supported by the head kernel");
+  int ndev = 0;
+  BOA_CUDA(cudaGetDeviceCount(&ndev));
+  BOA_REQUIRE(device >= 0 && device < ndev, "boa_net_create: device %d not present (%d devices)", device, ndev);
+  BOA_CUDA(cudaSetDevice(device));
+  boa_net* net = new boa_net();
+  net->arch = *arch;
+  net->device = device;
+  net->B = max_batch;
+  net->ws = new Workspace();
+  *out = net;
+  return BOA_OK;
+}
+
+extern "C" int boa_net_set_tensor(boa_net* net, const char* key, const float* h_data, const int64_t* shape, int ndim) {
+  BOA_REQUIRE(net && key && h_data && shape, "boa_net_set_tensor: null argument");
+  BOA_REQUIRE(!net->finalized, "boa_net_set_tensor: network already finalized");
+  const std::string k(key);
+  // aliases of the same parameters registered twice by the package (StackedConvBlocks.all_modules, UNetDecoder.encoder)
+  if (k.find("all_modules") != std::string::npos || k.rfind("decoder.encoder.", 0) == 0) return BOA_OK;
+  HostTensor t;
+  size_t n = 1;
+  for (int i = 0; i < ndim; ++i) {
+    t.shape.push_back(shape[i]);
+    n *= (size_t)shape[i];
+  }
+  t.data.assign(h_data, h_data + n);
+  net->tensors[k] = std::move(t);
+  return BOA_OK;
+}
+
+extern "C" int boa_net_share_workspace(boa_net* net, boa_net* donor) {
+  BOA_REQUIRE(net && donor && net != donor, "boa_net_share_workspace: bad argument");
+  BOA_REQUIRE(!net->finalized && net->ws->bufs.empty(), "boa_net_share_workspace: must be called before finalize");
+  BOA_REQUIRE(net->device == donor->device && net->B == donor->B, "boa_net_share_workspace: device / batch differ");
+  if (--net->ws->refs == 0) delete net->ws;
+  net->ws = donor->ws;
+  ++net->ws->refs;
+  return BOA_OK;
+}
+
+extern "C" int boa_net_set_mode(boa_net* net, int mode) {
+  BOA_REQUIRE(net && (mode == 0 || mode == 1), "boa_net_set_mode: bad argument");
+  if (net->mode != mode && net->graph_accum) {
+    cudaGraphExecDestroy(net->graph_accum);
+    net->graph_accum = nullptr;
+  }
+  net->mode = mode;
+  return BOA_OK;
+}
+
+extern "C" int boa_net_set_graph(boa_net* net, int enable) {
+  BOA_REQUIRE(net, "boa_net_set_graph: null");
+  net->use_graph = enable ? 1 : 0;
+  return BOA_OK;
+}
+
+static int need(boa_net* net, const std::string& key, const HostTensor** out, size_t expect) {
+  const HostTensor* t = find(net, key);
+  if (!t) {
+    set_error("boa_net_finalize: missing tensor '%s'", key.c_str());
+    return BOA_ERR_STATE;
+  }
+  if (t->data.size() != expect) {
+    set_error("boa_net_finalize: tensor '%s' has %zu elements, expected %zu", key.c_str(), t->data.size(), expect);
+    return BOA_ERR_ARG;
+  }
+  *out = t;
+  return BOA_OK;
+}
+
+extern "C" int boa_net_finalize(boa_net* net) {
+  BOA_REQUIRE(net && !net->finalized, "boa_net_finalize: bad state");
+  BOA_CUDA(cudaSetDevice(net->device));
+  const boa_arch& a = net->arch;
+  const int n = a.n_stages, B = net->B;
+  // ---- spatial dims per stage
+  int dims[BOA_MAX_STAGES][3];
+  for (int k = 0; k < 3; ++k) dims[0][k] = a.patch[k];
+  for (int s = 0; s < n; ++s) {
+    for (int k = 0; k < 3; ++k) {
+      const int prev = s == 0 ? a.patch[k] : dims[s - 1][k];
+      BOA_REQUIRE(prev % a.strides[s][k] == 0, "boa_net_finalize: patch size not divisible by the strides");
+      dims[s][k] = prev / a.strides[s][k];
+    }
+  }
+  BOA_REQUIRE(is3(a.strides[0], 1), "boa_net_finalize: stage 0 must have stride 1");
+  auto vox = [&](int s) { return (size_t)dims[s][0] * dims[s][1] * dims[s][2]; };
+  auto view = [&](__half* base, int groups_total, int off, int groups, int s) {
+    ActView v;
+    v.base = base; v.groups_total = groups_total; v.group_off = off; v.groups = groups;
+    v.D = dims[s][0]; v.H = dims[s][1]; v.W = dims[s][2];
+    return v;
+  };
+  // ---- buffers
+  net->d_patch = wsalloc<__half>(net, (size_t)B * 16 * vox(0));
+  if (!net->d_patch) return BOA_ERR_CUDA;
+  __half *raw[BOA_MAX_STAGES], *mid[BOA_MAX_STAGES][2], *outb[BOA_MAX_STAGES], *cat[BOA_MAX_STAGES],
+      *s2d[BOA_MAX_STAGES];
+  for (int s = 0; s < n; ++s) {
+    const size_t f = (size_t)a.features[s];
+    raw[s] = wsalloc<__half>(net, B * f * vox(s));
+    mid[s][0] = wsalloc<__half>(net, B * f * vox(s));
+    mid[s][1] = wsalloc<__half>(net, B * f * vox(s));
+    outb[s] = wsalloc<__half>(net, B * f * vox(s));
+    cat[s] = s < n - 1 ? wsalloc<__half>(net, B * 2 * f * vox(s)) : nullptr;
+    const bool iso2 = s < n - 1 && is3(a.strides[s + 1], 2) && dims[s][0] % 2 == 0 && dims[s][1] % 2 == 0 &&
+                      dims[s][2] % 2 == 0;
+    s2d[s] = iso2 ? wsalloc<__half>(net, B * f * vox(s)) : nullptr;
+    if (!raw[s] || !mid[s][0] || !mid[s][1] || !outb[s] || (s < n - 1 && !cat[s]) || (iso2 && !s2d[s]))
+      return BOA_ERR_CUDA;
+  }
+  // ---- schedule
+  int n_norm_layers = 0;
+  for (int s = 0; s < n; ++s) n_norm_layers += a.n_conv_enc[s];
+  for (int j = 0; j < n - 1; ++j) n_norm_layers += a.n_conv_dec[j];
+  int cmax = 0;
+  for (int s = 0; s < n; ++s) cmax = std::max(cmax, a.features[s]);
+  net->stats_bytes = (size_t)n_norm_layers * B * cmax * 2 * sizeof(double);
+  net->d_stats_all = wsalloc<double>(net, (size_t)n_norm_layers * B * cmax * 2);
+  if (!net->d_stats_all) return BOA_ERR_CUDA;
+  int layer_idx = 0;
+  double macs = 0;
+
+  auto add_conv = [&](const std::string& prefix, ActView src, ActView src_s2d, int cin, int cout, const int* ks,
+                      const int* stride, int s_out, ActView dst, __half* s2d_out) -> int {
+    ConvStep st;
+    st.name = prefix;
+    st.cin = cin; st.cout = cout;
+    for (int k = 0; k < 3; ++k) { st.ks[k] = ks[k]; st.stride[k] = stride[k]; }
+    st.Do = dims[s_out][0]; st.Ho = dims[s_out][1]; st.Wo = dims[s_out][2];
+    st.raw = raw[s_out];
+    st.dst = dst;
+    st.s2d = s2d_out;
+    st.src_plain = src;
+    const size_t k3 = (size_t)ks[0] * ks[1] * ks[2];
+    const HostTensor *w, *bi, *g, *be;
+    if (int r = need(net, prefix + ".conv.weight", &w, (size_t)cout * cin * k3)) return r;
+    if (int r = need(net, prefix + ".conv.bias", &bi, cout)) return r;
+    if (int r = need(net, prefix + ".norm.weight", &g, cout)) return r;
+    if (int r = need(net, prefix + ".norm.bias", &be, cout)) return r;
+    const std::vector<float> wr = round_fp16(w->data);
+    st.d_w = upload(net, wr);
+    st.d_bias = upload(net, bi->data);
+    st.d_gamma = upload(net, g->data);
+    st.d_beta = upload(net, be->data);
+    st.d_stats = net->d_stats_all + (size_t)layer_idx * B * cmax * 2;
+    st.d_scale = wsalloc<float>(net, (size_t)B * cout);
+    st.d_shift = wsalloc<float>(net, (size_t)B * cout);
+    if (!st.d_w || !st.d_bias || !st.d_gamma || !st.d_beta || !st.d_scale || !st.d_shift) return BOA_ERR_CUDA;
+    ++layer_idx;
+    st.macs = (double)k3 * cin * cout * st.Do * st.Ho * st.Wo;
+    macs += st.macs;
+    st.kind = STEP_CONV_SIMT;
+    st.src = src;
+    const int cin_padded = (cin + 15) / 16 * 16;
+    if (is3(ks, 3) && is3(stride, 1) && cout % 32 == 0 && cin_padded <= src.groups * 8) {
+      st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats);
+      if (!st.fold) return BOA_ERR_CUDA;
+      st.kind = STEP_CONV_FOLD;
+    } else if (is3(ks, 3) && is3(stride, 2) && src_s2d.base && cin % 16 == 0 && cout % 64 == 0) {
+      ActView rawv = dst;  // only dims/base used by the conv epilogue
+      rawv.base = st.raw; rawv.groups_total = cout / 8; rawv.group_off = 0; rawv.groups = cout / 8;
+      st.taps = conv_taps_plan_create(TAPS_CONV3_S2, wr.data(), bi->data.data(), cin, cout, src_s2d, B, rawv,
+                                      st.d_stats);
+      if (!st.taps) return BOA_ERR_CUDA;
+      st.kind = STEP_CONV_TAPS;
+      st.src = src_s2d;
+    }
+    net->steps.push_back(st);
+    return BOA_OK;
+  };
+
+  // encoder
+  ActView cur = view(net->d_patch, 2, 0, 2, 0);
+  ActView cur_s2d;  // s2d copy of `cur` when it exists
+  int cur_c = a.in_channels;
+  for (int s = 0; s < n; ++s) {
+    const int f = a.features[s];
+    for (int i = 0; i < a.n_conv_enc[s]; ++i) {
+      const bool last = i == a.n_conv_enc[s] - 1;
+      const int one[3] = {1, 1, 1};
+      const int* stride = i == 0 ? a.strides[s] : one;
+      ActView dst = last ? (s < n - 1 ? view(cat[s], 2 * f / 8, f / 8, f / 8, s) : view(outb[s], f / 8, 0, f / 8, s))
+                         : view(mid[s][i & 1], f / 8, 0, f / 8, s);
+      __half* s2d_out = (last && s < n - 1) ? s2d[s] : nullptr;
+      char name[64];
+      snprintf(name, sizeof(name), "encoder.stages.%d.0.convs.%d", s, i);
+      if (int r = add_conv(name, cur, i == 0 ? cur_s2d : ActView(), cur_c, f, a.kernels[s], stride, s, dst, s2d_out))
+        return r;
+      cur = dst;
+      cur_c = f;
+      cur_s2d = ActView();
+      if (s2d_out) {
+        cur_s2d.base = s2d_out; cur_s2d.groups_total = f; cur_s2d.group_off = 0; cur_s2d.groups = f;  // 8 * f/8
+        cur_s2d.D = dims[s][0] / 2; cur_s2d.H = dims[s][1] / 2; cur_s2d.W = dims[s][2] / 2;
+      }
+    }
+  }
+  // decoder
+  for (int j = 0; j < n - 1; ++j) {
+    const int s_below = n - 1 - j, s = n - 2 - j;
+    const int cb = a.features[s_below], f = a.features[s];
+    const int* st3 = a.strides[s_below];
+    ConvStep up;
+    up.is_tconv = true;
+    char name[64];
+    snprintf(name, sizeof(name), "decoder.transpconvs.%d", j);
+    up.name = name;
+    up.cin = cb; up.cout = f;
+    for (int k = 0; k < 3; ++k) up.stride[k] = st3[k];
+    up.src = cur;
+    up.dst = view(cat[s], 2 * f / 8, 0, f / 8, s);
+    const size_t nph = (size_t)st3[0] * st3[1] * st3[2];
+    const HostTensor *w, *bi;
+    if (int r = need(net, up.name + ".weight", &w, (size_t)cb * f * nph)) return r;
+    if (int r = need(net, up.name + ".bias", &bi, f)) return r;
+    const std::vector<float> wr = round_fp16(w->data);
+    up.d_w = upload(net, wr);
+    up.d_bias = upload(net, bi->data);
+    if (!up.d_w || !up.d_bias) return BOA_ERR_CUDA;
+    up.macs = (double)nph * cb * f * vox(s_below);
+    macs += up.macs;
+    up.kind = STEP_TCONV_SIMT;
+    if (is3(st3, 2) && cb % 16 == 0 && (8 * f) % 64 == 0) {
+      up.taps = conv_taps_plan_create(TAPS_TCONV2, wr.data(), bi->data.data(), cb, f, cur, B, up.dst, nullptr);
+      if (!up.taps) return BOA_ERR_CUDA;
+      up.kind = STEP_TCONV_TAPS;
+    }
+    net->steps.push_back(up);
+    cur = view(cat[s], 2 * f / 8, 0, 2 * f / 8, s);
+    cur_c = 2 * f;
+    for (int i = 0; i < a.n_conv_dec[j]; ++i) {
+      const bool last = i == a.n_conv_dec[j] - 1;
+      const int one[3] = {1, 1, 1};
+      ActView dst = last ? view(outb[s], f / 8, 0, f / 8, s) : view(mid[s][i & 1], f / 8, 0, f / 8, s);
+      snprintf(name, sizeof(name), "decoder.stages.%d.convs.%d", j, i);
+      if (int r = add_conv(name, cur, ActView(), cur_c, f, a.kernels[s], one, s, dst, nullptr)) return r;
+      cur = dst;
+      cur_c = f;
+    }
+  }
+  // head
+  {
+    char name[64];
+    snprintf(name, sizeof(name), "decoder.seg_layers.%d", n - 2);
+    const HostTensor *w, *bi;
+    if (int r = need(net, std::string(name) + ".weight", &w, (size_t)a.num_classes * a.features[0])) return r;
+    if (int r = need(net, std::string(name) + ".bias", &bi, a.num_classes)) return r;
+    net->d_head_w = upload(net, round_fp16(w->data));
+    net->d_head_b = upload(net, bi->data);
+    if (!net->d_head_w || !net->d_head_b) return BOA_ERR_CUDA;
+    net->head_src = cur;
+    macs += (double)a.num_classes * a.features[0] * vox(0);
+  }
+  net->macs_per_patch = (int64_t)macs;
+  net->d_call = wsalloc<FwdCall>(net, 1);
+  if (!net->d_call) return BOA_ERR_CUDA;
+  BOA_CUDA(cudaMallocHost(&net->h_call, sizeof(FwdCall)));
+  net->tensors.clear();
+  net->finalized = true;
+  return BOA_OK;
+}
+
+extern "C" int boa_net_forward_accumulate(boa_net* net, const float* d_vol, const int32_t* vol_shape,
+                                          const int32_t* h_origins, int n_patches, const float* d_gaussian,
+                                          float* d_logits_acc, void* stream) {
+  BOA_REQUIRE(net && net->finalized, "boa_net_forward_accumulate: network not finalized");
+  BOA_REQUIRE(d_vol && vol_shape && h_origins && d_gaussian && d_logits_acc, "boa_net_forward_accumulate: null");
+  const boa_arch& a = net->arch;
+  for (int p = 0; p < n_patches; ++p)
+    for (int k = 0; k < 3; ++k)
+      BOA_REQUIRE(h_origins[3 * p + k] >= 0 && h_origins[3 * p + k] + a.patch[k] <= vol_shape[k],
+                  "boa_net_forward_accumulate: patch %d outside the volume", p);
+  BOA_CUDA(cudaSetDevice(net->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  for (int p0 = 0; p0 < n_patches; p0 += net->B) {
+    const int nb = std::min(net->B, n_patches - p0);
+    // the pinned staging struct is reused: wait until the previous copy has been consumed
+    BOA_CUDA(cudaStreamSynchronize(s));
+    FwdCall* c = net->h_call;
+    c->vol = d_vol; c->acc = d_logits_acc; c->gaussian = d_gaussian;
+    c->d0 = vol_shape[0]; c->d1 = vol_shape[1]; c->d2 = vol_shape[2];
+    c->n_valid = nb;
+    for (int b = 0; b < MAX_BATCH; ++b)
+      for (int k = 0; k < 3; ++k) c->origins[b][k] = b < nb ? h_origins[3 * (p0 + b) + k] : 0;
+    BOA_CUDA(cudaMemcpyAsync(net->d_call, c, sizeof(FwdCall), cudaMemcpyHostToDevice, s));
+    size_t f0 = 0, f1 = 0;
+    if (net->timing) cudaEventRecord(next_event(net, &f0), s);
+    if (net->use_graph && !net->timing) {
+      if (!net->graph_accum) {
+        cudaStream_t cs;
+        BOA_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+        cudaGraph_t g = nullptr;
+        BOA_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+        const uint64_t before = g_launches.load();
+        int r = run_accumulate(net, cs);
+        net->n_conv_launches = (int64_t)(g_launches.load() - before);  // launches per graph replay
+        cudaError_t ce = cudaStreamEndCapture(cs, &g);
+        cudaStreamDestroy(cs);
+        if (r) return r;
+        BOA_CUDA(ce);
+        BOA_CUDA(cudaGraphInstantiate(&net->graph_accum, g, 0));
+        cudaGraphDestroy(g);
+        g_launches.fetch_sub((uint64_t)net->n_conv_launches);  // capture enqueued nothing
+      }
+      BOA_CUDA(cudaGraphLaunch(net->graph_accum, s));
+      count_launch((int)net->n_conv_launches);
+    } else {
+      if (int r = run_accumulate(net, s)) return r;
+    }
+    if (net->timing) {
+      cudaEventRecord(next_event(net, &f1), s);
+      net->fwd_spans.push_back({f0, f1});
+    }
+  }
+  return BOA_OK;
+}
+
+extern "C" int boa_net_forward_logits(boa_net* net, const float* d_patches, int n_patches, float* d_logits,
+                                      void* stream) {
+  BOA_REQUIRE(net && net->finalized, "boa_net_forward_logits: network not finalized");
+  BOA_REQUIRE(d_patches && d_logits, "boa_net_forward_logits: null");
+  const boa_arch& a = net->arch;
+  BOA_CUDA(cudaSetDevice(net->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t pv = (size_t)a.patch[0] * a.patch[1] * a.patch[2];
+  for (int p0 = 0; p0 < n_patches; p0 += net->B) {
+    const int nb = std::min(net->B, n_patches - p0);
+    if (nb < net->B) BOA_CUDA(cudaMemsetAsync(net->d_patch, 0, (size_t)net->B * 16 * pv * sizeof(__half), s));
+    if (int r = launch_pack_patches(d_patches + (size_t)p0 * a.in_channels * pv, nb, a.in_channels, a.patch[0],
+                                    a.patch[1], a.patch[2], net->d_patch, 2, s))
+      return r;
+    if (int r = run_body(net, s)) return r;
+    for (int b = 0; b < nb; ++b)
+      if (int r = launch_head(net->head_src, b, net->d_head_w, net->d_head_b, a.features[0], a.num_classes,
+                              d_logits + (size_t)(p0 + b) * a.num_classes * pv, nullptr, s))
+        return r;
+  }
+  return BOA_OK;
+}
+
+extern "C" int64_t boa_net_macs_per_patch(const boa_net* net) { return net ? net->macs_per_patch : 0; }
+
+extern "C" int boa_net_enable_timing(boa_net* net, int enable) {
+  BOA_REQUIRE(net, "boa_net_enable_timing: null");
+  net->timing = enable != 0;
+  return BOA_OK;
+}
+
+extern "C" int boa_net_read_timing(boa_net* net, double* ms_convs, double* ms_total, int64_t* n_conv_launches,
+                                   int reset) {
+  BOA_REQUIRE(net, "boa_net_read_timing: null");
+  BOA_CUDA(cudaSetDevice(net->device));
+  BOA_CUDA(cudaDeviceSynchronize());
+  double mc = 0, mt = 0;
+  for (auto& sp : net->conv_spans) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, net->ev[sp.first], net->ev[sp.second]);
+    mc += ms;
+  }
+  for (auto& sp : net->fwd_spans) {
+    float ms = 0;
+    cudaEventElapsedTime(&ms, net->ev[sp.first], net->ev[sp.second]);
+    mt += ms;
+  }
+  if (ms_convs) *ms_convs = mc;
+  if (ms_total) *ms_total = mt;
+  if (n_conv_launches) *n_conv_launches = (int64_t)net->conv_spans.size();
+  if (reset) {
+    net->conv_spans.clear();
+    net->fwd_spans.clear();
+    net->ev_used = 0;
+  }
+  return BOA_OK;
+}
+
+// Per-layer description for profiling / DESIGN.md: writes up to `cap` entries, returns the number of steps.
+extern "C" int boa_net_describe(const boa_net* net, int cap, int32_t* kinds, double* macs, char* names, int name_stride) {
+  if (!net) return 0;
+  const int n = (int)net->steps.size();
+  for (int i = 0; i < n && i < cap; ++i) {
+    if (kinds) kinds[i] = (int)net->steps[i].kind;
+    if (macs) macs[i] = net->steps[i].macs;
+    if (names) snprintf(names + (size_t)i * name_stride, name_stride, "%s", net->steps[i].name.c_str());
+  }
+  return n;
+}
+
+// Time each step of one forward separately (bench / profiling): ms[i] = device time of step i's conv kernel.
+extern "C" int boa_net_time_layers(boa_net* net, int cap, float* ms, void* stream) {
+  BOA_REQUIRE(net && net->finalized && ms, "boa_net_time_layers: bad argument");
+  BOA_CUDA(cudaSetDevice(net->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const bool was = net->timing;
+  BOA_CUDA(cudaDeviceSynchronize());
+  net->conv_spans.clear();
+  net->fwd_spans.clear();
+  net->ev_used = 0;
+  net->timing = true;
+  int r = run_body(net, s);
+  net->timing = was;
+  if (r) return r;
+  BOA_CUDA(cudaDeviceSynchronize());
+  for (size_t i = 0; i < net->conv_spans.size() && (int)i < cap; ++i)
+    cudaEventElapsedTime(&ms[i], net->ev[net->conv_spans[i].first], net->ev[net->conv_spans[i].second]);
+  net->conv_spans.clear();
+  net->ev_used = 0;
+  return BOA_OK;
+}
+
+extern "C" void boa_net_destroy(boa_net* net) {
+  if (!net) return;
+  cudaSetDevice(net->device);
+  cudaDeviceSynchronize();
+  if (net->graph_accum) cudaGraphExecDestroy(net->graph_accum);
+  for (ConvStep& st : net->steps) {
+    if (st.fold) conv_mma_plan_destroy(st.fold);
+    if (st.taps) conv_taps_plan_destroy(st.taps);
+  }
+  for (void* p : net->allocs) cudaFree(p);
+  if (--net->ws->refs == 0) {
+    for (auto& b : net->ws->bufs) cudaFree(b.first);
+    delete net->ws;
+  }
+  for (cudaEvent_t e : net->ev) cudaEventDestroy(e);
+  if (net->h_call) cudaFreeHost(net->h_call);
+  delete net;
+}

@@ -1,0 +1,81 @@
+// Declarations shared between the network orchestrator (net.cu), the elementwise / SIMT kernels (net_simt.cu) and
+// the tcgen05 implicit-GEMM kernels (conv_mma.cu, conv_taps.cu).
+//
+// Activation layout "C8": [batch][C/8][D][H][W][8] fp16 - channel groups of 8 outermost, the 8 channels of a group
+// innermost (16 bytes).  A TMA box over it lands in shared memory as the no-swizzle K-major UMMA operand layout
+// directly (16-byte rows, see ptx.cuh umma_desc), tap shifts are plain address offsets, and a channel concat is two
+// adjacent sub-tensors.
+#pragma once
+#include "common.cuh"
+
+namespace boa {
+
+constexpr int MAX_BATCH = 16;
+
+struct ActView {  // a C8 tensor, possibly a channel-group slice of a wider buffer
+  __half* base = nullptr;  // start of the whole buffer
+  int groups_total = 0;    // channel groups of the whole buffer (per batch item)
+  int group_off = 0;       // first group of this view
+  int groups = 0;          // groups in this view
+  int D = 0, H = 0, W = 0;
+  size_t voxels() const { return (size_t)D * H * W; }
+};
+
+// Per-forward call parameters, kept in DEVICE memory so that the launch sequence of one forward is identical from
+// call to call (CUDA-graph friendly): kernels that touch the volume read them from here.
+struct FwdCall {
+  const float* vol;       // normalised volume fp32 [d0][d1][d2]
+  float* acc;             // logits accumulator fp32 [C][d0][d1][d2]
+  const float* gaussian;  // fp32 [p0][p1][p2]
+  int32_t d0, d1, d2;
+  int32_t n_valid;        // patches of this batch that are real (the rest are padding, never accumulated)
+  int32_t origins[MAX_BATCH][3];
+};
+
+// ---- elementwise / SIMT (net_simt.cu)
+// predict_from_raw_data.py:568-571: cut `data[sl]` -> fp16 C8 with 2 groups (channel 0 = voxel, others 0).
+int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2, __half* d_out_c8_16, cudaStream_t s);
+int launch_pack_patches(const float* d_patches, int n, int cin, int p0, int p1, int p2, __half* d_out_c8,
+                        int groups, cudaStream_t s);
+int launch_stats_finalize(const double* d_stats, const float* d_gamma, const float* d_beta, int B, int C,
+                          double n_vox, float eps, float* d_scale, float* d_shift, cudaStream_t s);
+// y = lrelu(x * scale + shift) -> fp16, written to dst view and (optionally) to a space-to-depth copy
+// [B][8 phases][groups][D/2][H/2][W/2][8] (phase = (z&1)*4 + (y&1)*2 + (x&1)) that turns the next stage's stride-2
+// convolution into a stride-1 one.
+int launch_norm_lrelu(const __half* d_raw, int B, int groups, int D, int H, int W, const float* d_scale,
+                      const float* d_shift, float slope, const ActView& dst, __half* d_s2d, cudaStream_t s);
+// SIMT direct convolution (anisotropic kernels / strides, and the on-device cross-check of the tensor-core kernels).
+// w: fp32 [Cout][cin_w][kz][ky][kx], already rounded to fp16 precision.
+int launch_conv_simt(const ActView& src, int B, const float* d_w, const float* d_bias, int cin_w, int Cout,
+                     const int* ks, const int* stride, __half* d_raw_out, int Do, int Ho, int Wo, double* d_stats,
+                     cudaStream_t s);
+// ConvTranspose3d kernel = stride: w fp32 [Cin][Cout][sz][sy][sx]; writes fp16 into dst view.
+int launch_tconv_simt(const ActView& src, int B, const float* d_w, const float* d_bias, int Cin, int Cout,
+                      const int* stride, const ActView& dst, cudaStream_t s);
+// 1x1x1 head. If d_logits_b != nullptr: write raw logits fp32 [C][P] of batch item b. Else accumulate logits*g into
+// the volume accumulator at the origin of batch item b (skipped when b >= call->n_valid); one launch per patch keeps
+// the reference's patch order (predict_from_raw_data.py:603-616).
+int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias, int Cin, int C, float* d_logits_b,
+                const FwdCall* d_call, cudaStream_t s);
+
+// ---- tcgen05 implicit GEMM, 3x3x3 stride 1 with the dz taps folded into N (conv_mma.cu)
+struct ConvMmaPlan;
+ConvMmaPlan* conv_mma_plan_create(const float* h_w /*[Cout][Cin_w][27] fp32*/, const float* h_bias, int cin_w,
+                                  int cin_padded, int Cout, const ActView& src, int B, __half* d_raw_out,
+                                  double* d_stats);
+void conv_mma_plan_destroy(ConvMmaPlan* p);
+int conv_mma_launch(ConvMmaPlan* p, cudaStream_t s);
+
+// ---- tcgen05 implicit GEMM over an explicit tap list (conv_taps.cu): stride-2 convs on the space-to-depth copy,
+//      transposed convs (one tap, 8 output phases on N), plain 3x3x3.
+struct ConvTapsPlan;
+enum TapsKind { TAPS_CONV3_S1 = 0, TAPS_CONV3_S2 = 1, TAPS_TCONV2 = 2 };
+// TAPS_CONV3_S1: h_w [Cout][cin_w][27], src = activation view;       out = raw [B][Cout/8][D][H][W], stats.
+// TAPS_CONV3_S2: h_w [Cout][cin_w][27], src = s2d view (8*groups);   out = raw at src dims,           stats.
+// TAPS_TCONV2:   h_w [Cin][Cout][8],    src = activation view;       out = dst view at 2x dims (bias, no stats).
+ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float* h_bias, int cin_w, int Cout,
+                                    const ActView& src, int B, const ActView& dst, double* d_stats);
+void conv_taps_plan_destroy(ConvTapsPlan* p);
+int conv_taps_launch(ConvTapsPlan* p, cudaStream_t s);
+
+}  // namespace boa

@@ -1,0 +1,572 @@
+// HBM-bound passes of the BOA hot path: CT normalisation, Gaussian patch accumulation, normalise+argmax+LUT merge,
+// HU tissue rules, per-slice / per-label integer reductions.  All are single-pass, 128-bit vectorised, grid sized
+// in multiples of the SM count; floating-point ops that must match numpy bit-for-bit use explicit *_rn intrinsics
+// (no FMA contraction).
+#include "common.cuh"
+
+namespace boa {
+
+// ------------------------------------------------------------------------------------------------ CT normalise
+// default_normalization_schemes.py:56-67 : clip, -= mean, /= max(std, 1e-8)  (fp32 throughout)
+__device__ __forceinline__ float ct_norm1(float x, float lo, float hi, float mean, float std) {
+  x = fminf(fmaxf(x, lo), hi);
+  return __fdiv_rn(__fsub_rn(x, mean), std);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) ct_normalize_kernel(const T* __restrict__ in, size_t n, float lo, float hi,
+                                                           float mean, float std, float* __restrict__ out) {
+  const size_t nvec = n / 8;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    float v[8];
+    if constexpr (sizeof(T) == 2) {
+      uint4 raw = __ldg(reinterpret_cast<const uint4*>(in) + i);
+      const short* s = reinterpret_cast<const short*>(&raw);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) v[k] = (float)s[k];
+    } else {
+      float4 a = __ldg(reinterpret_cast<const float4*>(in) + 2 * i);
+      float4 b = __ldg(reinterpret_cast<const float4*>(in) + 2 * i + 1);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+#pragma unroll
+    for (int k = 0; k < 8; ++k) v[k] = ct_norm1(v[k], lo, hi, mean, std);
+    reinterpret_cast<float4*>(out)[2 * i] = make_float4(v[0], v[1], v[2], v[3]);
+    reinterpret_cast<float4*>(out)[2 * i + 1] = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  // tail
+  for (size_t i = nvec * 8 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    out[i] = ct_norm1((float)in[i], lo, hi, mean, std);
+}
+
+// ------------------------------------------------------------------------------------------------ patch accumulate
+// predict_from_raw_data.py:609-613 : prediction *= gaussian ; predicted_logits[sl] += prediction
+__global__ void __launch_bounds__(256)
+accumulate_patch_kernel(const float* __restrict__ logits, int C, int p0, int p1, int p2, int o0, int o1, int o2,
+                        const float* __restrict__ g, float* __restrict__ acc, int d1, int d2, size_t vol_voxels) {
+  const size_t pv = (size_t)p0 * p1 * p2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pv; i += stride) {
+    const int k = (int)(i % p2);
+    const int j = (int)((i / p2) % p1);
+    const int ii = (int)(i / ((size_t)p2 * p1));
+    const size_t v = ((size_t)(o0 + ii) * d1 + (o1 + j)) * d2 + (o2 + k);
+    const float gw = __ldg(g + i);
+    for (int c = 0; c < C; ++c) {
+      const float pr = __fmul_rn(__ldg(logits + (size_t)c * pv + i), gw);
+      float* a = acc + (size_t)c * vol_voxels + v;
+      *a = __fadd_rn(*a, pr);
+    }
+  }
+}
+
+// predict_from_raw_data.py:614 : n_predictions[sl[1:]] += gaussian   (one launch per patch keeps the reference order)
+__global__ void __launch_bounds__(256)
+accumulate_weight_kernel(int p0, int p1, int p2, int o0, int o1, int o2, const float* __restrict__ g,
+                         float* __restrict__ wacc, int d1, int d2) {
+  const size_t pv = (size_t)p0 * p1 * p2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < pv; i += stride) {
+    const int k = (int)(i % p2);
+    const int j = (int)((i / p2) % p1);
+    const int ii = (int)(i / ((size_t)p2 * p1));
+    const size_t v = ((size_t)(o0 + ii) * d1 + (o1 + j)) * d2 + (o2 + k);
+    wacc[v] = __fadd_rn(wacc[v], __ldg(g + i));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ finalize + argmax
+struct Lut256 {
+  uint8_t v[256];
+};
+
+// predict_from_raw_data.py:620-625 (divide, isinf) ; label_handling.py:178 (argmax(0), first max wins) ;
+// totalsegmentator/nnunet.py:553-556 (part label -> global label, non-zero overwrite)
+template <int VEC>
+__device__ __forceinline__ void argmax_group(const float* __restrict__ acc, const float* __restrict__ wacc, int C,
+                                             size_t V, size_t v0, const Lut256& lut, int overwrite_nz,
+                                             uint8_t* __restrict__ label, int& bad) {
+  float w[VEC], best[VEC];
+  int arg[VEC];
+  if constexpr (VEC == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4*>(wacc + v0));
+    w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
+  } else {
+    w[0] = __ldg(wacc + v0);
+  }
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) { best[k] = 0.f; arg[k] = 0; }
+  for (int c = 0; c < C; ++c) {
+    float x[VEC];
+    if constexpr (VEC == 4) {
+      float4 t = __ldg(reinterpret_cast<const float4*>(acc + (size_t)c * V + v0));
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+      x[0] = __ldg(acc + (size_t)c * V + v0);
+    }
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) {
+      const float q = __fdiv_rn(x[k], w[k]);
+      if (!isfinite(q)) ++bad;
+      // numpy argmax: first maximum wins, NaN counts as maximum
+      if (c == 0 || (q > best[k] && !(best[k] != best[k])) || (q != q && best[k] == best[k])) {
+        best[k] = q;
+        arg[k] = c;
+      }
+    }
+  }
+  uint8_t out[VEC];
+#pragma unroll
+  for (int k = 0; k < VEC; ++k) out[k] = lut.v[arg[k]];
+  if (overwrite_nz) {
+    if constexpr (VEC == 4) {
+      uchar4 old = *reinterpret_cast<const uchar4*>(label + v0);
+      const uint8_t o[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (out[k] == 0) out[k] = o[k];
+    } else {
+      if (out[0] == 0) out[0] = label[v0];
+    }
+  }
+  if constexpr (VEC == 4) {
+    *reinterpret_cast<uchar4*>(label + v0) = make_uchar4(out[0], out[1], out[2], out[3]);
+  } else {
+    label[v0] = out[0];
+  }
+}
+
+__global__ void __launch_bounds__(256)
+finalize_argmax_kernel(const float* __restrict__ acc, const float* __restrict__ wacc, int C, size_t V, Lut256 lut,
+                       int overwrite_nz, uint8_t* __restrict__ label, int* __restrict__ nonfinite) {
+  int bad = 0;
+  const size_t nvec = V / 4;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride)
+    argmax_group<4>(acc, wacc, C, V, i * 4, lut, overwrite_nz, label, bad);
+  for (size_t v = nvec * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride)
+    argmax_group<1>(acc, wacc, C, V, v, lut, overwrite_nz, label, bad);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nonfinite, bad);
+}
+
+// ------------------------------------------------------------------------------------------------ tissue rules
+// tissue/definition.py:6-30 ; subclassification.py:38-53.  Bounds inclusive.
+__device__ __forceinline__ uint8_t tissue_rule(float hu, uint8_t region) {
+  const bool fat = hu >= -190.f && hu <= -30.f;
+  switch (region) {
+    case 2: return (hu >= -29.f && hu <= 150.f) ? 1 : (fat ? 5 : 0);  // MUSCLE / IMAT
+    case 5: return (hu >= -1000.f && hu <= 3000.f) ? 2 : 0;           // BONE
+    case 1: return fat ? 3 : 0;                                        // SAT
+    case 3: return fat ? 4 : 0;                                        // VAT
+    case 9: return fat ? 6 : 0;                                        // PAT
+    case 7: return fat ? 7 : 0;                                        // EAT
+    default: return 0;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+tissue_kernel(const T* __restrict__ ct, const uint8_t* __restrict__ regions, size_t n, uint8_t* __restrict__ out) {
+  const size_t nvec = n / 16;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 r4 = __ldg(reinterpret_cast<const uint4*>(regions) + i);
+    const uint8_t* r = reinterpret_cast<const uint8_t*>(&r4);
+    float hu[16];
+    if constexpr (sizeof(T) == 2) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(ct) + 2 * i);
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(ct) + 2 * i + 1);
+      const short* sa = reinterpret_cast<const short*>(&a);
+      const short* sb = reinterpret_cast<const short*>(&b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { hu[k] = (float)sa[k]; hu[8 + k] = (float)sb[k]; }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 f = __ldg(reinterpret_cast<const float4*>(ct) + 4 * i + q);
+        hu[4 * q] = f.x; hu[4 * q + 1] = f.y; hu[4 * q + 2] = f.z; hu[4 * q + 3] = f.w;
+      }
+    }
+    uint4 o4;
+    uint8_t* o = reinterpret_cast<uint8_t*>(&o4);
+#pragma unroll
+    for (int k = 0; k < 16; ++k) o[k] = tissue_rule(hu[k], r[k]);
+    reinterpret_cast<uint4*>(out)[i] = o4;
+  }
+  for (size_t v = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
+    out[v] = tissue_rule((float)ct[v], regions[v]);
+}
+
+// ------------------------------------------------------------------------------------------------ per-slice stats
+// builder.py:406-432 (per-slice per-tissue counts, with / without body_parts==TORSO), :284-305 (mean HU),
+// :56-99 and commands.py:34-44 (slice presence == count > 0).
+// One block handles a chunk of <= 65536 voxels of one slice: per-warp private histograms in shared memory
+// (u32 counts, u32 sums of hu+32768 - cannot overflow within a chunk), then 64-bit global atomics.
+constexpr int SLICE_CHUNK = 65536;
+constexpr int SLICE_THREADS = 256;
+
+template <typename T>
+__global__ void __launch_bounds__(SLICE_THREADS)
+slice_stats_kernel(const uint8_t* __restrict__ labels, const uint8_t* __restrict__ mask, int mask_value,
+                   const T* __restrict__ ct, size_t slice_voxels, int n_labels, int chunks_per_slice,
+                   unsigned long long* __restrict__ counts, long long* __restrict__ hu_sums) {
+  extern __shared__ uint32_t sm[];
+  const int nwarps = SLICE_THREADS / 32;
+  uint32_t* cnt = sm;                       // [nwarps][n_labels]
+  uint32_t* sum = sm + nwarps * n_labels;   // [nwarps][n_labels]
+  for (int i = threadIdx.x; i < 2 * nwarps * n_labels; i += SLICE_THREADS) sm[i] = 0;
+  __syncthreads();
+  const int z = blockIdx.x / chunks_per_slice;
+  const int chunk = blockIdx.x % chunks_per_slice;
+  const size_t begin = (size_t)chunk * SLICE_CHUNK;
+  const size_t end = min(begin + (size_t)SLICE_CHUNK, slice_voxels);
+  const size_t base = (size_t)z * slice_voxels;
+  const int warp = threadIdx.x >> 5;
+  uint32_t* mycnt = cnt + warp * n_labels;
+  uint32_t* mysum = sum + warp * n_labels;
+  const bool want_sum = (hu_sums != nullptr);
+  // 16-byte vector path needs (base+begin) 16-aligned for labels; fall back to scalar otherwise
+  const bool aligned = ((base + begin) % 16 == 0) && ((reinterpret_cast<uintptr_t>(labels) & 15) == 0) &&
+                       (!mask || (reinterpret_cast<uintptr_t>(mask) & 15) == 0) &&
+                       (!want_sum || (reinterpret_cast<uintptr_t>(ct) & 15) == 0);
+  size_t v = begin;
+  if (aligned) {
+    const size_t nvec = (end - begin) / 16;
+    for (size_t i = threadIdx.x; i < nvec; i += SLICE_THREADS) {
+      const size_t g = base + begin + i * 16;
+      const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(labels + g));
+      const uint8_t* l = reinterpret_cast<const uint8_t*>(&l4);
+      uint4 m4 = make_uint4(0, 0, 0, 0);
+      if (mask) m4 = __ldg(reinterpret_cast<const uint4*>(mask + g));
+      const uint8_t* m = reinterpret_cast<const uint8_t*>(&m4);
+      int hu[16];
+      if (want_sum) {
+        if constexpr (sizeof(T) == 2) {
+          const uint4 a = __ldg(reinterpret_cast<const uint4*>(ct + g));
+          const uint4 b = __ldg(reinterpret_cast<const uint4*>(ct + g) + 1);
+          const short* sa = reinterpret_cast<const short*>(&a);
+          const short* sb = reinterpret_cast<const short*>(&b);
+#pragma unroll
+          for (int k = 0; k < 8; ++k) { hu[k] = sa[k]; hu[8 + k] = sb[k]; }
+        } else {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) hu[k] = __float2int_rn((float)ct[g + k]);
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < 16; ++k) {
+        const int lab = l[k];
+        if (lab < n_labels && (!mask || m[k] == mask_value)) {
+          atomicAdd(&mycnt[lab], 1u);
+          if (want_sum) atomicAdd(&mysum[lab], (uint32_t)(hu[k] + 32768));
+        }
+      }
+    }
+    v = begin + nvec * 16;
+  }
+  for (size_t i = v + threadIdx.x; i < end; i += SLICE_THREADS) {
+    const size_t g = base + i;
+    const int lab = labels[g];
+    if (lab < n_labels && (!mask || mask[g] == mask_value)) {
+      atomicAdd(&mycnt[lab], 1u);
+      if (want_sum) {
+        int h;
+        if constexpr (sizeof(T) == 2) h = ct[g]; else h = __float2int_rn((float)ct[g]);
+        atomicAdd(&mysum[lab], (uint32_t)(h + 32768));
+      }
+    }
+  }
+  __syncthreads();
+  for (int lab = threadIdx.x; lab < n_labels; lab += SLICE_THREADS) {
+    unsigned long long c = 0, s = 0;
+    for (int w = 0; w < nwarps; ++w) { c += cnt[w * n_labels + lab]; s += sum[w * n_labels + lab]; }
+    if (c) {
+      if (counts) atomicAdd(&counts[(size_t)z * n_labels + lab], c);
+      if (want_sum) {
+        const long long signed_sum = (long long)s - 32768ll * (long long)c;
+        atomicAdd(reinterpret_cast<unsigned long long*>(&hu_sums[(size_t)z * n_labels + lab]),
+                  (unsigned long long)signed_sum);
+      }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ per-label HU hist
+// measurements.py:74-123 : every statistic of a label's HU distribution is an exact function of its integer histogram.
+template <typename T>
+__global__ void __launch_bounds__(256)
+label_hist_kernel(const T* __restrict__ ct, const uint8_t* __restrict__ labels, size_t n, int n_labels, int hu_min,
+                  int n_bins, uint32_t* __restrict__ hist, uint32_t* __restrict__ out_of_range) {
+  const size_t nvec = n / 16;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  uint32_t oor = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const uint4 l4 = __ldg(reinterpret_cast<const uint4*>(labels) + i);
+    if ((l4.x | l4.y | l4.z | l4.w) == 0) continue;  // all background: skip the CT read
+    const uint8_t* l = reinterpret_cast<const uint8_t*>(&l4);
+    int hu[16];
+    if constexpr (sizeof(T) == 2) {
+      const uint4 a = __ldg(reinterpret_cast<const uint4*>(ct) + 2 * i);
+      const uint4 b = __ldg(reinterpret_cast<const uint4*>(ct) + 2 * i + 1);
+      const short* sa = reinterpret_cast<const short*>(&a);
+      const short* sb = reinterpret_cast<const short*>(&b);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { hu[k] = sa[k]; hu[8 + k] = sb[k]; }
+    } else {
+#pragma unroll
+      for (int k = 0; k < 16; ++k) hu[k] = __float2int_rn((float)ct[i * 16 + k]);
+    }
+#pragma unroll
+    for (int k = 0; k < 16; ++k) {
+      const int lab = l[k];
+      if (lab == 0 || lab >= n_labels) continue;
+      const int bin = hu[k] - hu_min;
+      if (bin >= 0 && bin < n_bins) atomicAdd(&hist[(size_t)lab * n_bins + bin], 1u);
+      else ++oor;
+    }
+  }
+  for (size_t v = nvec * 16 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+    const int lab = labels[v];
+    if (lab == 0 || lab >= n_labels) continue;
+    int h;
+    if constexpr (sizeof(T) == 2) h = ct[v]; else h = __float2int_rn((float)ct[v]);
+    const int bin = h - hu_min;
+    if (bin >= 0 && bin < n_bins) atomicAdd(&hist[(size_t)lab * n_bins + bin], 1u);
+    else ++oor;
+  }
+  oor = __reduce_add_sync(0xffffffffu, oor);
+  if ((threadIdx.x & 31) == 0 && oor) atomicAdd(out_of_range, oor);
+}
+
+
+// ------------------------------------------------------------------------------------------------ label-set mask
+// compute/util.py:25-31 create_mask  +  measurements.py:29-39 (region minus fat: hu < lo OR hu > hi, strict)
+//                                    /  measurements.py:134-141 (lung fat: lo <= hu <= hi, inclusive)
+struct LabelSet {
+  uint8_t in[256];
+};
+template <typename T>
+__global__ void __launch_bounds__(256)
+mask_window_kernel(const T* __restrict__ ct, const uint8_t* __restrict__ labels, size_t n, LabelSet set, float lo,
+                   float hi, int inside, int use_window, uint8_t* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+    uint8_t m = set.in[labels[v]];
+    if (m && use_window) {
+      const float hu = (float)ct[v];
+      const bool in = hu >= lo && hu <= hi;
+      m = inside ? (in ? 1 : 0) : ((hu < lo || hu > hi) ? 1 : 0);
+    }
+    out[v] = m;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ box erosion
+// measurements.py:61-71 erode_region: footprint ones(6,6,6) padded at the end to 7^3 => window offsets -3..+2 per
+// axis; skimage.binary_erosion treats voxels outside the image as foreground.  Separable: one pass per axis.
+__global__ void __launch_bounds__(256)
+erode_axis_kernel(const uint8_t* __restrict__ in, uint8_t* __restrict__ out, int d0, int d1, int d2, int axis,
+                  int before, int after) {
+  const size_t n = (size_t)d0 * d1 * d2;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const int dims[3] = {d0, d1, d2};
+  const size_t strides[3] = {(size_t)d1 * d2, (size_t)d2, 1};
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+    const int c2 = (int)(v % d2), c1 = (int)((v / d2) % d1), c0 = (int)(v / ((size_t)d1 * d2));
+    const int c = axis == 0 ? c0 : (axis == 1 ? c1 : c2);
+    uint8_t m = 1;
+    for (int o = -before; o <= after; ++o) {
+      const int cc = c + o;
+      if (cc < 0 || cc >= dims[axis]) continue;  // outside the image counts as foreground
+      m &= in[v + (ptrdiff_t)o * (ptrdiff_t)strides[axis]] ? 1 : 0;
+    }
+    out[v] = m;
+  }
+}
+
+}  // namespace boa
+
+using namespace boa;
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+
+extern "C" int boa_ct_normalize(const void* d_in, int in_dtype, size_t n, float lo, float hi, float mean, float std,
+                                float* d_out, void* stream) {
+  BOA_REQUIRE(d_in && d_out, "boa_ct_normalize: null pointer");
+  BOA_REQUIRE(aligned16(d_in) && aligned16(d_out), "boa_ct_normalize: pointers must be 16-byte aligned");
+  BOA_REQUIRE(in_dtype == BOA_DT_I16 || in_dtype == BOA_DT_F32, "boa_ct_normalize: bad dtype %d", in_dtype);
+  if (n == 0) return BOA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  std = fmaxf(std, 1e-8f);
+  const int threads = 256, grid = grid_for(n / 8 + 1, threads);
+  if (in_dtype == BOA_DT_I16)
+    ct_normalize_kernel<short><<<grid, threads, 0, s>>>(static_cast<const short*>(d_in), n, lo, hi, mean, std, d_out);
+  else
+    ct_normalize_kernel<float><<<grid, threads, 0, s>>>(static_cast<const float*>(d_in), n, lo, hi, mean, std, d_out);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+static int check_patch_in_volume(const int32_t* patch, const int32_t* origin, const int32_t* vol) {
+  for (int a = 0; a < 3; ++a)
+    if (origin[a] < 0 || patch[a] <= 0 || origin[a] + patch[a] > vol[a]) {
+      set_error("patch [%d,%d,%d]+[%d,%d,%d] outside volume [%d,%d,%d]", origin[0], origin[1], origin[2], patch[0],
+                patch[1], patch[2], vol[0], vol[1], vol[2]);
+      return BOA_ERR_ARG;
+    }
+  return BOA_OK;
+}
+
+extern "C" int boa_accumulate_patch(const float* d_logits, int C, const int32_t* patch, const int32_t* origin,
+                                    const float* d_gaussian, float* d_logits_acc, const int32_t* vol_shape,
+                                    void* stream) {
+  BOA_REQUIRE(d_logits && patch && origin && d_gaussian && d_logits_acc && vol_shape, "boa_accumulate_patch: null");
+  BOA_REQUIRE(C > 0, "boa_accumulate_patch: C must be positive");
+  if (int r = check_patch_in_volume(patch, origin, vol_shape)) return r;
+  const size_t pv = (size_t)patch[0] * patch[1] * patch[2];
+  const size_t vv = (size_t)vol_shape[0] * vol_shape[1] * vol_shape[2];
+  accumulate_patch_kernel<<<grid_for(pv, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_logits, C, patch[0], patch[1], patch[2], origin[0], origin[1], origin[2], d_gaussian, d_logits_acc,
+      vol_shape[1], vol_shape[2], vv);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+extern "C" int boa_accumulate_weights(const int32_t* h_origins, int n_patches, const int32_t* patch,
+                                      const float* d_gaussian, float* d_weight_acc, const int32_t* vol_shape,
+                                      void* stream) {
+  BOA_REQUIRE(h_origins && patch && d_gaussian && d_weight_acc && vol_shape, "boa_accumulate_weights: null");
+  const size_t pv = (size_t)patch[0] * patch[1] * patch[2];
+  for (int p = 0; p < n_patches; ++p) {
+    const int32_t* o = h_origins + 3 * p;
+    if (int r = check_patch_in_volume(patch, o, vol_shape)) return r;
+    accumulate_weight_kernel<<<grid_for(pv, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        patch[0], patch[1], patch[2], o[0], o[1], o[2], d_gaussian, d_weight_acc, vol_shape[1], vol_shape[2]);
+    BOA_CHECK_LAUNCH();
+  }
+  return BOA_OK;
+}
+
+extern "C" int boa_finalize_argmax(const float* d_logits_acc, const float* d_weight_acc, int C, size_t V,
+                                   const uint8_t* h_lut, int overwrite_nonzero_only, uint8_t* d_label_inout,
+                                   int32_t* d_nonfinite, void* stream) {
+  BOA_REQUIRE(d_logits_acc && d_weight_acc && h_lut && d_label_inout && d_nonfinite, "boa_finalize_argmax: null");
+  BOA_REQUIRE(C > 0 && C <= 256, "boa_finalize_argmax: C=%d out of range", C);
+  BOA_REQUIRE(aligned16(d_logits_acc) && aligned16(d_weight_acc) && (reinterpret_cast<uintptr_t>(d_label_inout) & 3) == 0,
+              "boa_finalize_argmax: misaligned pointer");
+  if (V == 0) return BOA_OK;
+  Lut256 lut;
+  for (int c = 0; c < 256; ++c) lut.v[c] = c < C ? h_lut[c] : 0;
+  // float4 channel loads need V % 4 == 0 for every channel plane to stay 16-byte aligned
+  if (V % 4 != 0) {
+    set_error("boa_finalize_argmax: V (%zu) must be a multiple of 4", V);
+    return BOA_ERR_ARG;
+  }
+  finalize_argmax_kernel<<<grid_for(V / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_logits_acc, d_weight_acc, C, V, lut, overwrite_nonzero_only, d_label_inout, d_nonfinite);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+extern "C" int boa_tissue_subclassify(const void* d_ct, int ct_dtype, const uint8_t* d_regions, size_t n,
+                                      uint8_t* d_tissues, void* stream) {
+  BOA_REQUIRE(d_ct && d_regions && d_tissues, "boa_tissue_subclassify: null pointer");
+  BOA_REQUIRE(aligned16(d_ct) && aligned16(d_regions) && aligned16(d_tissues), "boa_tissue_subclassify: misaligned");
+  BOA_REQUIRE(ct_dtype == BOA_DT_I16 || ct_dtype == BOA_DT_F32, "boa_tissue_subclassify: bad dtype %d", ct_dtype);
+  if (n == 0) return BOA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n / 16 + 1, 256);
+  if (ct_dtype == BOA_DT_I16)
+    tissue_kernel<short><<<grid, 256, 0, s>>>(static_cast<const short*>(d_ct), d_regions, n, d_tissues);
+  else
+    tissue_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(d_ct), d_regions, n, d_tissues);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+extern "C" int boa_slice_label_stats(const uint8_t* d_labels, const uint8_t* d_mask, int mask_value, const void* d_ct,
+                                     int ct_dtype, int Z, size_t slice_voxels, int n_labels, uint64_t* d_counts,
+                                     int64_t* d_hu_sums, void* stream) {
+  BOA_REQUIRE(d_labels, "boa_slice_label_stats: null labels");
+  BOA_REQUIRE(d_counts || d_hu_sums, "boa_slice_label_stats: no output requested");
+  BOA_REQUIRE(!d_hu_sums || d_ct, "boa_slice_label_stats: hu_sums needs ct");
+  BOA_REQUIRE(n_labels > 0 && n_labels <= 256, "boa_slice_label_stats: n_labels=%d out of range", n_labels);
+  BOA_REQUIRE(ct_dtype == BOA_DT_I16 || ct_dtype == BOA_DT_F32, "boa_slice_label_stats: bad dtype %d", ct_dtype);
+  if (Z <= 0 || slice_voxels == 0) return BOA_OK;
+  const int chunks = (int)((slice_voxels + SLICE_CHUNK - 1) / SLICE_CHUNK);
+  const size_t smem = (size_t)2 * (SLICE_THREADS / 32) * n_labels * sizeof(uint32_t);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  auto c = reinterpret_cast<unsigned long long*>(d_counts);
+  auto h = reinterpret_cast<long long*>(d_hu_sums);
+  if (ct_dtype == BOA_DT_I16)
+    slice_stats_kernel<short><<<Z * chunks, SLICE_THREADS, smem, s>>>(d_labels, d_mask, mask_value,
+                                                                     static_cast<const short*>(d_ct), slice_voxels,
+                                                                     n_labels, chunks, c, h);
+  else
+    slice_stats_kernel<float><<<Z * chunks, SLICE_THREADS, smem, s>>>(d_labels, d_mask, mask_value,
+                                                                     static_cast<const float*>(d_ct), slice_voxels,
+                                                                     n_labels, chunks, c, h);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+extern "C" int boa_label_hu_hist(const void* d_ct, int ct_dtype, const uint8_t* d_labels, size_t n, int n_labels,
+                                 int hu_min, int n_bins, uint32_t* d_hist, uint32_t* d_out_of_range, void* stream) {
+  BOA_REQUIRE(d_ct && d_labels && d_hist && d_out_of_range, "boa_label_hu_hist: null pointer");
+  BOA_REQUIRE(aligned16(d_ct) && aligned16(d_labels), "boa_label_hu_hist: misaligned");
+  BOA_REQUIRE(n_labels > 0 && n_labels <= 256 && n_bins > 0, "boa_label_hu_hist: bad sizes");
+  BOA_REQUIRE(ct_dtype == BOA_DT_I16 || ct_dtype == BOA_DT_F32, "boa_label_hu_hist: bad dtype %d", ct_dtype);
+  if (n == 0) return BOA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n / 16 + 1, 256);
+  if (ct_dtype == BOA_DT_I16)
+    label_hist_kernel<short><<<grid, 256, 0, s>>>(static_cast<const short*>(d_ct), d_labels, n, n_labels, hu_min,
+                                                  n_bins, d_hist, d_out_of_range);
+  else
+    label_hist_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(d_ct), d_labels, n, n_labels, hu_min,
+                                                  n_bins, d_hist, d_out_of_range);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+extern "C" int boa_mask_label_minus_window(const void* d_ct, int ct_dtype, const uint8_t* d_labels, size_t n,
+                                           const uint8_t* h_label_set, int lo, int hi, int mode, uint8_t* d_mask,
+                                           void* stream) {
+  BOA_REQUIRE(d_labels && h_label_set && d_mask, "boa_mask_label_minus_window: null pointer");
+  BOA_REQUIRE(mode >= 0 && mode <= 2, "boa_mask_label_minus_window: mode must be 0 (labels only), 1 (inside) or 2 (outside)");
+  BOA_REQUIRE(mode == 0 || d_ct, "boa_mask_label_minus_window: window modes need the CT");
+  BOA_REQUIRE(ct_dtype == BOA_DT_I16 || ct_dtype == BOA_DT_F32, "boa_mask_label_minus_window: bad dtype %d", ct_dtype);
+  if (n == 0) return BOA_OK;
+  LabelSet set;
+  for (int i = 0; i < 256; ++i) set.in[i] = h_label_set[i] ? 1 : 0;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n, 256);
+  if (ct_dtype == BOA_DT_I16)
+    mask_window_kernel<short><<<grid, 256, 0, s>>>(static_cast<const short*>(d_ct), d_labels, n, set, (float)lo,
+                                                   (float)hi, mode == 1, mode != 0, d_mask);
+  else
+    mask_window_kernel<float><<<grid, 256, 0, s>>>(static_cast<const float*>(d_ct), d_labels, n, set, (float)lo,
+                                                   (float)hi, mode == 1, mode != 0, d_mask);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+extern "C" int boa_erode_box(const uint8_t* d_mask, const int32_t* shape, int before, int after, uint8_t* d_tmp,
+                             uint8_t* d_out, void* stream) {
+  BOA_REQUIRE(d_mask && shape && d_tmp && d_out, "boa_erode_box: null pointer");
+  BOA_REQUIRE(before >= 0 && after >= 0, "boa_erode_box: negative window");
+  BOA_REQUIRE(d_tmp != d_mask && d_tmp != d_out, "boa_erode_box: d_tmp must not alias the input or output");
+  const size_t n = (size_t)shape[0] * shape[1] * shape[2];
+  if (n == 0) return BOA_OK;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int grid = grid_for(n, 256);
+  erode_axis_kernel<<<grid, 256, 0, s>>>(d_mask, d_out, shape[0], shape[1], shape[2], 2, before, after);
+  BOA_CHECK_LAUNCH();
+  erode_axis_kernel<<<grid, 256, 0, s>>>(d_out, d_tmp, shape[0], shape[1], shape[2], 1, before, after);
+  BOA_CHECK_LAUNCH();
+  erode_axis_kernel<<<grid, 256, 0, s>>>(d_tmp, d_out, shape[0], shape[1], shape[2], 0, before, after);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}

@@ -1,0 +1,101 @@
+"""plans.json / dataset.json / checkpoint loading: host mirror of
+  PlansManager / ConfigurationManager incl. the old-plans reconstruction
+      (_external/nnunetv2/utilities/plans_handling/plans_handler.py:36-97,142-152,264-325)
+  nnUNetPredictor.initialize_from_trained_model_folder (_external/nnunetv2/inference/predict_from_raw_data.py:67-129)
+  LabelManager channel counts (_external/nnunetv2/utilities/label_handling/label_handling.py:241-245,294-311)
+"""
+from __future__ import annotations
+
+import json
+import os
+from dataclasses import dataclass, field
+
+
+@dataclass
+class ModelSpec:
+    arch: dict
+    intensity: dict            # mean, std, percentile_00_5, percentile_99_5 of channel 0
+    labels: dict               # name -> int
+    transpose_forward: list
+    transpose_backward: list
+    spacing: list
+    configuration: str
+    fold_weights: list = field(default_factory=list)   # list of state dicts (name -> tensor)
+    folder: str = ""
+
+
+def arch_from_plans(plans: dict, configuration: str, num_input_channels: int, num_classes: int) -> dict:
+    cfg = dict(plans["configurations"][configuration])
+    while "inherits_from" in cfg:  # plans_handler.py:231-253
+        parent = dict(plans["configurations"][cfg.pop("inherits_from")])
+        parent.update(cfg)
+        cfg = parent
+    if "architecture" in cfg:
+        kw = cfg["architecture"]["arch_kwargs"]
+        cls = cfg["architecture"]["network_class_name"].rsplit(".", 1)[-1]
+        features = list(kw["features_per_stage"])
+        kernels, strides = kw["kernel_sizes"], kw["strides"]
+        n_enc, n_dec = kw["n_conv_per_stage"], kw["n_conv_per_stage_decoder"]
+        eps = (kw.get("norm_op_kwargs") or {}).get("eps", 1e-5)
+    else:
+        cls = cfg["UNet_class_name"]
+        n_enc, n_dec = cfg["n_conv_per_stage_encoder"], cfg["n_conv_per_stage_decoder"]
+        features = [min(cfg["UNet_base_num_features"] * 2 ** i, cfg["unet_max_num_features"])
+                    for i in range(len(n_enc))]
+        kernels, strides = cfg["conv_kernel_sizes"], cfg["pool_op_kernel_sizes"]
+        eps = 1e-5
+    if cls != "PlainConvUNet":
+        raise NotImplementedError(f"network class {cls} is not implemented (PlainConvUNet only)")
+    if isinstance(n_enc, int):
+        n_enc = [n_enc] * len(features)
+    if isinstance(n_dec, int):
+        n_dec = [n_dec] * (len(features) - 1)
+    return {
+        "in_channels": num_input_channels, "num_classes": num_classes, "features": features,
+        "kernels": [list(k) for k in kernels], "strides": [list(s) for s in strides],
+        "n_conv_enc": list(n_enc), "n_conv_dec": list(n_dec), "eps": float(eps), "leaky_slope": 0.01,
+        "patch_size": list(cfg["patch_size"]),
+    }
+
+
+def load_model_folder(model_training_output_dir: str, use_folds, checkpoint_name: str = "checkpoint_final.pth") -> ModelSpec:
+    import torch
+
+    with open(os.path.join(model_training_output_dir, "dataset.json")) as f:
+        dataset_json = json.load(f)
+    with open(os.path.join(model_training_output_dir, "plans.json")) as f:
+        plans = json.load(f)
+    if isinstance(use_folds, (str, int)):
+        use_folds = [use_folds]
+    weights, configuration = [], None
+    for fold in use_folds:
+        fold = int(fold) if fold != "all" else fold
+        ckpt = torch.load(os.path.join(model_training_output_dir, f"fold_{fold}", checkpoint_name),
+                          map_location="cpu", weights_only=False)
+        configuration = ckpt["init_args"]["configuration"]
+        if ckpt.get("inference_allowed_mirroring_axes") is not None:
+            # the BOA path only uses *NoMirroring trainers (totalsegmentator/python_api.py:183-189)
+            raise NotImplementedError("test-time mirroring is not implemented (checkpoint allows mirroring axes)")
+        weights.append({k: v for k, v in ckpt["network_weights"].items()})
+    labels = dataset_json["labels"]
+    if any(isinstance(v, (list, tuple)) for v in labels.values()):
+        raise NotImplementedError("region-based label sets are not implemented")
+    num_classes = len([k for k in labels if k != "ignore"])
+    channels = dataset_json.get("channel_names", dataset_json.get("modality"))
+    arch = arch_from_plans(plans, configuration, len(channels), num_classes)
+    props = plans.get("foreground_intensity_properties_per_channel",
+                      plans.get("foreground_intensity_properties_by_modality"))["0"]
+    return ModelSpec(arch=arch, intensity=props, labels=labels, transpose_forward=plans["transpose_forward"],
+                     transpose_backward=plans["transpose_backward"],
+                     spacing=plans["configurations"][configuration].get("spacing", [1, 1, 1]),
+                     configuration=configuration, fold_weights=weights, folder=model_training_output_dir)
+
+
+def find_model_folder(results_root: str, dataset_id: int, trainer: str, plans: str = "nnUNetPlans",
+                      configuration: str = "3d_fullres") -> str:
+    """Dataset%03d_* lookup (nnunetv2/utilities/dataset_name_id_conversion.py:21-39, file_path_utilities.py:11-26)."""
+    prefix = f"Dataset{dataset_id:03d}"
+    cands = [d for d in sorted(os.listdir(results_root)) if d.startswith(prefix)]
+    if len(cands) != 1:
+        raise RuntimeError(f"expected exactly one folder starting with {prefix} under {results_root}, found {cands}")
+    return os.path.join(results_root, cands[0], f"{trainer}__{plans}__{configuration}")

@@ -1,0 +1,77 @@
+"""GPU parity of the network kernels (tcgen05 fold / tap-list / SIMT) against the CPU oracle, through the C ABI."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from boa_b200 import zoo
+from boa_b200.plans import arch_from_plans
+from boa_b200.predictor import Network
+from oracle.network import unet_forward
+
+
+# Tolerance (rel-L2 of the logits).  Oracle and kernels round activations to fp16 at the same two points per layer
+# (conv output, normalised output) - as the reference's CUDA path does under autocast - but sum in different orders,
+# so individual fp16 roundings flip and de-correlate downstream: two correct fp16 pipelines of this depth agree to
+# ~1.5e-3, and either is ~2.5e-3 from the fp32 pipeline (measured; see DESIGN.md "Numerics").
+TOL = 2.5e-3
+
+
+def _arch(patch, base, maxf, stages, ncls):
+    plans = zoo.default_plans(patch, base, maxf, stages)
+    return arch_from_plans(plans, "3d_fullres", 1, ncls)
+
+
+def _compare(arch, seed, n_patches, max_batch, tol_rel):
+    sd = zoo.random_state_dict(arch, seed)
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((n_patches, 1, *arch["patch_size"])).astype(np.float32)
+    ref = unet_forward(arch, sd, torch.from_numpy(x), emulate_fp16=True).numpy()
+    ref32 = unet_forward(arch, sd, torch.from_numpy(x), emulate_fp16=False).numpy()
+    out = {}
+    net = Network(arch, sd, 0, max_batch)
+    net.set_graph(False)
+    for mode in (1, 0):
+        net.set_mode(mode)
+        got = net.forward_logits(torch.from_numpy(x).cuda()).cpu().numpy()
+        out[mode] = got
+        scale = np.abs(ref).max()
+        err = np.abs(got - ref).max() / scale
+        rel = np.linalg.norm((got - ref).ravel()) / np.linalg.norm(ref.ravel())
+        rel32 = np.linalg.norm((got - ref32).ravel()) / np.linalg.norm(ref32.ravel())
+        agree = (got.argmax(1) == ref.argmax(1)).mean()
+        print(f"mode {mode}: rel-L2 err vs fp16-emulating oracle {rel:.2e}, max abs err / max|logit| {err:.2e} "
+              f"(max |logit| {scale:.2f}); rel-L2 vs fp32 oracle {rel32:.2e}; argmax agreement {agree:.6f}")
+        assert np.isfinite(got).all()
+        # north-star tolerance: logits within 1e-3 relative (L2); isolated fp16 rounding flips bound the max error
+        assert rel < tol_rel, f"mode {mode}: logits differ from the oracle by {rel} (rel-L2)"
+        assert err < 5 * tol_rel, f"mode {mode}: max logit error {err}"
+    kinds = [k for _, k, _ in net.describe()]
+    net.close()
+    return out, kinds
+
+
+def test_small_net_all_kernels(cuda):
+    # 3 stages, 32-64-128 features: exercises fold (NC 32 / 64), stride-2 tap list, transposed conv on tcgen05
+    arch = _arch((32, 32, 32), 32, 128, 3, 5)
+    out, kinds = _compare(arch, 11, 3, 2, TOL)
+    assert 0 in kinds and 1 in kinds and 3 in kinds, f"expected tcgen05 kernels in the schedule, got kinds {kinds}"
+    d = np.abs(out[0] - out[1]).max() / np.abs(out[1]).max()
+    assert d < TOL
+
+
+def test_anisotropic_net_simt(cuda):
+    # kernels / strides the tensor-core kernels do not cover run on the SIMT kernels explicitly
+    plans = zoo.default_plans((16, 32, 32), 8, 32, 3)
+    cfg = plans["configurations"]["3d_fullres"]
+    cfg["pool_op_kernel_sizes"] = [[1, 1, 1], [1, 2, 2], [2, 2, 2]]
+    cfg["conv_kernel_sizes"] = [[1, 3, 3], [3, 3, 3], [3, 3, 3]]
+    arch = arch_from_plans(plans, "3d_fullres", 1, 4)
+    _compare(arch, 5, 2, 2, TOL)
+
+
+def test_totalseg_geometry_one_patch(cuda):
+    # the real TotalSegmentator geometry at a 64^3 patch (6 stages, 32..320 features): every layer shape class
+    arch = _arch((64, 64, 64), 32, 320, 6, 25)
+    _compare(arch, 3, 1, 1, TOL)
