@@ -62,6 +62,8 @@ _SIGS = {
     "boa_erode_box": (C.c_int, [_P, C.POINTER(C.c_int32), C.c_int, C.c_int, _P, _P, _P]),
     "boa_mask_label_minus_window": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.POINTER(C.c_uint8), C.c_int, C.c_int,
                                               C.c_int, _P, _P]),
+    "boa_resample_z_cubic": (C.c_int, [_P, C.c_int, C.c_int, C.c_size_t, C.c_int, _P, _P, _P]),
+    "boa_resample_z_nearest_u8": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_int, _P, _P]),
     "boa_add_slab": (C.c_int, [_P, _P, C.c_size_t, _P]),
 }
 EXPORTS = sorted(_SIGS)

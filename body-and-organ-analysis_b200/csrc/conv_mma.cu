@@ -105,50 +105,53 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    uint32_t it = 0, tcount = 0;
-    const uint32_t a_lbo = (uint32_t)zb * SLAB * 16u;  // next channel group (K chunk of 8)
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0;
-      const uint32_t tph = nbuf == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
-      mbar_wait(&tempty[buf], tph ^ 1);
-      tc_fence_after();
-      const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
-      for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
-        const int st = it & 1;
-        mbar_wait(&full[st], (it >> 1) & 1);
+    // ===================================================================== MMA issuer (ONE thread runs the loop)
+    if (elect_one()) {
+      uint32_t it = 0, tcount = 0;
+      const uint32_t a_lbo = (uint32_t)zb * SLAB * 16u;  // next channel group (K chunk of 8)
+      // descriptors with a zero address field; tap / slab / row-block shifts are added to the low word (16-byte units;
+      // shared memory is < 256 KB so the 14-bit address field never carries)
+      const uint64_t a_desc0 = umma_desc(0, a_lbo, XB * 16u);
+      const uint64_t b_desc0 = umma_desc(0, 3u * NC * 16u, 128u);
+      constexpr uint32_t BG16 = b_group / 16u;           // one (dy,dx) weight block, in 16-byte units
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0;
+        const uint32_t tph = nbuf == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
+        mbar_wait(&tempty[buf], tph ^ 1);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + st * stage_bytes);
-        const uint32_t b0 = a0 + a_bytes;
-        for (int i = 0; i < zb; ++i) {          // input z-plane (slab) i feeds output slots i-2 .. i
-          const int lo = max(0, i - 2), hi = min(p.zt - 1, i);
-          const int jlo = lo - (i - 2);         // first valid dz block (blocks are ordered dz = 2,1,0)
-          const bool fresh = (kc == 0) && (i <= p.zt - 1);  // slot i receives its first contribution now
-#pragma unroll
-          for (int g = 0; g < 9; ++g) {
-            const int dy = g / 3, dx = g % 3;
-            const uint64_t ad = umma_desc(a0 + (uint32_t)(i * SLAB + dy * XB + dx) * 16u, a_lbo, XB * 16u);
-            const uint32_t bg = b0 + g * b_group + (uint32_t)jlo * NC * 16u;
-            if (g == 0 && fresh) {
-              const int nprev = hi - lo;        // already-touched slots below slot hi
-              if (nprev > 0) {
-                const uint64_t bd = umma_desc(bg, 3u * NC * 16u, 128u);
-                if (elect_one()) umma_f16(dcol0 + lo * NC, ad, bd, umma_idesc_f16(128, nprev * NC), 1u);
-              }
-              const uint64_t bd2 = umma_desc(bg + (uint32_t)nprev * NC * 16u, 3u * NC * 16u, 128u);
-              if (elect_one()) umma_f16(dcol0 + hi * NC, ad, bd2, umma_idesc_f16(128, NC), 0u);
+        const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
+        for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
+          const int st = it & 1;
+          mbar_wait(&full[st], (it >> 1) & 1);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + st * stage_bytes);
+          const uint64_t a_base = a_desc0 + (uint64_t)(a0 >> 4);
+          const uint64_t b_base = b_desc0 + (uint64_t)((a0 + a_bytes) >> 4);
+          for (int i = 0; i < zb; ++i) {          // input z-plane (slab) i feeds output slots i-2 .. i
+            const int lo = max(0, i - 2), hi = min(p.zt - 1, i);
+            const int jlo = lo - (i - 2);         // first valid dz block (blocks are ordered dz = 2,1,0)
+            const int n = hi - lo + 1;
+            const uint64_t ad = a_base + (uint64_t)(i * SLAB);
+            const uint64_t bd = b_base + (uint64_t)(jlo * NC);
+            const uint32_t dcol = dcol0 + (uint32_t)(lo * NC);
+            const uint32_t idesc = umma_idesc_f16(128, (uint32_t)(n * NC));
+            if (kc == 0 && i <= p.zt - 1) {
+              // slot i (= hi) receives its first contribution now: overwrite it, accumulate into the slots below
+              if (n > 1) umma_f16(dcol, ad, bd, umma_idesc_f16(128, (uint32_t)((n - 1) * NC)), 1u);
+              umma_f16(dcol0 + (uint32_t)(hi * NC), ad, bd + (uint64_t)((n - 1) * NC), umma_idesc_f16(128, NC), 0u);
             } else {
-              const uint64_t bd = umma_desc(bg, 3u * NC * 16u, 128u);
-              if (elect_one()) umma_f16(dcol0 + lo * NC, ad, bd, umma_idesc_f16(128, (hi - lo + 1) * NC), 1u);
+              umma_f16(dcol, ad, bd, idesc, 1u);
             }
+#pragma unroll
+            for (int g = 1; g < 9; ++g)
+              umma_f16(dcol, ad + (uint64_t)((g / 3) * XB + (g % 3)), bd + (uint64_t)(g * BG16), idesc, 1u);
           }
+          umma_commit(&empty[st]);   // smem stage reusable once these MMAs retire
         }
-        if (elect_one()) umma_commit(&empty[st]);   // smem stage reusable once these MMAs retire
-        __syncwarp();
+        umma_commit(&tfull[buf]);     // accumulators of this tile complete
       }
-      if (elect_one()) umma_commit(&tfull[buf]);     // accumulators of this tile complete
-      __syncwarp();
     }
+    __syncwarp();
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
@@ -251,9 +254,13 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
     return nullptr;
   }
   ConvMmaPlan* pl = new ConvMmaPlan();
-  const int NC = (Cout % 64 == 0) ? 64 : 32;
+  // NC = 64 reaches the full MMA rate (N = 192); small volumes (deep stages) cannot fill the machine with tiles, so
+  // they take NC = 32 (twice the CTAs, shorter per-tile chains) and a z-tile no taller than the volume.
+  const int zt = src.D < 8 ? src.D : 8;
+  const int tiles64 = ((src.W + TILE_X - 1) / TILE_X) * ((src.H + TILE_Y - 1) / TILE_Y) * ((src.D + zt - 1) / zt) * B *
+                      (Cout / 64 > 0 ? Cout / 64 : 1);
+  const int NC = (Cout % 64 == 0 && tiles64 >= sm_count()) ? 64 : 32;
   pl->nc = NC;
-  const int zt = 8;
   ConvMmaParams& p = pl->prm;
   p.B = B; p.kc_count = cin_padded / 16; p.Cout = Cout; p.D = src.D; p.H = src.H; p.W = src.W; p.zt = zt;
   p.tiles_x = (src.W + TILE_X - 1) / TILE_X;

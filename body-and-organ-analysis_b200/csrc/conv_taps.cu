@@ -26,14 +26,15 @@ namespace boa {
 constexpr int TAPS_THREADS = 192;
 constexpr int TT_X = 8, TT_Y = 16;
 constexpr int TAPS_MAX_OPS = 27;
-constexpr int TAB_STRIDE = 32;  // ints per chunk-table entry: [0] n_ops, [1] b_off (16-byte units), [2..] a_off
+constexpr int TAB_STRIDE = 32;  // ints per class-table entry: [0] n_ops, [1] ops of all earlier chunks, [2..] a_off
 
 struct TapsParams {
   const __half* bpacked;
   const float* bias;
   __half* out;
   double* stats;
-  const int32_t* table;  // [kc_count][TAB_STRIDE]
+  const int32_t* table;  // [n_classes][TAB_STRIDE]: n_ops, ops before this class, a_off[n_ops]
+  int n_classes, chunks_per_class;
   int kind;
   int B, kc_count, Ntotal, D, H, W, zt;
   int box_x, box_y, box_z, org;
@@ -64,8 +65,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
   uint64_t* tfull = bars + 8;    // [2] MMA -> epilogue
   uint64_t* tempty = bars + 10;  // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
+  int32_t* stab = reinterpret_cast<int32_t*>(bars + 14);  // [n_classes][TAB_STRIDE] tap table (<= 8 classes)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nstage = p.stages;
+  for (int i = threadIdx.x; i < p.n_classes * TAB_STRIDE; i += blockDim.x) stab[i] = __ldg(p.table + i);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) {
@@ -99,8 +102,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
       taps_decode_tile(tile, p, nt, b, tz, ty, tx);
       for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
         mbar_wait(&empty[st], ph ^ 1);
-        const int n_ops = __ldg(p.table + kc * TAB_STRIDE);
-        const int b_off = __ldg(p.table + kc * TAB_STRIDE + 1);
+        const int cls = kc / p.chunks_per_class;
+        const int n_ops = __ldg(p.table + cls * TAB_STRIDE);
+        // weights are packed chunk-major: all ops of the classes before this one, then this class's earlier chunks
+        const int b_off = (__ldg(p.table + cls * TAB_STRIDE + 1) + (kc - cls * p.chunks_per_class) * n_ops) * NC * 2;
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)st * stage_bytes;
           const uint32_t bbytes = (uint32_t)n_ops * NC * 32u;
@@ -116,43 +121,43 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
       }
     }
   } else if (warp == 1) {
-    // ===================================================================== MMA issuer
-    uint32_t tcount = 0;
-    int st = 0;
-    uint32_t ph = 0;
-    const uint32_t slab16 = (uint32_t)(p.box_x * p.box_y);           // 16-byte units per z-plane of the box
-    const uint32_t a_lbo = (uint32_t)p.box_z * slab16 * 16u;         // next channel group (8 channels of K)
-    const uint32_t a_sbo = (uint32_t)p.box_x * 16u;                  // next y row (8 rows of M)
-    const uint32_t idesc = umma_idesc_f16(128, NC);
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      const uint32_t buf = tcount & 1;
-      mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
-      tc_fence_after();
-      const uint32_t dcol0 = tbase + buf * buf_cols;
-      int tab_next = __ldg(p.table + lane);
-      for (int kc = 0; kc < p.kc_count; ++kc) {
-        const int tab = tab_next;
-        if (kc + 1 < p.kc_count) tab_next = __ldg(p.table + (kc + 1) * TAB_STRIDE + lane);  // hide the fetch
-        const int n_ops = __shfl_sync(0xffffffffu, tab, 0);
-        mbar_wait(&full[st], ph);
+    // ===================================================================== MMA issuer (ONE thread runs the loop)
+    if (elect_one()) {
+      uint32_t tcount = 0;
+      int st = 0;
+      uint32_t ph = 0;
+      const uint32_t slab16 = (uint32_t)(p.box_x * p.box_y);           // 16-byte units per z-plane of the box
+      const uint32_t a_lbo = (uint32_t)p.box_z * slab16 * 16u;         // next channel group (8 channels of K)
+      const uint64_t a_desc0 = umma_desc(0, a_lbo, (uint32_t)p.box_x * 16u);
+      const uint64_t b_desc0 = umma_desc(0, NC * 16u, 128u);
+      const uint32_t idesc = umma_idesc_f16(128, NC);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount & 1;
+        mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
         tc_fence_after();
-        const uint32_t a0 = smem_u32(smem + (size_t)st * stage_bytes);
-        const uint32_t b0 = a0 + p.a_bytes;
-        for (int z = 0; z < p.zt; ++z) {
+        const uint32_t dcol0 = tbase + buf * buf_cols;
+        for (int kc = 0; kc < p.kc_count; ++kc) {
+          const int32_t* tab = stab + (kc / p.chunks_per_class) * TAB_STRIDE;
+          const int n_ops = tab[0];
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint32_t a0 = smem_u32(smem + (size_t)st * stage_bytes);
+          const uint64_t a_base = a_desc0 + (uint64_t)(a0 >> 4);
+          const uint64_t b_base = b_desc0 + (uint64_t)((a0 + p.a_bytes) >> 4);
           for (int op = 0; op < n_ops; ++op) {
-            const uint32_t a_off = (uint32_t)__shfl_sync(0xffffffffu, tab, 2 + op);
-            const uint64_t ad = umma_desc(a0 + ((uint32_t)z * slab16 + a_off) * 16u, a_lbo, a_sbo);
-            const uint64_t bd = umma_desc(b0 + (uint32_t)op * NC * 32u, NC * 16u, 128u);
-            if (elect_one()) umma_f16(dcol0 + (uint32_t)z * NC, ad, bd, idesc, (kc | op) ? 1u : 0u);
+            const uint64_t ad = a_base + (uint64_t)(uint32_t)tab[2 + op];
+            const uint64_t bd = b_base + (uint64_t)(op * NC * 2);
+            const uint32_t acc = (kc | op) ? 1u : 0u;
+            for (int z = 0; z < p.zt; ++z)
+              umma_f16(dcol0 + (uint32_t)(z * NC), ad + (uint64_t)(z * slab16), bd, idesc, acc);
           }
+          umma_commit(&empty[st]);
+          if (++st == nstage) { st = 0; ph ^= 1; }
         }
-        if (elect_one()) umma_commit(&empty[st]);
-        __syncwarp();
-        if (++st == nstage) { st = 0; ph ^= 1; }
+        umma_commit(&tfull[buf]);
       }
-      if (elect_one()) umma_commit(&tfull[buf]);
-      __syncwarp();
     }
+    __syncwarp();
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;
@@ -308,7 +313,9 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
   // ---- chunk table + packed weights
   const int cpp = cin_padded / 16;                                   // K chunks per phase (or per tensor)
   p.kc_count = kind == TAPS_CONV3_S2 ? 8 * cpp : cpp;
-  std::vector<int32_t> table((size_t)p.kc_count * TAB_STRIDE, 0);
+  p.chunks_per_class = cpp;
+  p.n_classes = p.kc_count / cpp;  // 8 phases for the stride-2 gather, 1 otherwise
+  std::vector<int32_t> table((size_t)p.n_classes * TAB_STRIDE, 0);
   struct Op { int a_off, tap; };
   std::vector<std::vector<Op>> ops(p.kc_count);
   int max_ops = 0;
@@ -336,9 +343,12 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
     } else {
       o.push_back({0, 0});
     }
-    table[(size_t)kc * TAB_STRIDE] = (int)o.size();
-    table[(size_t)kc * TAB_STRIDE + 1] = (int)(total_ops * NC * 2);  // 16-byte units: NC*32 bytes per op
-    for (size_t i = 0; i < o.size(); ++i) table[(size_t)kc * TAB_STRIDE + 2 + i] = o[i].a_off;
+    if (kc % cpp == 0) {
+      const size_t cls = (size_t)(kc / cpp);
+      table[cls * TAB_STRIDE] = (int)o.size();
+      table[cls * TAB_STRIDE + 1] = (int)total_ops;
+      for (size_t i = 0; i < o.size(); ++i) table[cls * TAB_STRIDE + 2 + i] = o[i].a_off;
+    }
     max_ops = std::max(max_ops, (int)o.size());
     total_ops += o.size();
   }
@@ -399,7 +409,7 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
     return nullptr;
   }
   p.stages = stages;
-  pl->smem = (size_t)stages * stage + 256;
+  pl->smem = (size_t)stages * stage + 256 + 8 * TAB_STRIDE * sizeof(int32_t);
   // the attribute is per kernel, not per plan: always opt in to the full 227 KB
   cudaError_t e = NC == 128 ? cudaFuncSetAttribute(conv_taps_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)
                             : cudaFuncSetAttribute(conv_taps_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);

@@ -24,7 +24,7 @@ struct HostTensor {
   std::vector<int64_t> shape;
 };
 
-enum StepKind { STEP_CONV_FOLD, STEP_CONV_TAPS, STEP_CONV_SIMT, STEP_TCONV_TAPS, STEP_TCONV_SIMT };
+enum StepKind { STEP_CONV_FOLD, STEP_CONV_TAPS, STEP_CONV_SIMT, STEP_TCONV_TAPS, STEP_TCONV_SIMT, STEP_CONV_FIRST };
 
 struct ConvStep {  // conv -> (stats) -> norm + lrelu   |   transposed conv
   StepKind kind;
@@ -69,7 +69,8 @@ struct boa_net {
   // head
   float *d_head_w = nullptr, *d_head_b = nullptr;
   ActView head_src;
-  __half* d_patch = nullptr;  // [B][2][P] C8 input
+  __half* d_patch = nullptr;  // [B][2][P] C8 input, or plain fp16 [B][P] when the first layer is the direct kernel
+  bool plain_input = false;
   FwdCall* d_call = nullptr;
   FwdCall* h_call = nullptr;  // pinned
   double* d_stats_all = nullptr;
@@ -172,7 +173,9 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
     }
     return r;
   }
-  if (net->mode == 0 && st.kind == STEP_CONV_FOLD) r = conv_mma_launch(st.fold, s);
+  if (st.kind == STEP_CONV_FIRST)
+    r = launch_conv_first(st.src.base, B, st.d_w, st.d_bias, st.cout, st.raw, st.Do, st.Ho, st.Wo, st.d_stats, s);
+  else if (net->mode == 0 && st.kind == STEP_CONV_FOLD) r = conv_mma_launch(st.fold, s);
   else if (net->mode == 0 && st.kind == STEP_CONV_TAPS) r = conv_taps_launch(st.taps, s);
   else
     r = launch_conv_simt(st.src_plain, B, st.d_w, st.d_bias, st.cin, st.cout, st.ks, st.stride, st.raw, st.Do, st.Ho,
@@ -199,7 +202,8 @@ int run_body(boa_net* net, cudaStream_t s) {
 
 int run_accumulate(boa_net* net, cudaStream_t s) {
   const boa_arch& a = net->arch;
-  if (int r = launch_extract_patches(net->d_call, net->B, a.patch[0], a.patch[1], a.patch[2], net->d_patch, s)) return r;
+  if (int r = launch_extract_patches(net->d_call, net->B, a.patch[0], a.patch[1], a.patch[2], net->d_patch,
+                                     net->plain_input, s)) return r;
   if (int r = run_body(net, s)) return r;
   for (int b = 0; b < net->B; ++b)
     if (int r = launch_head(net->head_src, b, net->d_head_w, net->d_head_b, a.features[0], a.num_classes, nullptr,
@@ -349,6 +353,10 @@ extern "C" int boa_net_finalize(boa_net* net) {
   int layer_idx = 0;
   double macs = 0;
 
+  // first layer: Cin = 1, 3x3x3, stride 1 runs as a direct convolution from a plain fp16 patch (no C8 padding)
+  net->plain_input = a.in_channels == 1 && is3(a.kernels[0], 3) && conv_first_supported(a.features[0]) &&
+                     a.n_conv_enc[0] >= 1;
+  bool first_plain = net->plain_input;
   auto add_conv = [&](const std::string& prefix, ActView src, ActView src_s2d, int cin, int cout, const int* ks,
                       const int* stride, int s_out, ActView dst, __half* s2d_out) -> int {
     ConvStep st;
@@ -381,7 +389,9 @@ extern "C" int boa_net_finalize(boa_net* net) {
     st.kind = STEP_CONV_SIMT;
     st.src = src;
     const int cin_padded = (cin + 15) / 16 * 16;
-    if (is3(ks, 3) && is3(stride, 1) && cout % 32 == 0 && cin_padded <= src.groups * 8) {
+    if (first_plain) {
+      st.kind = STEP_CONV_FIRST;
+    } else if (is3(ks, 3) && is3(stride, 1) && cout % 32 == 0 && cin_padded <= src.groups * 8) {
       st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats);
       if (!st.fold) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_FOLD;
@@ -394,6 +404,7 @@ extern "C" int boa_net_finalize(boa_net* net) {
       st.kind = STEP_CONV_TAPS;
       st.src = src_s2d;
     }
+    first_plain = false;
     net->steps.push_back(st);
     return BOA_OK;
   };
@@ -555,9 +566,12 @@ extern "C" int boa_net_forward_logits(boa_net* net, const float* d_patches, int 
   for (int p0 = 0; p0 < n_patches; p0 += net->B) {
     const int nb = std::min(net->B, n_patches - p0);
     if (nb < net->B) BOA_CUDA(cudaMemsetAsync(net->d_patch, 0, (size_t)net->B * 16 * pv * sizeof(__half), s));
-    if (int r = launch_pack_patches(d_patches + (size_t)p0 * a.in_channels * pv, nb, a.in_channels, a.patch[0],
-                                    a.patch[1], a.patch[2], net->d_patch, 2, s))
+    if (net->plain_input) {
+      if (int r = launch_pack_patches_plain(d_patches + (size_t)p0 * pv, (size_t)nb * pv, net->d_patch, s)) return r;
+    } else if (int r = launch_pack_patches(d_patches + (size_t)p0 * a.in_channels * pv, nb, a.in_channels,
+                                           a.patch[0], a.patch[1], a.patch[2], net->d_patch, 2, s)) {
       return r;
+    }
     if (int r = run_body(net, s)) return r;
     for (int b = 0; b < nb; ++b)
       if (int r = launch_head(net->head_src, b, net->d_head_w, net->d_head_b, a.features[0], a.num_classes,

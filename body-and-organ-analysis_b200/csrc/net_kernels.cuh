@@ -34,7 +34,14 @@ struct FwdCall {
 
 // ---- elementwise / SIMT (net_simt.cu)
 // predict_from_raw_data.py:568-571: cut `data[sl]` -> fp16 C8 with 2 groups (channel 0 = voxel, others 0).
-int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2, __half* d_out_c8_16, cudaStream_t s);
+// plain = true: fp16 [B][p0][p1][p2] for the dedicated first-layer kernel instead of the 16-channel C8 tensor.
+int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2, __half* d_out, bool plain,
+                           cudaStream_t s);
+int launch_pack_patches_plain(const float* d_patches, size_t total, __half* d_out, cudaStream_t s);
+// First encoder conv (Cin = 1, 3x3x3, stride 1): direct FP32 convolution from the plain fp16 patch.
+bool conv_first_supported(int Cout);
+int launch_conv_first(const __half* d_in, int B, const float* d_w, const float* d_bias, int Cout, __half* d_raw_out,
+                      int D, int H, int W, double* d_stats, cudaStream_t s);
 int launch_pack_patches(const float* d_patches, int n, int cin, int p0, int p1, int p2, __half* d_out_c8,
                         int groups, cudaStream_t s);
 int launch_stats_finalize(const double* d_stats, const float* d_gamma, const float* d_beta, int B, int C,

@@ -50,6 +50,131 @@ extract_patches_kernel(const FwdCall* __restrict__ call, int n, int p0, int p1, 
   }
 }
 
+// Plain variant for the dedicated first-layer kernel: fp16 [n][p0][p1][p2].
+__global__ void __launch_bounds__(256)
+extract_patches_plain_kernel(const FwdCall* __restrict__ call, int n, int p0, int p1, int p2,
+                             __half* __restrict__ out) {
+  const float* __restrict__ vol = call->vol;
+  const int d1 = call->d1, d2 = call->d2, n_valid = call->n_valid;
+  const size_t pv = (size_t)p0 * p1 * p2;
+  const size_t total = (size_t)n * pv;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t v = i % pv;
+    const int b = (int)(i / pv);
+    const int bb = b < n_valid ? b : 0;
+    const int k = (int)(v % p2), j = (int)((v / p2) % p1), ii = (int)(v / ((size_t)p2 * p1));
+    const int o0 = call->origins[bb][0], o1 = call->origins[bb][1], o2 = call->origins[bb][2];
+    out[i] = __float2half_rn(__ldg(vol + ((size_t)(o0 + ii) * d1 + (o1 + j)) * d2 + (o2 + k)));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+pack_patches_plain_kernel(const float* __restrict__ in, size_t total, __half* __restrict__ out) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride)
+    out[i] = __float2half_rn(__ldg(in + i));
+}
+
+// ------------------------------------------------------------------------------------------ first layer (Cin = 1)
+// Conv3d(1 -> COUT, 3x3x3, stride 1, pad 1) of the first encoder block.  K = 27 is far too thin for the tensor
+// cores (it would run with K padded to 16 channels = 16x the work); as a direct convolution it is FP32-FMA work of
+// 27*COUT per voxel with a 2-byte read and a 2*COUT-byte write.  One thread = one voxel, all COUT channels in
+// registers; weights [27][COUT] broadcast from shared memory as float4; InstanceNorm sum / sum^2 reduced per block.
+template <int COUT>
+__global__ void __launch_bounds__(256)
+conv_first_kernel(const __half* __restrict__ in, const float* __restrict__ w /*[COUT][27]*/,
+                  const float* __restrict__ bias, uint4* __restrict__ out, double* __restrict__ stats, int D, int H,
+                  int W) {
+  constexpr int ZT = 4;  // voxels per thread along z: each weight vector read from shared memory feeds 4 FMAs
+  __shared__ __align__(16) float sw[27 * COUT];
+  __shared__ float sred[2][8][COUT];
+  for (int i = threadIdx.x; i < 27 * COUT; i += 256) sw[i] = w[(i % COUT) * 27 + i / COUT];
+  __syncthreads();
+  const int zchunks = (D + ZT - 1) / ZT;
+  const int b = blockIdx.z / zchunks, z0 = (blockIdx.z % zchunks) * ZT;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
+  const bool valid = x < W && y < H;
+  const size_t vox = (size_t)D * H * W;
+  const __half* src = in + (size_t)b * vox;
+  float acc[ZT][COUT];
+#pragma unroll
+  for (int j = 0; j < ZT; ++j)
+#pragma unroll
+    for (int c = 0; c < COUT; ++c) acc[j][c] = 0.f;
+  if (valid) {
+#pragma unroll
+    for (int t2 = 0; t2 < 9; ++t2) {
+      const int yi = y + t2 / 3 - 1, xi = x + t2 % 3 - 1;
+      const bool inplane = yi >= 0 && yi < H && xi >= 0 && xi < W;
+      float v[ZT + 2];
+#pragma unroll
+      for (int k = 0; k < ZT + 2; ++k) {
+        const int zi = z0 + k - 1;
+        v[k] = (inplane && zi >= 0 && zi < D) ? __half2float(__ldg(src + ((size_t)zi * H + yi) * W + xi)) : 0.f;
+      }
+#pragma unroll
+      for (int dz = 0; dz < 3; ++dz) {
+        const float4* wr = reinterpret_cast<const float4*>(sw + (dz * 9 + t2) * COUT);
+#pragma unroll
+        for (int q = 0; q < COUT / 4; ++q) {
+          const float4 w4 = wr[q];
+#pragma unroll
+          for (int j = 0; j < ZT; ++j) {
+            acc[j][4 * q] = fmaf(v[j + dz], w4.x, acc[j][4 * q]);
+            acc[j][4 * q + 1] = fmaf(v[j + dz], w4.y, acc[j][4 * q + 1]);
+            acc[j][4 * q + 2] = fmaf(v[j + dz], w4.z, acc[j][4 * q + 2]);
+            acc[j][4 * q + 3] = fmaf(v[j + dz], w4.w, acc[j][4 * q + 3]);
+          }
+        }
+      }
+    }
+  }
+  float s1[COUT], s2[COUT];
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
+  if (valid) {
+#pragma unroll
+    for (int j = 0; j < ZT; ++j) {
+      const int z = z0 + j;
+      if (z < D) {
+        uint4* dst = out + ((size_t)b * (COUT / 8)) * vox + ((size_t)z * H + y) * W + x;
+#pragma unroll
+        for (int g = 0; g < COUT / 8; ++g) {
+          float f[8];
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            f[e] = acc[j][g * 8 + e] + __ldg(bias + g * 8 + e);
+            s1[g * 8 + e] += f[e];
+            s2[g * 8 + e] = fmaf(f[e], f[e], s2[g * 8 + e]);
+          }
+          dst[(size_t)g * vox] = pack8(f);
+        }
+      }
+    }
+  }
+  // block reduction of sum / sum^2 per channel: warp shuffle, then the 8 warps through shared memory
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int c = 0; c < COUT; ++c) {
+    float a1 = s1[c], a2 = s2[c];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) {
+      a1 += __shfl_xor_sync(0xffffffffu, a1, off);
+      a2 += __shfl_xor_sync(0xffffffffu, a2, off);
+    }
+    if (lane == 0) { sred[0][warp][c] = a1; sred[1][warp][c] = a2; }
+  }
+  __syncthreads();
+  if (threadIdx.x < 2 * COUT) {
+    const int which = threadIdx.x / COUT, c = threadIdx.x % COUT;
+    double t = 0;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) t += (double)sred[which][wv][c];
+    atomicAdd(&stats[((size_t)b * COUT + c) * 2 + which], t);
+  }
+}
+
 // Generic: fp32 [n][cin][P] -> C8 with `groups` channel groups (channels >= cin zero).
 __global__ void __launch_bounds__(256)
 pack_patches_kernel(const float* __restrict__ in, int n, int cin, size_t pv, int groups, uint4* __restrict__ out) {
@@ -89,36 +214,51 @@ __global__ void stats_finalize_kernel(const double* __restrict__ stats, const fl
 
 // ------------------------------------------------------------------------------------------ normalise + LeakyReLU
 __global__ void __launch_bounds__(256)
-norm_lrelu_kernel(const uint4* __restrict__ raw, int B, int groups, int D, int H, int W,
-                  const float* __restrict__ scale, const float* __restrict__ shift, float slope,
-                  uint4* __restrict__ dst, int dst_groups_total, int dst_group_off, uint4* __restrict__ s2d) {
+norm_lrelu_kernel(const uint4* __restrict__ raw, int groups, int D, int H, int W, const float* __restrict__ scale,
+                  const float* __restrict__ shift, float slope, uint4* __restrict__ dst, int dst_groups_total,
+                  int dst_group_off, uint4* __restrict__ s2d) {
+  // blockIdx.y = b * groups + g : the 8 scale/shift pairs are loaded once per thread
+  const int bg = blockIdx.y, b = bg / groups, g = bg % groups;
   const size_t vox = (size_t)D * H * W;
-  const size_t total = (size_t)B * groups * vox;
+  float a[8], sh[8];
+  {
+    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)bg * 8));
+    const float4 a1 = __ldg(reinterpret_cast<const float4*>(scale + (size_t)bg * 8) + 1);
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)bg * 8));
+    const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift + (size_t)bg * 8) + 1);
+    a[0] = a0.x; a[1] = a0.y; a[2] = a0.z; a[3] = a0.w; a[4] = a1.x; a[5] = a1.y; a[6] = a1.z; a[7] = a1.w;
+    sh[0] = s0.x; sh[1] = s0.y; sh[2] = s0.z; sh[3] = s0.w; sh[4] = s1.x; sh[5] = s1.y; sh[6] = s1.z; sh[7] = s1.w;
+  }
+  const uint4* __restrict__ src = raw + (size_t)bg * vox;
+  uint4* __restrict__ out = dst ? dst + ((size_t)b * dst_groups_total + dst_group_off + g) * vox : nullptr;
+  uint4* __restrict__ out2 = s2d ? s2d + ((size_t)b * 8 * groups + g) * (vox >> 3) : nullptr;
+  const size_t phase_stride = (size_t)groups * (vox >> 3);
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
-    const size_t v = i % vox;
-    const int g = (int)((i / vox) % groups);
-    const int b = (int)(i / ((size_t)groups * vox));
-    float f[8];
-    unpack8(__ldg(raw + i), f);
-    const float4 a0 = __ldg(reinterpret_cast<const float4*>(scale + ((size_t)b * groups + g) * 8));
-    const float4 a1 = __ldg(reinterpret_cast<const float4*>(scale + ((size_t)b * groups + g) * 8) + 1);
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(shift + ((size_t)b * groups + g) * 8));
-    const float4 s1 = __ldg(reinterpret_cast<const float4*>(shift + ((size_t)b * groups + g) * 8) + 1);
-    const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-    const float s[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+  constexpr int U = 4;
+  for (size_t v0 = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v0 < vox; v0 += U * stride) {
+    uint4 r[U];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      const float z = __fadd_rn(__fmul_rn(f[e], a[e]), s[e]);
-      f[e] = z > 0.f ? z : __fmul_rn(z, slope);
-    }
-    const uint4 o = pack8(f);
-    if (dst) dst[((size_t)b * dst_groups_total + dst_group_off + g) * vox + v] = o;
-    if (s2d) {
-      const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((size_t)W * H));
-      const int ph = ((z & 1) * 2 + (y & 1)) * 2 + (x & 1);
-      const size_t hv = ((size_t)(z >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
-      s2d[(((size_t)b * 8 + ph) * groups + g) * (vox >> 3) + hv] = o;
+    for (int u = 0; u < U; ++u)
+      if (v0 + u * stride < vox) r[u] = __ldcs(src + v0 + u * stride);
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const size_t v = v0 + u * stride;
+      if (v >= vox) break;
+      float f[8];
+      unpack8(r[u], f);
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        const float z = __fadd_rn(__fmul_rn(f[e], a[e]), sh[e]);
+        f[e] = z > 0.f ? z : __fmul_rn(z, slope);
+      }
+      const uint4 o = pack8(f);
+      if (out) out[v] = o;
+      if (out2) {
+        const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((size_t)W * H));
+        const int ph = ((z & 1) * 2 + (y & 1)) * 2 + (x & 1);
+        const size_t hv = ((size_t)(z >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+        out2[(size_t)ph * phase_stride + hv] = o;
+      }
     }
   }
 }
@@ -229,17 +369,19 @@ tconv_simt_kernel(const uint4* __restrict__ in, int in_groups_total, int in_grou
 
 // ------------------------------------------------------------------------------------------ head (+ accumulate)
 // 1x1x1 segmentation head fused with `prediction *= gaussian; predicted_logits[sl] += prediction`
-// (predict_from_raw_data.py:543,609-613).  One thread = one voxel; weights [C][Cin] in shared memory, read as float4
-// broadcasts.  HBM-bound: reads Cin fp16 + RMW of C fp32 per voxel.
+// (predict_from_raw_data.py:543,609-613).  HBM-bound: reads CIN fp16 and read-modify-writes C fp32 per voxel.
+// One thread = one voxel; the RMW runs in batches of 8 classes (8 independent loads in flight per thread);
+// weights [C][CIN] are broadcast from shared memory as float4.
 constexpr int HEAD_MAX_CIN = 64;
 constexpr int HEAD_MAX_C = 128;
+template <int CIN>
 __global__ void __launch_bounds__(256)
 head_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off, int b, int D, int H, int W,
-            const float* __restrict__ w, const float* __restrict__ bias, int Cin, int C,
-            float* __restrict__ logits_b, const FwdCall* __restrict__ call) {
-  extern __shared__ float sw[];  // [C][Cin] then [C] bias
-  float* sb = sw + C * Cin;
-  for (int i = threadIdx.x; i < Cin * C; i += blockDim.x) sw[i] = w[i];
+            const float* __restrict__ w, const float* __restrict__ bias, int C, float* __restrict__ logits_b,
+            const FwdCall* __restrict__ call) {
+  extern __shared__ __align__(16) float sw[];  // [C][CIN] then [C] bias
+  float* sb = sw + C * CIN;
+  for (int i = threadIdx.x; i < CIN * C; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) sb[i] = bias[i];
   __syncthreads();
   float* __restrict__ acc = nullptr;
@@ -255,53 +397,88 @@ head_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off,
   }
   const size_t vox = (size_t)D * H * W;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const int ngroups = Cin / 8;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < vox; v += stride) {
-    float x[HEAD_MAX_CIN];
+    float x[CIN];
 #pragma unroll
-    for (int gi = 0; gi < HEAD_MAX_CIN / 8; ++gi) {
-      if (gi < ngroups) {
-        float f[8];
-        unpack8(__ldg(in + ((size_t)b * in_groups_total + in_group_off + gi) * vox + v), f);
+    for (int gi = 0; gi < CIN / 8; ++gi) {
+      float f[8];
+      unpack8(__ldg(in + ((size_t)b * in_groups_total + in_group_off + gi) * vox + v), f);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) x[gi * 8 + e] = f[e];
-      }
+      for (int e = 0; e < 8; ++e) x[gi * 8 + e] = f[e];
     }
-    size_t av = 0;
+    float* a = nullptr;
     float gw = 0.f;
     if (!logits_b) {
       const int k = (int)(v % W), j = (int)((v / W) % H), ii = (int)(v / ((size_t)W * H));
-      av = ((size_t)(o0 + ii) * d1 + (o1 + j)) * d2 + (o2 + k);
+      a = acc + ((size_t)(o0 + ii) * d1 + (o1 + j)) * d2 + (o2 + k);
       gw = __ldg(g + v);
     }
-    for (int c = 0; c < C; ++c) {
-      const float4* wr = reinterpret_cast<const float4*>(sw + c * Cin);
-      float s = 0.f;
+    for (int c0 = 0; c0 < C; c0 += 8) {
+      float old[8];
+      if (!logits_b) {
 #pragma unroll
-      for (int q = 0; q < HEAD_MAX_CIN / 4; ++q) {
-        if (q * 4 < Cin) {
-          const float4 w4 = wr[q];
-          s = fmaf(x[4 * q], w4.x, s);
-          s = fmaf(x[4 * q + 1], w4.y, s);
-          s = fmaf(x[4 * q + 2], w4.z, s);
-          s = fmaf(x[4 * q + 3], w4.w, s);
-        }
+        for (int u = 0; u < 8; ++u) old[u] = (c0 + u < C) ? a[(size_t)(c0 + u) * vol_voxels] : 0.f;
       }
-      s += sb[c];
-      if (logits_b) {
-        logits_b[(size_t)c * vox + v] = s;
-      } else {
-        float* a = acc + (size_t)c * vol_voxels + av;
-        *a = __fadd_rn(*a, __fmul_rn(s, gw));
+      float sres[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int c = min(c0 + u, C - 1);
+        const float4* wr = reinterpret_cast<const float4*>(sw + c * CIN);
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int q = 0; q < CIN / 4; q += 2) {
+          const float4 w4 = wr[q], w5 = wr[q + 1];
+          s0 = fmaf(x[4 * q], w4.x, s0); s0 = fmaf(x[4 * q + 1], w4.y, s0);
+          s0 = fmaf(x[4 * q + 2], w4.z, s0); s0 = fmaf(x[4 * q + 3], w4.w, s0);
+          s1 = fmaf(x[4 * q + 4], w5.x, s1); s1 = fmaf(x[4 * q + 5], w5.y, s1);
+          s1 = fmaf(x[4 * q + 6], w5.z, s1); s1 = fmaf(x[4 * q + 7], w5.w, s1);
+        }
+        sres[u] = (s0 + s1) + sb[c];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (c0 + u < C) {
+          if (logits_b) logits_b[(size_t)(c0 + u) * vox + v] = sres[u];
+          else a[(size_t)(c0 + u) * vol_voxels] = __fadd_rn(old[u], __fmul_rn(sres[u], gw));
+        }
       }
     }
   }
 }
 
 // ================================================================================================ launchers
-int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2, __half* d_out, cudaStream_t s) {
-  const size_t total = (size_t)B * 2 * p0 * p1 * p2;
-  extract_patches_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_call, B, p0, p1, p2, reinterpret_cast<uint4*>(d_out));
+int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2, __half* d_out, bool plain,
+                           cudaStream_t s) {
+  if (plain) {
+    const size_t total = (size_t)B * p0 * p1 * p2;
+    extract_patches_plain_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_call, B, p0, p1, p2, d_out);
+  } else {
+    const size_t total = (size_t)B * 2 * p0 * p1 * p2;
+    extract_patches_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_call, B, p0, p1, p2, reinterpret_cast<uint4*>(d_out));
+  }
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+int launch_pack_patches_plain(const float* d_patches, size_t total, __half* d_out, cudaStream_t s) {
+  pack_patches_plain_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_patches, total, d_out);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+bool conv_first_supported(int Cout) { return Cout == 32 || Cout == 16 || Cout == 8; }
+
+int launch_conv_first(const __half* d_in, int B, const float* d_w, const float* d_bias, int Cout, __half* d_raw_out,
+                      int D, int H, int W, double* d_stats, cudaStream_t s) {
+  const dim3 grid((W + 31) / 32, (H + 7) / 8, (unsigned)(((D + 3) / 4) * B));
+  uint4* out = reinterpret_cast<uint4*>(d_raw_out);
+  if (Cout == 32) conv_first_kernel<32><<<grid, 256, 0, s>>>(d_in, d_w, d_bias, out, d_stats, D, H, W);
+  else if (Cout == 16) conv_first_kernel<16><<<grid, 256, 0, s>>>(d_in, d_w, d_bias, out, d_stats, D, H, W);
+  else if (Cout == 8) conv_first_kernel<8><<<grid, 256, 0, s>>>(d_in, d_w, d_bias, out, d_stats, D, H, W);
+  else {
+    set_error("conv_first: Cout=%d not instantiated", Cout);
+    return BOA_ERR_UNSUPPORTED;
+  }
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }
@@ -325,9 +502,15 @@ int launch_stats_finalize(const double* d_stats, const float* d_gamma, const flo
 
 int launch_norm_lrelu(const __half* d_raw, int B, int groups, int D, int H, int W, const float* d_scale,
                       const float* d_shift, float slope, const ActView& dst, __half* d_s2d, cudaStream_t s) {
-  const size_t total = (size_t)B * groups * D * H * W;
-  norm_lrelu_kernel<<<grid_for(total, 256), 256, 0, s>>>(
-      reinterpret_cast<const uint4*>(d_raw), B, groups, D, H, W, d_scale, d_shift, slope,
+  const size_t vox = (size_t)D * H * W;
+  const int planes = B * groups;
+  // ~8 resident blocks per SM in total, split over the (b, group) planes; 4 vectors per thread per iteration
+  int bx = (int)((vox + 4 * 256 - 1) / (4 * 256));
+  const int cap = (sm_count() * 8 + planes - 1) / planes;
+  if (bx > cap) bx = cap;
+  if (bx < 1) bx = 1;
+  norm_lrelu_kernel<<<dim3(bx, planes), 256, 0, s>>>(
+      reinterpret_cast<const uint4*>(d_raw), groups, D, H, W, d_scale, d_shift, slope,
       reinterpret_cast<uint4*>(dst.base), dst.groups_total, dst.group_off, reinterpret_cast<uint4*>(d_s2d));
   BOA_CHECK_LAUNCH();
   return BOA_OK;
@@ -364,9 +547,25 @@ int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias
   }
   const size_t vox = src.voxels();
   const size_t smem = ((size_t)C * Cin + C) * sizeof(float);
-  head_kernel<<<grid_for(vox, 256, 4), 256, smem, s>>>(reinterpret_cast<const uint4*>(src.base), src.groups_total,
-                                                       src.group_off, b, src.D, src.H, src.W, d_w, d_bias, Cin, C,
-                                                       d_logits_b, d_call);
+  const uint4* in = reinterpret_cast<const uint4*>(src.base);
+  const int grid = grid_for(vox, 256, 8);
+#define BOA_HEAD(CIN_)                                                                                              \
+  head_kernel<CIN_><<<grid, 256, smem, s>>>(in, src.groups_total, src.group_off, b, src.D, src.H, src.W, d_w, d_bias, \
+                                            C, d_logits_b, d_call)
+  switch (Cin) {
+    case 8: BOA_HEAD(8); break;
+    case 16: BOA_HEAD(16); break;
+    case 24: BOA_HEAD(24); break;
+    case 32: BOA_HEAD(32); break;
+    case 40: BOA_HEAD(40); break;
+    case 48: BOA_HEAD(48); break;
+    case 56: BOA_HEAD(56); break;
+    case 64: BOA_HEAD(64); break;
+    default:
+      set_error("head: Cin=%d not instantiated", Cin);
+      return BOA_ERR_UNSUPPORTED;
+  }
+#undef BOA_HEAD
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }

@@ -1,0 +1,56 @@
+"""Label tables of the reference (exported by tools/export_class_maps.py from
+_external/totalsegmentator/map_to_binary.py) and the LUTs derived from them."""
+from __future__ import annotations
+
+import json
+import os
+from functools import lru_cache
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "class_maps.json")
+
+TOTAL_TASK_IDS = [291, 292, 293, 294, 295]           # totalsegmentator/python_api.py:182-189
+BODY_REGIONS_TASK_ID, BODY_PARTS_TASK_ID = 542, 543  # body_composition_analysis/tasks.py:15-48
+
+# body_composition_analysis/body_regions/definition.py, body_parts/definition.py, tissue/definition.py
+BODY_REGION = {"SUBCUTANEOUS_TISSUE": 1, "MUSCLE": 2, "ABDOMINAL_CAVITY": 3, "THORACIC_CAVITY": 4, "BONE": 5,
+               "GLANDS": 6, "PERICARDIUM": 7, "BREAST_IMPLANT": 8, "MEDIASTINUM": 9, "BRAIN": 10, "NERVOUS_SYSTEM": 11}
+BODY_PART_TORSO = 1
+TISSUES = {"MUSCLE": 1, "BONE": 2, "SAT": 3, "VAT": 4, "IMAT": 5, "PAT": 6, "EAT": 7}
+
+
+@lru_cache(maxsize=1)
+def tables() -> dict:
+    with open(_DATA) as f:
+        return json.load(f)
+
+
+def class_map(task: str) -> dict[int, str]:
+    return {int(k): v for k, v in tables()["class_map_all_keys"][task].items()}
+
+
+def part_luts() -> list[list[int]]:
+    """For each of the five `total` part models: LUT part-class index -> global `total` label
+    (totalsegmentator/nnunet.py:534-556: class_map_inv[class_map_5_parts[part][jdx]])."""
+    t = tables()
+    inv = {v: int(k) for k, v in t["class_map"]["total"].items()}
+    luts = []
+    for tid in TOTAL_TASK_IDS:
+        part = t["class_map_5_parts"][t["map_taskid_to_partname_ct"][str(tid)]]
+        lut = [0] * (len(part) + 1)
+        for jdx, name in part.items():
+            lut[int(jdx)] = inv[name]
+        luts.append(lut)
+    return luts
+
+
+def measurement_label_map(model_name: str) -> dict[str, int]:
+    """compute/measurements.py:290-294: every `<task>_<name>` key of the complete reverse class map that starts with
+    the model name (and not `<model>_v2`), stripped of `<model>_` - in class_map definition order."""
+    t = tables()
+    out = {}
+    for task in t["class_map_order"]:
+        for idx, name in t["class_map_all_keys"][task].items():
+            key = f"{task}_{name}"
+            if key.startswith(model_name) and not key.startswith(model_name + "_v2"):
+                out[key[len(model_name) + 1:]] = int(idx)
+    return out

@@ -1,0 +1,152 @@
+"""`total-measurements.json` numerics on the GPU: drop-in for compute_measurements / metrics_for_each_region / ct_pfav /
+autochthon_reference (compute/measurements.py:22-343).
+
+One pass over (CT, label map) builds a per-label integer-HU histogram (boa_label_hu_hist); every statistic the
+reference computes per label with boolean masks, gathers and sorts - count, mean, std, min, median, max, 25th / 75th
+percentile, the lung-fat-window subsets and the label unions - is an exact function of those histograms, evaluated on
+the host in float64 (a few KB).  The autochthon reference and the optional CNR adjustment need an eroded mask:
+label-set mask -> 6^3 box erosion -> histogram, all on the device.
+"""
+from __future__ import annotations
+
+from typing import Any
+
+import numpy as np
+import torch
+
+from . import passes
+from .labels import measurement_label_map
+
+ADIPOSE_TISSUE = (-200, -40)
+CNR_ADJUSTED_REGIONS = {"total": {"aorta", "autochthon_left", "autochthon_right"},
+                        "heartchambers_highres": {"pulmonary_artery"}}
+LUNG_MASKS = ["lung_upper_lobe_left", "lung_lower_lobe_left", "lung_upper_lobe_right", "lung_middle_lobe_right",
+              "lung_lower_lobe_right"]
+HU_MIN, N_BINS = -32768, 65536  # the whole int16 range: no voxel can fall outside
+
+
+def _order_stat(cum, values, k):
+    return float(values[np.searchsorted(cum, k, side="right")])
+
+
+def _percentile(cum, values, n, q):
+    pos = (n - 1) * q / 100.0  # numpy method="linear"
+    lo, hi = int(np.floor(pos)), int(np.ceil(pos))
+    a, b = _order_stat(cum, values, lo), _order_stat(cum, values, hi)
+    t = pos - lo
+    return float(b - (b - a) * (1 - t)) if t >= 0.5 else float(a + (b - a) * t)
+
+
+def metrics_from_hist(hist: np.ndarray, hu_min: int, autochthon_mean, autochthon_std, img_spacing,
+                      cnr_none: bool = False) -> dict[str, Any]:
+    """metrics_for_region (measurements.py:74-123) from hist[i] = #voxels with HU == hu_min + i."""
+    hist = hist.astype(np.int64)
+    n = int(hist.sum())
+    if n == 0:
+        return {"present": False}
+    nz = np.nonzero(hist)[0]
+    lo, hi = int(nz[0]), int(nz[-1]) + 1
+    h = hist[lo:hi]
+    values = np.arange(hu_min + lo, hu_min + hi, dtype=np.int64)
+    cum = np.cumsum(h)
+    mean = float(int((h * values).sum()) / n)
+    var = float((h * (values - mean) ** 2).sum() / n)
+    m: dict[str, Any] = {"present": True}
+    m["volume_ml"] = n * (np.prod(img_spacing) / 1000.0)
+    m["mean_hu"] = mean
+    m["std_hu"] = float(np.sqrt(var))
+    m["min_hu"] = float(values[0])
+    m["median_hu"] = _percentile(cum, values, n, 50)
+    m["max_hu"] = float(values[-1])
+    for p in (25, 75):
+        m[f"{p}th_percentile_hu"] = _percentile(cum, values, n, p)
+    if autochthon_mean is not None and autochthon_std is not None and not cnr_none:
+        m["cnr"] = (mean - autochthon_mean) / autochthon_std
+    else:
+        m["cnr"] = None
+    return m
+
+
+def _window(hist_row: np.ndarray, lo: int, hi: int) -> np.ndarray:
+    out = np.zeros_like(hist_row)
+    out[lo - HU_MIN:hi - HU_MIN + 1] = hist_row[lo - HU_MIN:hi - HU_MIN + 1]
+    return out
+
+
+def _masked_hist(ct: torch.Tensor, mask: torch.Tensor) -> np.ndarray:
+    hist, _ = passes.label_hu_hist(ct, mask, 2, HU_MIN, N_BINS)
+    return hist[1].cpu().numpy().view(np.uint32)
+
+
+def _eroded_region_hist(ct, labels, ids, minus_fat: bool) -> np.ndarray:
+    mask = passes.label_set_mask(labels, ids, ct, ADIPOSE_TISSUE[0], ADIPOSE_TISSUE[1], 2 if minus_fat else 0)
+    return _masked_hist(ct, passes.erode_box(mask, 3, 2))
+
+
+def compute_measurements_on_device(ct: torch.Tensor, segmentations: dict[str, torch.Tensor], spacing,
+                                   cnr_adjustment: bool = False, return_ct_pfav_mask: bool = False):
+    """ct int16 [z,y,x] on the device; segmentations: model name -> uint8 label map (same shape); spacing as
+    SimpleITK's GetSpacing().  Returns the dict compute_measurements returns (+ the ct_pfav mask tensor on request)."""
+    measurements: dict[str, Any] = {"segmentations": {}, "info": {}}
+    pfav_mask = None
+    if not segmentations:
+        return (measurements, None) if return_ct_pfav_mask else measurements
+    if ct.dtype != torch.int16:
+        raise TypeError("compute_measurements_on_device needs an int16 CT (exact integer-HU histograms)")
+    aut_mean = aut_std = None
+    for model_name in sorted(segmentations, key=lambda m: m != "total"):
+        labels = segmentations[model_name]
+        if labels.shape != ct.shape:
+            raise ValueError("The spacing of the image and of the segmentation should be the same")
+        label_map = measurement_label_map(model_name)
+        n_labels = max(label_map.values()) + 1
+        hist_dev, _ = passes.label_hu_hist(ct, labels, n_labels, HU_MIN, N_BINS)
+        hist = hist_dev.cpu().numpy().view(np.uint32)
+        if model_name == "total":
+            ids = [label_map["autochthon_right"], label_map["autochthon_left"]]
+            h = _eroded_region_hist(ct, labels, ids, minus_fat=True)
+            if h.sum() > 0:
+                ref = metrics_from_hist(h, HU_MIN, None, None, spacing)
+                aut_mean, aut_std = ref["mean_hu"], ref["std_hu"]
+        res = {}
+        for region, label in label_map.items():
+            res[region] = metrics_from_hist(hist[label], HU_MIN, aut_mean, aut_std, spacing)
+        if "autochthon_left" in label_map and "autochthon_right" in label_map:
+            union = hist[label_map["autochthon_left"]].astype(np.int64) + hist[label_map["autochthon_right"]]
+            res["autochthon"] = metrics_from_hist(union, HU_MIN, aut_mean, aut_std, spacing)
+        if model_name == "total":
+            def lung(names):
+                u = np.zeros(N_BINS, dtype=np.int64)
+                for nme in names:
+                    u += _window(hist[label_map[nme]], *ADIPOSE_TISSUE)
+                return metrics_from_hist(u, HU_MIN, aut_mean, aut_std, spacing)
+            for nme in LUNG_MASKS:
+                res["ct_pfav_" + nme] = lung([nme])
+            for side in ("left", "right"):
+                res[f"ct_pfav_lobe_{side}"] = lung([ll for ll in LUNG_MASKS if ll.endswith(side)])
+            res["ct_pfav_lungs"] = lung(LUNG_MASKS)
+            if return_ct_pfav_mask:
+                pfav_mask = passes.label_set_mask(labels, [label_map[ll] for ll in LUNG_MASKS], ct,
+                                                  ADIPOSE_TISSUE[0], ADIPOSE_TISSUE[1], 1)
+        measurements["segmentations"][model_name] = res
+        if cnr_adjustment and model_name in CNR_ADJUSTED_REGIONS and aut_mean is not None and aut_std is not None:
+            adj = {}
+            sel = {r: v for r, v in label_map.items() if r in CNR_ADJUSTED_REGIONS[model_name]}
+            for region, label in sel.items():
+                if hist[label].sum() == 0:
+                    adj[region] = {"present": False}
+                    continue
+                h = _eroded_region_hist(ct, labels, [label], minus_fat="autochthon" in region)
+                adj[region] = metrics_from_hist(h, HU_MIN, aut_mean, aut_std, spacing,
+                                                cnr_none=region.partition("_")[0] == "autochthon")
+            if "autochthon_left" in sel and "autochthon_right" in sel:
+                ids = [sel["autochthon_left"], sel["autochthon_right"]]
+                if sum(int(hist[i].sum()) for i in ids) == 0:
+                    adj["autochthon"] = {"present": False}
+                else:
+                    h = _eroded_region_hist(ct, labels, ids, minus_fat=True)
+                    adj["autochthon"] = metrics_from_hist(h, HU_MIN, aut_mean, aut_std, spacing, cnr_none=True)
+            measurements.setdefault("cnr_adjusted", {}).update(adj)
+    measurements["info"]["autochthon_mean"] = aut_mean
+    measurements["info"]["autochthon_std"] = aut_std
+    return (measurements, pfav_mask) if return_ct_pfav_mask else measurements

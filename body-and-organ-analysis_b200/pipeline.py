@@ -1,0 +1,249 @@
+"""Volume-level pipeline on the device: preprocessing -> sliding-window networks -> label maps -> tissue map ->
+measurement tables.  Host mirror of the per-volume work of
+
+  nnUNet_predict_image            (_external/totalsegmentator/nnunet.py:326-829; `total` = 5 part models merged by LUT)
+  DefaultPreprocessor.run_case_npy (_external/nnunetv2/preprocessing/preprocessors/default_preprocessor.py:45-118:
+                                    crop_to_nonzero -> CTNormalization -> resample)
+  export_prediction (un-crop)      (_external/nnunetv2/inference/export_prediction.py:45-47)
+  body_composition_analysis.inference / run_pipeline (infer/infer.py:39-89, commands.py:84-170)
+  compute_all_models               (compute/inference.py:50-143)
+
+The CT goes to the device once (int16, 2 bytes / voxel); label maps come back as uint8 and the measurement tables as a
+few KB.  Logits never leave HBM.
+"""
+from __future__ import annotations
+
+import os
+from dataclasses import dataclass, field
+
+import numpy as np
+import torch
+
+from . import bca, passes
+from .geometry import shard_patches, sliding_window_origins
+from .labels import BODY_PARTS_TASK_ID, BODY_REGIONS_TASK_ID, TOTAL_TASK_IDS, part_luts
+from .measurements import compute_measurements_on_device
+from .plans import find_model_folder, load_model_folder
+from .predictor import finalize_argmax, nnUNetPredictor, weight_sum
+
+TRAINERS = {**{t: "nnUNetTrainerNoMirroring" for t in TOTAL_TASK_IDS},
+            BODY_REGIONS_TASK_ID: "nnUNetTrainerNoMirroring",
+            BODY_PARTS_TASK_ID: "nnUNetTrainer_1500epochs_NoMirroring"}
+
+
+class ModelZoo:
+    """Networks stay resident across tasks and volumes (the reference reloads every checkpoint for every volume,
+    predict_from_raw_data.py:86-118); networks of one geometry share one activation workspace."""
+
+    def __init__(self, weights_root: str | None = None, device=None, max_batch: int | None = None):
+        self._specs = None
+        self.root = weights_root or os.environ.get("TOTALSEG_WEIGHTS_PATH") or os.environ.get("nnUNet_results")
+        if not self.root:
+            raise RuntimeError("no weights directory: pass weights_root or set TOTALSEG_WEIGHTS_PATH")
+        self.device, self.max_batch = device, max_batch
+        self._cache: dict = {}
+        self._donor: nnUNetPredictor | None = None
+
+    @classmethod
+    def from_specs(cls, specs: dict, device=None, max_batch: int | None = None) -> "ModelZoo":
+        """In-memory zoo: task id -> ModelSpec holding ALL folds of that task (synthetic weights, tests, bench)."""
+        zoo = cls.__new__(cls)
+        zoo.root, zoo.device, zoo.max_batch = None, device, max_batch
+        zoo._cache, zoo._donor, zoo._specs = {}, None, specs
+        return zoo
+
+    def get(self, task_id: int, folds, step_size: float) -> nnUNetPredictor:
+        key = (task_id, tuple(folds), step_size)
+        if key not in self._cache:
+            p = nnUNetPredictor(tile_step_size=step_size, use_gaussian=True, use_mirroring=False,
+                                perform_everything_on_device=True, device=self.device, max_batch=self.max_batch,
+                                workspace_donor=self._donor)
+            if getattr(self, "_specs", None) is not None:
+                import copy
+                spec = copy.copy(self._specs[task_id])
+                spec.fold_weights = [self._specs[task_id].fold_weights[int(f)] for f in folds]
+                p.manual_initialization(spec)
+            else:
+                p.initialize_from_trained_model_folder(find_model_folder(self.root, task_id, TRAINERS[task_id]), folds)
+            self._donor = self._donor or p
+            self._cache[key] = p
+        return self._cache[key]
+
+
+def nonzero_bbox(vol: torch.Tensor):
+    """crop_to_nonzero (nnunetv2/preprocessing/cropping/cropping.py:6-39): bounding box of data != 0 (filling holes
+    does not change a bounding box)."""
+    nz = vol != 0
+    box = []
+    for ax in range(3):
+        other = tuple(a for a in range(3) if a != ax)
+        idx = torch.nonzero(nz.any(dim=other)).flatten()
+        if idx.numel() == 0:
+            return [(0, s) for s in vol.shape]
+        box.append((int(idx[0]), int(idx[-1]) + 1))
+    return box
+
+
+@dataclass
+class DistContext:
+    """One process per GPU; patches of a volume are split into count-balanced contiguous runs."""
+    rank: int = 0
+    world_size: int = 1
+    group: object = None
+
+
+def _exchange_accumulators(acc: torch.Tensor, dist_ctx: DistContext) -> None:
+    """The single exchange step per model: sum the per-rank partial logits accumulators (NCCL all-reduce over NVLink;
+    integer tables need no exchange because every rank then holds the full label map)."""
+    import torch.distributed as dist
+    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=dist_ctx.group)
+
+
+def predict_labels_sharded(pred: nnUNetPredictor, data: torch.Tensor, lut=None, label_inout=None,
+                           overwrite_nonzero_only=False, dist_ctx: DistContext | None = None) -> torch.Tensor:
+    if dist_ctx is None or dist_ctx.world_size == 1:
+        return pred.predict_labels(data, lut, label_inout, overwrite_nonzero_only)
+    with torch.cuda.device(pred.device_index):
+        vol, origins, unpad = pred._prepare(data)
+        b, e = shard_patches(len(origins), dist_ctx.world_size, dist_ctx.rank)
+        acc = torch.zeros((pred.num_classes, *vol.shape), dtype=torch.float32, device=pred.device)
+        if e > b:
+            pred.accumulate(vol, origins[b:e], acc)
+        _exchange_accumulators(acc, dist_ctx)
+        w = weight_sum(vol.shape, pred.patch_size, origins, pred.gaussian())
+        lab = finalize_argmax(acc, w, lut)[unpad].contiguous()
+        if label_inout is None:
+            return lab
+        if overwrite_nonzero_only:
+            nz = lab != 0
+            label_inout[nz] = lab[nz]
+        else:
+            label_inout.copy_(lab)
+        return label_inout
+
+
+def _preprocess(ct: torch.Tensor, spec) -> tuple[torch.Tensor, list]:
+    """crop_to_nonzero -> CTNormalization (fp32).  Returns the [1, z, y, x] network input and the crop box."""
+    box = nonzero_bbox(ct)
+    crop = ct[box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]].contiguous()
+    p = spec.intensity
+    norm = passes.ct_normalize(crop, float(p["percentile_00_5"]), float(p["percentile_99_5"]), float(p["mean"]),
+                               float(p["std"]))
+    return norm[None], box
+
+
+def segment_task(ct: torch.Tensor, zoo: ModelZoo, task_ids, folds, step_size: float, luts=None,
+                 dist_ctx: DistContext | None = None) -> torch.Tensor:
+    """One nnUNet_predict_image call on a volume that is already at the task's spacing: uint8 label map [z,y,x]."""
+    out = torch.zeros(ct.shape, dtype=torch.uint8, device=ct.device)
+    multi = len(task_ids) > 1
+    for i, tid in enumerate(task_ids):
+        pred = zoo.get(tid, folds, step_size)
+        data, box = _preprocess(ct, pred.spec)
+        sl = tuple(slice(b, e) for b, e in box)
+        full = all(b == 0 and e == s for (b, e), s in zip(box, ct.shape))
+        lut = luts[i] if luts is not None else None
+        if full:
+            predict_labels_sharded(pred, data, lut, out, overwrite_nonzero_only=multi, dist_ctx=dist_ctx)
+        else:
+            lab = predict_labels_sharded(pred, data, lut, dist_ctx=dist_ctx)
+            if multi:
+                view = out[sl]
+                nz = lab != 0
+                view[nz] = lab[nz]
+            else:
+                out[sl] = lab
+    return out
+
+
+def segment_total(ct: torch.Tensor, zoo: ModelZoo, dist_ctx: DistContext | None = None) -> torch.Tensor:
+    """task `total`, 1.5 mm: 5 part models, fold 0, step 0.8, merged through the part -> global LUTs
+    (totalsegmentator/python_api.py:182-189, nnunet.py:507-559)."""
+    return segment_task(ct, zoo, TOTAL_TASK_IDS, [0], 0.8, part_luts(), dist_ctx)
+
+
+def segment_bca_net(ct_5mm: torch.Tensor, zoo: ModelZoo, task: str, fast: bool,
+                    dist_ctx: DistContext | None = None) -> torch.Tensor:
+    tid = BODY_PARTS_TASK_ID if task == "body_parts" else BODY_REGIONS_TASK_ID
+    folds = [0] if fast else [0, 1, 2, 3, 4]  # body_composition_analysis/tasks.py:15-48
+    return segment_task(ct_5mm, zoo, [tid], folds, 0.5, None, dist_ctx)
+
+
+@dataclass
+class VolumeResult:
+    total: torch.Tensor | None = None
+    body_parts: torch.Tensor | None = None
+    body_regions: torch.Tensor | None = None
+    tissues: torch.Tensor | None = None
+    ct_pfav: torch.Tensor | None = None
+    total_measurements: dict | None = None
+    bca_measurements: dict | None = None
+    vertebrae: dict | None = None
+    timings: dict = field(default_factory=dict)
+
+
+def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total", "bca"), fast_bca: bool = False,
+                   cnr_adjustment: bool = False, dist_ctx: DistContext | None = None) -> VolumeResult:
+    """compute_all_models + run_pipeline numerics for one CT already on the device (int16 [z,y,x]).
+
+    spacing_zyx: voxel spacing of the array axes.  `total` expects 1.5 mm (resampling is identity there,
+    totalsegmentator/resampling.py:179-181); the BCA nets run at 5 mm slice thickness (resample_only_thickness)."""
+    from .resample import resample_thickness, upsample_labels_nearest
+
+    res = VolumeResult()
+    models = set(models)
+    if "bca" in models:
+        models.add("total")  # compute/config.py:54-55
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    marks = [("start", ev())]
+    marks[-1][1].record()
+
+    def mark(name):
+        e = ev()
+        e.record()
+        marks.append((name, e))
+
+    if "total" in models:
+        if not np.allclose(spacing_zyx, 1.5):
+            raise NotImplementedError("`total` needs a 1.5 mm volume: 3-D cubic resampling is not on the GPU path yet")
+        res.total = segment_total(ct, zoo, dist_ctx)
+        mark("total_nets")
+        sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
+        res.total_measurements, res.ct_pfav = compute_measurements_on_device(
+            ct, {"total": res.total}, sx_sy_sz, cnr_adjustment, return_ct_pfav_mask=True)
+        mark("total_measurements")
+    if "bca" in models or "body_parts" in models or "body_regions" in models:
+        ct5 = resample_thickness(ct, spacing_zyx[0], 5.0)
+        mark("resample")
+        want_parts = "bca" in models or "body_parts" in models
+        want_regions = "bca" in models or "body_regions" in models
+        if want_parts:
+            res.body_parts = upsample_labels_nearest(segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx), ct.shape[0])
+        if want_regions:
+            res.body_regions = upsample_labels_nearest(segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx), ct.shape[0])
+        mark("bca_nets")
+    if "bca" in models:
+        res.tissues = bca.subclassify_tissues(ct, res.body_regions)
+        sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
+        res.bca_measurements, res.vertebrae, _ = bca.build_bca_measurements(
+            ct, res.tissues, res.body_parts, res.body_regions, res.total, sx_sy_sz)
+        mark("bca_measurements")
+    torch.cuda.synchronize()
+    for (n0, e0), (n1, e1) in zip(marks, marks[1:]):
+        res.timings[n1] = e0.elapsed_time(e1) / 1e3
+    return res
+
+
+def analyze_from_host(ct_host: torch.Tensor, spacing_zyx, zoo: ModelZoo, device=None, **kw) -> dict:
+    """The call a user of the Python API makes for one CT held in (pinned) host memory: H2D of the int16 volume,
+    all networks and passes on the device, D2H of the uint8 label maps; returns host tensors + measurement dicts."""
+    dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    ct = ct_host.to(dev, non_blocking=True)
+    res = analyze_volume(ct, spacing_zyx, zoo, **kw)
+    out = {"total_measurements": res.total_measurements, "bca_measurements": res.bca_measurements,
+           "vertebrae": res.vertebrae, "timings": res.timings}
+    for name in ("total", "body_parts", "body_regions", "tissues", "ct_pfav"):
+        t = getattr(res, name)
+        out[name] = t.to("cpu", non_blocking=True) if t is not None else None
+    torch.cuda.synchronize(dev)
+    return out

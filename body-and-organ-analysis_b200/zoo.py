@@ -163,3 +163,24 @@ def synthetic_ct(shape, seed: int = 0) -> np.ndarray:
     sigma = np.where(vol > 500, 150.0, np.where(vol < -500, 50.0, 18.0)).astype(np.float32)
     vol = vol + sigma * rng.standard_normal(shape, dtype=np.float32)
     return np.clip(np.rint(vol), -1024, 2047).astype(np.int16)
+
+
+def synthetic_specs(patch=(128, 128, 128), base=32, max_features=320, n_stages=6, bca_folds=5, seed: int = 0,
+                    datasets=None) -> dict:
+    """In-memory ModelSpecs (no disk round trip) for ModelZoo.from_specs: same geometry and seeds as write_zoo."""
+    from .plans import ModelSpec, arch_from_plans
+
+    out = {}
+    for did, (name, trainer, ncls) in DATASETS.items():
+        if datasets is not None and did not in datasets:
+            continue
+        spacing = (1.5, 1.5, 1.5) if did < 500 else (5.0, 1.5, 1.5)
+        plans = default_plans(patch, base, max_features, n_stages, spacing, name)
+        arch = arch_from_plans(plans, "3d_fullres", 1, ncls)
+        nf = 1 if did < 500 else bca_folds
+        weights = [random_state_dict(arch, seed * 1000 + did * 10 + f) for f in range(nf)]
+        out[did] = ModelSpec(arch=arch, intensity=plans["foreground_intensity_properties_per_channel"]["0"],
+                             labels={"background": 0, **{f"class_{i}": i for i in range(1, ncls)}},
+                             transpose_forward=[0, 1, 2], transpose_backward=[0, 1, 2], spacing=list(spacing),
+                             configuration="3d_fullres", fold_weights=weights, folder="<synthetic>")
+    return out

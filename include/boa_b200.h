@@ -164,6 +164,15 @@ int boa_mask_label_minus_window(const void* d_ct, int ct_dtype, const uint8_t* d
 int boa_erode_box(const uint8_t* d_mask, const int32_t* shape, int before, int after, uint8_t* d_tmp, uint8_t* d_out,
                   void* stream);
 
+/* Slice-thickness resampling of the body-composition path (resample_only_thickness,
+ * _external/totalsegmentator/nnunet.py:457-475; scipy.ndimage.zoom(order=3, mode="nearest") with zoom (z, 1, 1),
+ * _external/totalsegmentator/resampling.py:24-56): interpolating cubic B-spline along the outermost axis in fp64,
+ * truncated toward zero like `astype(np.int32)`.  d_scratch: double [(z_in + 24) * plane].  plane = d1 * d2. */
+int boa_resample_z_cubic(const void* d_in, int in_dtype, int z_in, size_t plane, int z_out, double* d_scratch,
+                         int16_t* d_out, void* stream);
+/* Order-0 zoom of a label map along the outermost axis back to the input grid (nnunet.py:685-687). */
+int boa_resample_z_nearest_u8(const uint8_t* d_in, int z_in, size_t plane, int z_out, uint8_t* d_out, void* stream);
+
 /* Multi-GPU exchange, device side: d_dst[i] += d_src[i] (fp32, round-to-nearest, fixed order chosen by the caller). */
 int boa_add_slab(float* d_dst, const float* d_src, size_t n, void* stream);
 

@@ -67,6 +67,8 @@ def install():
                     m.Environment = lambda **k: None
                     m.FileSystemLoader = lambda *a, **k: None
                     m.select_autoescape = lambda *a, **k: None
+                if name == "weasyprint":
+                    m.HTML = object
                 if name == "nibabel":
                     m.Nifti1Image = object
                     m.spatialimages = types.SimpleNamespace(SpatialImage=object)

@@ -1,0 +1,120 @@
+"""CPU: the oracle restatement against golden vectors produced by the REFERENCE's own functions
+(tests/golden/make_golden.py), and the product's host logic against both."""
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _close(a, b, path=""):
+    if isinstance(a, dict):
+        assert isinstance(b, dict) and list(a.keys()) == list(b.keys()), f"{path}: keys differ {list(a)[:5]} vs {list(b)[:5]}"
+        for k in a:
+            _close(a[k], b[k], f"{path}/{k}")
+    elif isinstance(a, (list, tuple)):
+        assert len(a) == len(b), path
+        for i, (x, y) in enumerate(zip(a, b)):
+            _close(x, y, f"{path}[{i}]")
+    elif a is None or isinstance(a, (bool, str)):
+        assert a == b, f"{path}: {a!r} != {b!r}"
+    else:
+        assert b is not None, f"{path}: {a} vs None"
+        assert np.isclose(float(a), float(b), rtol=1e-11, atol=1e-11), f"{path}: {a} != {b}"
+
+
+def test_sliding_window_steps_match_reference():
+    from boa_b200.geometry import compute_steps_for_sliding_window as prod_steps, sliding_window_origins
+    from oracle.sliding_window import compute_steps_for_sliding_window as orc_steps, sliding_window_slicers
+    doc = json.load(open(os.path.join(G, "geometry.json")))
+    for c in doc["steps"]:
+        assert orc_steps(c["image"], c["patch"], c["step"]) == c["steps"]
+        assert prod_steps(c["image"], c["patch"], c["step"]) == c["steps"]
+        origins = sliding_window_origins(c["image"], c["patch"], c["step"])
+        sl = sliding_window_slicers(c["image"], c["patch"], c["step"])
+        assert [tuple(int(s.start) for s in t) for t in sl] == [tuple(map(int, o)) for o in origins]
+    # the counts BASELINE.md quotes
+    assert len(sliding_window_origins((512, 512, 512), (128,) * 3, 0.8)) == 125
+    assert len(sliding_window_origins((300, 512, 512), (128,) * 3, 0.8)) == 75
+    assert len(sliding_window_origins((154, 512, 512), (128,) * 3, 0.5)) == 98
+
+
+def test_gaussian_matches_reference():
+    from boa_b200.geometry import compute_gaussian as prod_g
+    from oracle.sliding_window import compute_gaussian as orc_g
+    z = np.load(os.path.join(G, "gaussian.npz"))
+    for key in z.files:
+        tile = tuple(int(t) for t in key.split("x"))
+        assert np.array_equal(orc_g(tile, 1.0 / 8, 10), z[key])
+        assert np.array_equal(prod_g(tile, 1.0 / 8, 10.0), z[key])
+    doc = json.load(open(os.path.join(G, "geometry.json")))["gaussian128"]
+    g = prod_g((128, 128, 128))
+    assert hashlib.sha256(g.tobytes()).hexdigest() == doc["sha256"]
+    assert float(g.max()) == doc["max"] == 10.0 and float(g.min()) == doc["min"]
+
+
+def test_ct_normalization_matches_reference():
+    from oracle.passes import ct_normalize
+    z = np.load(os.path.join(G, "ct_norm.npz"))
+    props = json.loads(str(z["props"]))
+    assert np.array_equal(ct_normalize(z["x"], props), z["y"])
+
+
+def test_tissue_rules_match_reference():
+    from oracle.passes import subclassify_tissues
+    z = np.load(os.path.join(G, "tissue.npz"))
+    assert np.array_equal(subclassify_tissues(z["ct"], z["regions"]), z["tissues"])
+
+
+def test_total_measurements_match_reference():
+    from oracle.report import compute_measurements
+    z = np.load(os.path.join(G, "phantom.npz"))
+    gold = json.load(open(os.path.join(G, "measurements.json")))
+    got = compute_measurements(z["ct"], z["total"], tuple(z["spacing"]), cnr_adjustment=True)
+    assert np.array_equal(got.pop("_ct_pfav_mask"), z["ct_pfav"])
+    assert len(gold["segmentations"]["total"]) == 304
+    _close(gold, got)
+
+
+def test_bca_report_matches_reference():
+    from oracle.report import bca_json
+    z = np.load(os.path.join(G, "phantom.npz"))
+    zb = np.load(os.path.join(G, "phantom_bca.npz"))
+    gold = json.load(open(os.path.join(G, "bca.json")))
+    js, vert = bca_json(z["ct"], zb["tissues"], z["parts"], z["regions"], z["total"], tuple(zb["spacing"]))
+    _close(gold["json"], js)
+    assert {k: list(v) for k, v in vert.items()} == gold["vertebrae"]
+
+
+def test_product_host_statistics_match_reference():
+    """The product's host side (histogram -> metrics, slice tables -> report) fed with oracle-computed tables."""
+    from boa_b200 import bca as pbca
+    from boa_b200.measurements import HU_MIN, N_BINS, metrics_from_hist
+    from oracle import passes as op
+    z = np.load(os.path.join(G, "phantom.npz"))
+    zb = np.load(os.path.join(G, "phantom_bca.npz"))
+    gold = json.load(open(os.path.join(G, "measurements.json")))
+    ct, total = z["ct"], z["total"]
+    am, asd = gold["info"]["autochthon_mean"], gold["info"]["autochthon_std"]
+    from boa_b200.labels import measurement_label_map
+    lm = measurement_label_map("total")
+    assert list(lm.keys()) == [k for k in gold["segmentations"]["total"] if not k.startswith("ct_pfav") and k != "autochthon"]
+    for region, label in list(lm.items())[::7]:
+        h = np.bincount(ct[total == label].astype(np.int64) - HU_MIN, minlength=N_BINS)
+        _close(gold["segmentations"]["total"][region], metrics_from_hist(h, HU_MIN, am, asd, tuple(z["spacing"])), region)
+    # report from tables
+    sp = tuple(zb["spacing"])
+    tc, th = op.slice_label_stats(zb["tissues"], 8, ct)
+    tct, tht = op.slice_label_stats(zb["tissues"], 8, ct, z["parts"], 1)
+    rc, _ = op.slice_label_stats(z["regions"], 12)
+    oc, _ = op.slice_label_stats(total, 118)
+    t = pbca.slice_tables_from_arrays(ct.shape[0], tc, th, tct, tht, rc, oc)
+    js, vert, _ = pbca.build_bca_measurements(None, None, None, None, None, sp, tables=t)
+    goldb = json.load(open(os.path.join(G, "bca.json")))
+    _close(goldb["json"], js)
+    assert {k: list(v) for k, v in vert.items()} == goldb["vertebrae"]
+    ex = pbca.AggregatableBodyPart(goldb["body_part"])
+    assert pbca.secondary_findings(t, ex, float(np.prod(sp) / 1000.0)) == goldb["other_findings"]
