@@ -18,6 +18,7 @@
 //     16 input channels; TMEM accumulators double-buffered when zt*NC <= 256.
 #include <vector>
 #include "net_kernels.cuh"
+#include "conv_epilogue.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -35,6 +36,7 @@ struct ConvMmaParams {
   int B, kc_count, Cout, D, H, W, zt;
   int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
   int in_groups_total, in_group_off;
+  int ntaps;  // 9: (dy,dx) taps as address shifts; 1: the in-plane taps already sit on K (first layer), centre only
 };
 
 __device__ __forceinline__ void decode_tile(int t, const ConvMmaParams& p, int& nt, int& b, int& tz, int& ty,
@@ -53,7 +55,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
   const int zb = p.zt + 2;
   const uint32_t a_bytes = 2u * zb * SLAB * 16u;
   constexpr uint32_t b_group = 96u * NC;  // [2 kchunks][3*NC rows][16 B]
-  constexpr uint32_t b_bytes = 9u * b_group;
+  const uint32_t b_bytes = (uint32_t)p.ntaps * b_group;
   const uint32_t stage_bytes = a_bytes + b_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
   uint64_t* full = bars;        // [2] TMA -> MMA
@@ -131,7 +133,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
             const int lo = max(0, i - 2), hi = min(p.zt - 1, i);
             const int jlo = lo - (i - 2);         // first valid dz block (blocks are ordered dz = 2,1,0)
             const int n = hi - lo + 1;
-            const uint64_t ad = a_base + (uint64_t)(i * SLAB);
+            const uint64_t ad = a_base + (uint64_t)(i * SLAB + (p.ntaps == 1 ? XB + 1 : 0));
             const uint64_t bd = b_base + (uint64_t)(jlo * NC);
             const uint32_t dcol = dcol0 + (uint32_t)(lo * NC);
             const uint32_t idesc = umma_idesc_f16(128, (uint32_t)(n * NC));
@@ -142,9 +144,11 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
             } else {
               umma_f16(dcol, ad, bd, idesc, 1u);
             }
+            if (p.ntaps == 9) {
 #pragma unroll
-            for (int g = 1; g < 9; ++g)
-              umma_f16(dcol, ad + (uint64_t)((g / 3) * XB + (g % 3)), bd + (uint64_t)(g * BG16), idesc, 1u);
+              for (int g = 1; g < 9; ++g)
+                umma_f16(dcol, ad + (uint64_t)((g / 3) * XB + (g % 3)), bd + (uint64_t)(g * BG16), idesc, 1u);
+            }
           }
           umma_commit(&empty[st]);   // smem stage reusable once these MMAs retire
         }
@@ -158,6 +162,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
     const int row = q * 32 + lane;
     uint32_t tcount = 0;
     const int out_groups = p.Cout / 8;
+    RunningStats run[NC / 32];
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       int nt, b, tz, ty, tx;
       decode_tile(tile, p, nt, b, tz, ty, tx);
@@ -168,66 +173,21 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
       const int x = tx * TILE_X + (row & 7), y = ty * TILE_Y + (row >> 3);
       const bool rowvalid = (x < p.W) && (y < p.H);
       const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(p.zt * NC);
-#pragma unroll 1
+      const size_t zstride = (size_t)p.H * p.W, gstride = (size_t)p.D * zstride;
+#pragma unroll
       for (int chunk = 0; chunk < NC / 32; ++chunk) {
         const int cbase = nt * NC + chunk * 32;
-        float s1[32], s2[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
-        float bs[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) bs[c] = __ldg(p.bias + cbase + c);
-#pragma unroll 1
-        for (int slot = 0; slot < p.zt; ++slot) {
-          const int z = tz * p.zt + slot;
-          uint32_t v[32];
-          tmem_ld32(tlane + slot * NC + chunk * 32, v);
-          tmem_ld_wait();
-          if (z < p.D && rowvalid) {
-            float f[32];
-#pragma unroll
-            for (int c = 0; c < 32; ++c) {
-              f[c] = __uint_as_float(v[c]) + bs[c];
-              s1[c] += f[c];
-              s2[c] = fmaf(f[c], f[c], s2[c]);
-            }
-            uint4* dst = reinterpret_cast<uint4*>(p.out) +
-                         ((((size_t)b * out_groups + (cbase >> 3)) * p.D + z) * p.H + y) * p.W + x;
-            const size_t gstride = (size_t)p.D * p.H * p.W;
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              uint4 o;
-              __half2* h = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-              for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
-              dst[j * gstride] = o;
-            }
-          }
-        }
-        // transpose-reduce over the 32 lanes: afterwards lane l holds the warp total of channel cbase + l
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) {
-          const bool upper = (lane & off) != 0;
-#pragma unroll
-          for (int k = 0; k < off; ++k) {
-            const float send1 = upper ? s1[k] : s1[k + off];
-            const float send2 = upper ? s2[k] : s2[k + off];
-            const float r1 = __shfl_xor_sync(0xffffffffu, send1, off);
-            const float r2 = __shfl_xor_sync(0xffffffffu, send2, off);
-            s1[k] = (upper ? s1[k + off] : s1[k]) + r1;
-            s2[k] = (upper ? s2[k + off] : s2[k]) + r2;
-          }
-        }
-        if (p.stats) {
-          double* st = p.stats + ((size_t)b * p.Cout + cbase + lane) * 2;
-          atomicAdd(st, (double)s1[0]);
-          atomicAdd(st + 1, (double)s2[0]);
-        }
+        uint4* dst = reinterpret_cast<uint4*>(p.out) +
+                     ((((size_t)b * out_groups + (cbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
+        conv_epilogue_strip(tlane + chunk * 32, NC, p.zt, p.bias + cbase, rowvalid, tz * p.zt, p.D, dst, zstride, gstride,
+                            lane, b * p.Cout + cbase, run[chunk], p.stats);
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
+#pragma unroll
+    for (int chunk = 0; chunk < NC / 32; ++chunk) stats_flush(run[chunk], p.stats, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -247,7 +207,11 @@ struct ConvMmaPlan {
 };
 
 ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin_w, int cin_padded, int Cout,
-                                  const ActView& src, int B, __half* d_raw_out, double* d_stats) {
+                                  const ActView& src, int B, __half* d_raw_out, double* d_stats, bool taps_on_k) {
+  // taps_on_k (first layer, Cin = 1): the source tensor carries the 9 in-plane neighbours of every voxel as its
+  // channels 0..8, h_w is [Cout][1][27]; only the dz taps remain as (folded) taps.
+  const int ntaps = taps_on_k ? 1 : 9;
+  if (taps_on_k) { cin_w = 9; cin_padded = 16; }
   if (cin_padded % 16 || Cout % 32 || cin_padded > src.groups * 8) {
     set_error("conv_mma: unsupported channels cin=%d(padded %d) cout=%d src groups=%d", cin_w, cin_padded, Cout,
               src.groups);
@@ -270,16 +234,17 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_z * B * p.n_ntiles;
   p.in_groups_total = src.groups_total; p.in_group_off = src.group_off;
   p.out = d_raw_out; p.stats = d_stats;
-  pl->macs = 27.0 * cin_w * Cout * (double)src.voxels() * B;
+  p.ntaps = ntaps;
+  pl->macs = 27.0 * (taps_on_k ? 1 : cin_w) * Cout * (double)src.voxels() * B;
 
   // pack weights: [nt][kc][g=(dy,dx)][kchunk][n = j*NC + co, j <-> dz = 2-j][8 cin]
   const size_t b_group = 96 * (size_t)NC / 2;  // halves
-  std::vector<__half> hb((size_t)p.n_ntiles * p.kc_count * 9 * b_group);
+  std::vector<__half> hb((size_t)p.n_ntiles * p.kc_count * ntaps * b_group);
   for (int nt = 0; nt < p.n_ntiles; ++nt)
     for (int kc = 0; kc < p.kc_count; ++kc)
-      for (int g = 0; g < 9; ++g) {
+      for (int g = 0; g < ntaps; ++g) {
         const int dy = g / 3, dx = g % 3;
-        __half* blk = hb.data() + (((size_t)nt * p.kc_count + kc) * 9 + g) * b_group;
+        __half* blk = hb.data() + (((size_t)nt * p.kc_count + kc) * ntaps + g) * b_group;
         for (int kch = 0; kch < 2; ++kch)
           for (int j = 0; j < 3; ++j)
             for (int co = 0; co < NC; ++co)
@@ -287,7 +252,9 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
                 const int ci = kc * 16 + kch * 8 + e;
                 const int dz = 2 - j;
                 float v = 0.f;
-                if (ci < cin_w) v = h_w[((size_t)(nt * NC + co) * cin_w + ci) * 27 + dz * 9 + dy * 3 + dx];
+                if (ci < cin_w)
+                  v = taps_on_k ? h_w[(size_t)(nt * NC + co) * 27 + dz * 9 + (ci == 0 ? 4 : (ci <= 4 ? ci - 1 : ci))]
+                                : h_w[((size_t)(nt * NC + co) * cin_w + ci) * 27 + dz * 9 + dy * 3 + dx];
                 blk[((size_t)kch * 3 * NC + j * NC + co) * 8 + e] = __float2half_rn(v);
               }
       }
@@ -306,7 +273,7 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
     conv_mma_plan_destroy(pl);
     return nullptr;
   }
-  const size_t stage = 2 * (size_t)(zt + 2) * SLAB * 16 + 9 * 96 * (size_t)NC;
+  const size_t stage = 2 * (size_t)(zt + 2) * SLAB * 16 + (size_t)ntaps * 96 * (size_t)NC;
   pl->smem = 2 * stage + 128;
   cudaError_t e = NC == 64 ? cudaFuncSetAttribute(conv3_fold_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)
                            : cudaFuncSetAttribute(conv3_fold_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);

@@ -18,6 +18,7 @@
 // columns per output z-plane of the tile, double buffered.
 #include <vector>
 #include "net_kernels.cuh"
+#include "conv_epilogue.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
@@ -163,6 +164,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
     const int q = warp & 3;
     const int row = q * 32 + lane;
     uint32_t tcount = 0;
+    RunningStats run[NC / 32];
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       int nt, b, tz, ty, tx;
       taps_decode_tile(tile, p, nt, b, tz, ty, tx);
@@ -172,94 +174,42 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
       const int x = tx * TT_X + (row & 7), y = ty * TT_Y + (row >> 3);
       const bool rowvalid = (x < p.W) && (y < p.H);
       const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + buf * buf_cols;
-#pragma unroll 1
+#pragma unroll
       for (int chunk = 0; chunk < NC / 32; ++chunk) {
         const int nbase = nt * NC + chunk * 32;  // first GEMM column of this 32-wide strip
-        float bs[32];
-#pragma unroll
-        for (int c = 0; c < 32; ++c) bs[c] = __ldg(p.bias + (nbase + c) % p.Cout);
         if (p.kind != TAPS_TCONV2) {
-          float s1[32], s2[32];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) { s1[c] = 0.f; s2[c] = 0.f; }
-          const int out_groups = p.Cout / 8;
-          const size_t gstride = (size_t)p.D * p.H * p.W;
-#pragma unroll 1
-          for (int slot = 0; slot < p.zt; ++slot) {
-            const int z = tz * p.zt + slot;
-            uint32_t v[32];
-            tmem_ld32(tlane + slot * NC + chunk * 32, v);
-            tmem_ld_wait();
-            if (z < p.D && rowvalid) {
-              float f[32];
-#pragma unroll
-              for (int c = 0; c < 32; ++c) {
-                f[c] = __uint_as_float(v[c]) + bs[c];
-                s1[c] += f[c];
-                s2[c] = fmaf(f[c], f[c], s2[c]);
-              }
-              uint4* dst = reinterpret_cast<uint4*>(p.out) +
-                           ((((size_t)b * out_groups + (nbase >> 3)) * p.D + z) * p.H + y) * p.W + x;
-#pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                uint4 o;
-                __half2* h = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-                for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
-                dst[j * gstride] = o;
-              }
-            }
-          }
-#pragma unroll
-          for (int off = 16; off >= 1; off >>= 1) {
-            const bool upper = (lane & off) != 0;
-#pragma unroll
-            for (int k = 0; k < off; ++k) {
-              const float send1 = upper ? s1[k] : s1[k + off];
-              const float send2 = upper ? s2[k] : s2[k + off];
-              const float r1 = __shfl_xor_sync(0xffffffffu, send1, off);
-              const float r2 = __shfl_xor_sync(0xffffffffu, send2, off);
-              s1[k] = (upper ? s1[k + off] : s1[k]) + r1;
-              s2[k] = (upper ? s2[k + off] : s2[k]) + r2;
-            }
-          }
-          if (p.stats) {
-            double* st = p.stats + ((size_t)b * p.Cout + nbase + lane) * 2;
-            atomicAdd(st, (double)s1[0]);
-            atomicAdd(st + 1, (double)s2[0]);
-          }
+          const size_t zstride = (size_t)p.H * p.W, gstride = (size_t)p.D * zstride;
+          uint4* dst = reinterpret_cast<uint4*>(p.out) +
+                       ((((size_t)b * (p.Cout / 8) + (nbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
+          conv_epilogue_strip(tlane + chunk * 32, NC, p.zt, p.bias + nbase, rowvalid, tz * p.zt, p.D, dst, zstride,
+                              gstride, lane, b * p.Cout + nbase, run[chunk], p.stats);
         } else {
-          // transposed conv: column n = phase * Cout + co ; scatter to (2z+pz, 2y+py, 2x+px)
+          // transposed conv: GEMM column n = (((pz*2+py) * Cout/8 + cg) * 2 + px) * 8 + e : the two x-phases of a
+          // channel group are neighbours on N, so a thread writes 32 contiguous bytes (xo = 2x, 2x+1) per group
           const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
-#pragma unroll 1
-          for (int slot = 0; slot < p.zt; ++slot) {
-            const int z = tz * p.zt + slot;
-            uint32_t v[32];
-            tmem_ld32(tlane + slot * NC + chunk * 32, v);
-            tmem_ld_wait();
-            if (z < p.D && rowvalid) {
+          const int cgroups = p.Cout / 8;
+          float bs[32];
 #pragma unroll
-              for (int j = 0; j < 4; ++j) {
-                const int n = nbase + 8 * j;
-                const int phs = n / p.Cout, co = n % p.Cout;
-                const int zo = 2 * z + (phs >> 2), yo = 2 * y + ((phs >> 1) & 1), xo = 2 * x + (phs & 1);
-                uint4 o;
-                __half2* h = reinterpret_cast<__half2*>(&o);
+          for (int c = 0; c < 32; ++c) bs[c] = __ldg(p.bias + (((nbase + c) >> 4) % cgroups) * 8 + (c & 7));
+          uint4* d[2];
 #pragma unroll
-                for (int e = 0; e < 4; ++e)
-                  h[e] = __floats2half2_rn(__uint_as_float(v[8 * j + 2 * e]) + bs[8 * j + 2 * e],
-                                           __uint_as_float(v[8 * j + 2 * e + 1]) + bs[8 * j + 2 * e + 1]);
-                reinterpret_cast<uint4*>(p.out)[((((size_t)b * p.out_groups_total + p.out_group_off + (co >> 3)) * Do +
-                                                  zo) * Ho + yo) * Wo + xo] = o;
-              }
-            }
+          for (int jj = 0; jj < 2; ++jj) {
+            const int n = nbase + 16 * jj;
+            const int cg = (n >> 4) % cgroups, pzpy = n / (2 * p.Cout);
+            const int zo = 2 * (tz * p.zt) + (pzpy >> 1), yo = 2 * y + (pzpy & 1);
+            d[jj] = reinterpret_cast<uint4*>(p.out) +
+                    ((((size_t)b * p.out_groups_total + p.out_group_off + cg) * Do + zo) * Ho + yo) * Wo + 2 * x;
           }
+          tconv_epilogue_strip(tlane + chunk * 32, NC, p.zt, bs, rowvalid, tz * p.zt, p.D, d[0], d[1],
+                               (size_t)2 * Ho * Wo);
         }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&tempty[buf]);
     }
+#pragma unroll
+    for (int chunk = 0; chunk < NC / 32; ++chunk) stats_flush(run[chunk], p.stats, lane);
   }
   tc_fence_before();
   __syncthreads();
@@ -370,7 +320,8 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
               float v = 0.f;
               if (ci < cin_w) {
                 if (kind == TAPS_TCONV2) {
-                  const int phs = ng / Cout, co = ng % Cout;
+                  const int px = (ng >> 3) & 1, cg = (ng >> 4) % (Cout / 8), pzpy = ng / (2 * Cout);
+                  const int phs = pzpy * 2 + px, co = cg * 8 + (ng & 7);
                   v = h_w[((size_t)ci * Cout + co) * 8 + phs];
                 } else {
                   v = h_w[((size_t)ng * cin_w + ci) * 27 + op.tap];

@@ -70,7 +70,7 @@ struct boa_net {
   float *d_head_w = nullptr, *d_head_b = nullptr;
   ActView head_src;
   __half* d_patch = nullptr;  // [B][2][P] C8 input, or plain fp16 [B][P] when the first layer is the direct kernel
-  bool plain_input = false;
+  int input_mode = 0;  // 0: C8 16ch, 1: plain fp16 (direct first layer), 2: C8 with the 9 in-plane neighbours on K
   FwdCall* d_call = nullptr;
   FwdCall* h_call = nullptr;  // pinned
   double* d_stats_all = nullptr;
@@ -203,7 +203,7 @@ int run_body(boa_net* net, cudaStream_t s) {
 int run_accumulate(boa_net* net, cudaStream_t s) {
   const boa_arch& a = net->arch;
   if (int r = launch_extract_patches(net->d_call, net->B, a.patch[0], a.patch[1], a.patch[2], net->d_patch,
-                                     net->plain_input, s)) return r;
+                                     net->input_mode, s)) return r;
   if (int r = run_body(net, s)) return r;
   for (int b = 0; b < net->B; ++b)
     if (int r = launch_head(net->head_src, b, net->d_head_w, net->d_head_b, a.features[0], a.num_classes, nullptr,
@@ -354,9 +354,12 @@ extern "C" int boa_net_finalize(boa_net* net) {
   double macs = 0;
 
   // first layer: Cin = 1, 3x3x3, stride 1 runs as a direct convolution from a plain fp16 patch (no C8 padding)
-  net->plain_input = a.in_channels == 1 && is3(a.kernels[0], 3) && conv_first_supported(a.features[0]) &&
-                     a.n_conv_enc[0] >= 1;
-  bool first_plain = net->plain_input;
+  // first layer (Cin = 1, 3x3x3): on the tensor cores with the 9 in-plane taps moved onto K (K = 16, three folded
+  // dz taps) when Cout % 32 == 0, else the direct FP32 kernel from a plain fp16 patch
+  const bool first33 = a.in_channels == 1 && is3(a.kernels[0], 3) && a.n_conv_enc[0] >= 1;
+  net->input_mode = (first33 && a.features[0] % 32 == 0) ? 2 : (first33 && conv_first_supported(a.features[0]) ? 1 : 0);
+  bool first_plain = net->input_mode == 1;
+  bool first_nb9 = net->input_mode == 2;
   auto add_conv = [&](const std::string& prefix, ActView src, ActView src_s2d, int cin, int cout, const int* ks,
                       const int* stride, int s_out, ActView dst, __half* s2d_out) -> int {
     ConvStep st;
@@ -391,6 +394,10 @@ extern "C" int boa_net_finalize(boa_net* net) {
     const int cin_padded = (cin + 15) / 16 * 16;
     if (first_plain) {
       st.kind = STEP_CONV_FIRST;
+    } else if (first_nb9) {
+      st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats, true);
+      if (!st.fold) return BOA_ERR_CUDA;
+      st.kind = STEP_CONV_FOLD;
     } else if (is3(ks, 3) && is3(stride, 1) && cout % 32 == 0 && cin_padded <= src.groups * 8) {
       st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats);
       if (!st.fold) return BOA_ERR_CUDA;
@@ -405,6 +412,7 @@ extern "C" int boa_net_finalize(boa_net* net) {
       st.src = src_s2d;
     }
     first_plain = false;
+    first_nb9 = false;
     net->steps.push_back(st);
     return BOA_OK;
   };
@@ -566,7 +574,11 @@ extern "C" int boa_net_forward_logits(boa_net* net, const float* d_patches, int 
   for (int p0 = 0; p0 < n_patches; p0 += net->B) {
     const int nb = std::min(net->B, n_patches - p0);
     if (nb < net->B) BOA_CUDA(cudaMemsetAsync(net->d_patch, 0, (size_t)net->B * 16 * pv * sizeof(__half), s));
-    if (net->plain_input) {
+    if (net->input_mode == 2) {
+      if (int r = launch_pack_patches_nb9(d_patches + (size_t)p0 * pv, nb, a.patch[0], a.patch[1], a.patch[2],
+                                          net->d_patch, s))
+        return r;
+    } else if (net->input_mode == 1) {
       if (int r = launch_pack_patches_plain(d_patches + (size_t)p0 * pv, (size_t)nb * pv, net->d_patch, s)) return r;
     } else if (int r = launch_pack_patches(d_patches + (size_t)p0 * a.in_channels * pv, nb, a.in_channels,
                                            a.patch[0], a.patch[1], a.patch[2], net->d_patch, 2, s)) {

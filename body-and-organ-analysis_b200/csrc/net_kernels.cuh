@@ -34,10 +34,13 @@ struct FwdCall {
 
 // ---- elementwise / SIMT (net_simt.cu)
 // predict_from_raw_data.py:568-571: cut `data[sl]` -> fp16 C8 with 2 groups (channel 0 = voxel, others 0).
-// plain = true: fp16 [B][p0][p1][p2] for the dedicated first-layer kernel instead of the 16-channel C8 tensor.
-int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2, __half* d_out, bool plain,
+// mode 0: 16-channel C8 tensor, channel 0 = voxel.  mode 1: plain fp16 [B][p0][p1][p2] (direct first-layer kernel).
+// mode 2: 16-channel C8 tensor whose channels 0..8 are the 9 in-plane (dy,dx) neighbours of the voxel, zero outside
+//         the PATCH (first layer on the tensor cores with the in-plane taps on K).
+int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2, __half* d_out, int mode,
                            cudaStream_t s);
 int launch_pack_patches_plain(const float* d_patches, size_t total, __half* d_out, cudaStream_t s);
+int launch_pack_patches_nb9(const float* d_patches, int n, int p0, int p1, int p2, __half* d_out, cudaStream_t s);
 // First encoder conv (Cin = 1, 3x3x3, stride 1): direct FP32 convolution from the plain fp16 patch.
 bool conv_first_supported(int Cout);
 int launch_conv_first(const __half* d_in, int B, const float* d_w, const float* d_bias, int Cout, __half* d_raw_out,
@@ -69,7 +72,7 @@ int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias
 struct ConvMmaPlan;
 ConvMmaPlan* conv_mma_plan_create(const float* h_w /*[Cout][Cin_w][27] fp32*/, const float* h_bias, int cin_w,
                                   int cin_padded, int Cout, const ActView& src, int B, __half* d_raw_out,
-                                  double* d_stats);
+                                  double* d_stats, bool taps_on_k = false);
 void conv_mma_plan_destroy(ConvMmaPlan* p);
 int conv_mma_launch(ConvMmaPlan* p, cudaStream_t s);
 

@@ -50,6 +50,46 @@ extract_patches_kernel(const FwdCall* __restrict__ call, int n, int p0, int p1, 
   }
 }
 
+// Neighbour variant: C8 with 2 groups whose channels 0..8 are the in-plane neighbours of the voxel (channel 0 = the
+// voxel, 1..4 = taps 0..3, 5..8 = taps 5..8 with tap = dy*3+dx), zero
+// outside the patch (the conv's zero padding is relative to the patch).  src == nullptr: cut from the volume.
+__global__ void __launch_bounds__(256)
+extract_patches_nb9_kernel(const FwdCall* __restrict__ call, const float* __restrict__ src, int n, int p0, int p1,
+                           int p2, uint4* __restrict__ out) {
+  const size_t pv = (size_t)p0 * p1 * p2;
+  const size_t total = (size_t)n * pv;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const float* vol = src ? src : call->vol;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t v = i % pv;
+    const int b = (int)(i / pv);
+    const int k = (int)(v % p2), j = (int)((v / p2) % p1), ii = (int)(v / ((size_t)p2 * p1));
+    size_t base;
+    size_t sy, sz;
+    if (src) {
+      base = (size_t)b * pv; sy = (size_t)p2; sz = (size_t)p2 * p1;
+    } else {
+      const int bb = b < call->n_valid ? b : 0;
+      sy = (size_t)call->d2; sz = (size_t)call->d2 * call->d1;
+      base = (size_t)call->origins[bb][0] * sz + (size_t)call->origins[bb][1] * sy + (size_t)call->origins[bb][2];
+    }
+    float f[16];
+#pragma unroll
+    for (int t = 0; t < 16; ++t) f[t] = 0.f;
+#pragma unroll
+    for (int c = 0; c < 9; ++c) {
+      const int t = c == 0 ? 4 : (c <= 4 ? c - 1 : c);  // channel 0 = the voxel itself (what the SIMT cross-check reads)
+      const int jj = j + t / 3 - 1, kk = k + t % 3 - 1;
+      if (jj >= 0 && jj < p1 && kk >= 0 && kk < p2) f[c] = __ldg(vol + base + (size_t)ii * sz + (size_t)jj * sy + kk);
+    }
+    float lo[8], hi[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { lo[e] = f[e]; hi[e] = f[8 + e]; }
+    out[((size_t)b * 2) * pv + v] = pack8(lo);
+    out[((size_t)b * 2 + 1) * pv + v] = pack8(hi);
+  }
+}
+
 // Plain variant for the dedicated first-layer kernel: fp16 [n][p0][p1][p2].
 __global__ void __launch_bounds__(256)
 extract_patches_plain_kernel(const FwdCall* __restrict__ call, int n, int p0, int p1, int p2,
@@ -413,33 +453,30 @@ head_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off,
       a = acc + ((size_t)(o0 + ii) * d1 + (o1 + j)) * d2 + (o2 + k);
       gw = __ldg(g + v);
     }
-    for (int c0 = 0; c0 < C; c0 += 8) {
-      float old[8];
+    // batches of up to 32 classes: issue every accumulator load first, hide their latency behind the dot products
+    for (int c0 = 0; c0 < C; c0 += 32) {
+      float old[32];
       if (!logits_b) {
 #pragma unroll
-        for (int u = 0; u < 8; ++u) old[u] = (c0 + u < C) ? a[(size_t)(c0 + u) * vol_voxels] : 0.f;
-      }
-      float sres[8];
-#pragma unroll
-      for (int u = 0; u < 8; ++u) {
-        const int c = min(c0 + u, C - 1);
-        const float4* wr = reinterpret_cast<const float4*>(sw + c * CIN);
-        float s0 = 0.f, s1 = 0.f;
-#pragma unroll
-        for (int q = 0; q < CIN / 4; q += 2) {
-          const float4 w4 = wr[q], w5 = wr[q + 1];
-          s0 = fmaf(x[4 * q], w4.x, s0); s0 = fmaf(x[4 * q + 1], w4.y, s0);
-          s0 = fmaf(x[4 * q + 2], w4.z, s0); s0 = fmaf(x[4 * q + 3], w4.w, s0);
-          s1 = fmaf(x[4 * q + 4], w5.x, s1); s1 = fmaf(x[4 * q + 5], w5.y, s1);
-          s1 = fmaf(x[4 * q + 6], w5.z, s1); s1 = fmaf(x[4 * q + 7], w5.w, s1);
-        }
-        sres[u] = (s0 + s1) + sb[c];
+        for (int u = 0; u < 32; ++u)
+          if (c0 + u < C) old[u] = __ldcg(a + (size_t)(c0 + u) * vol_voxels);
       }
 #pragma unroll
-      for (int u = 0; u < 8; ++u) {
+      for (int u = 0; u < 32; ++u) {
         if (c0 + u < C) {
-          if (logits_b) logits_b[(size_t)(c0 + u) * vox + v] = sres[u];
-          else a[(size_t)(c0 + u) * vol_voxels] = __fadd_rn(old[u], __fmul_rn(sres[u], gw));
+          const float4* wr = reinterpret_cast<const float4*>(sw + (c0 + u) * CIN);
+          float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+          for (int q = 0; q < CIN / 4; q += 2) {
+            const float4 w4 = wr[q], w5 = wr[q + 1];
+            s0 = fmaf(x[4 * q], w4.x, s0); s0 = fmaf(x[4 * q + 1], w4.y, s0);
+            s0 = fmaf(x[4 * q + 2], w4.z, s0); s0 = fmaf(x[4 * q + 3], w4.w, s0);
+            s1 = fmaf(x[4 * q + 4], w5.x, s1); s1 = fmaf(x[4 * q + 5], w5.y, s1);
+            s1 = fmaf(x[4 * q + 6], w5.z, s1); s1 = fmaf(x[4 * q + 7], w5.w, s1);
+          }
+          const float sres = (s0 + s1) + sb[c0 + u];
+          if (logits_b) logits_b[(size_t)(c0 + u) * vox + v] = sres;
+          else __stcg(a + (size_t)(c0 + u) * vol_voxels, __fadd_rn(old[u], __fmul_rn(sres, gw)));
         }
       }
     }
@@ -447,9 +484,21 @@ head_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off,
 }
 
 // ================================================================================================ launchers
-int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2, __half* d_out, bool plain,
+int launch_pack_patches_nb9(const float* d_patches, int n, int p0, int p1, int p2, __half* d_out, cudaStream_t s) {
+  const size_t total = (size_t)n * p0 * p1 * p2;
+  extract_patches_nb9_kernel<<<grid_for(total, 256), 256, 0, s>>>(nullptr, d_patches, n, p0, p1, p2,
+                                                                  reinterpret_cast<uint4*>(d_out));
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2, __half* d_out, int mode,
                            cudaStream_t s) {
-  if (plain) {
+  if (mode == 2) {
+    const size_t total = (size_t)B * p0 * p1 * p2;
+    extract_patches_nb9_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_call, nullptr, B, p0, p1, p2,
+                                                                    reinterpret_cast<uint4*>(d_out));
+  } else if (mode == 1) {
     const size_t total = (size_t)B * p0 * p1 * p2;
     extract_patches_plain_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_call, B, p0, p1, p2, d_out);
   } else {

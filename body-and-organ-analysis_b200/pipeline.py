@@ -20,7 +20,7 @@ import numpy as np
 import torch
 
 from . import bca, passes
-from .geometry import shard_patches, sliding_window_origins
+from .dist import DistContext, exchange_slabs, gather_label_slabs, plan_shards
 from .labels import BODY_PARTS_TASK_ID, BODY_REGIONS_TASK_ID, TOTAL_TASK_IDS, part_luts
 from .measurements import compute_measurements_on_device
 from .plans import find_model_folder, load_model_folder
@@ -84,39 +84,31 @@ def nonzero_bbox(vol: torch.Tensor):
     return box
 
 
-@dataclass
-class DistContext:
-    """One process per GPU; patches of a volume are split into count-balanced contiguous runs."""
-    rank: int = 0
-    world_size: int = 1
-    group: object = None
-
-
-def _exchange_accumulators(acc: torch.Tensor, dist_ctx: DistContext) -> None:
-    """The single exchange step per model: sum the per-rank partial logits accumulators (NCCL all-reduce over NVLink;
-    integer tables need no exchange because every rank then holds the full label map)."""
-    import torch.distributed as dist
-    dist.all_reduce(acc, op=dist.ReduceOp.SUM, group=dist_ctx.group)
-
-
 def predict_labels_sharded(pred: nnUNetPredictor, data: torch.Tensor, lut=None, label_inout=None,
                            overwrite_nonzero_only=False, dist_ctx: DistContext | None = None) -> torch.Tensor:
+    """predict_labels with the patches of the volume sharded over the ranks of dist_ctx (see dist.py)."""
     if dist_ctx is None or dist_ctx.world_size == 1:
         return pred.predict_labels(data, lut, label_inout, overwrite_nonzero_only)
     with torch.cuda.device(pred.device_index):
         vol, origins, unpad = pred._prepare(data)
-        b, e = shard_patches(len(origins), dist_ctx.world_size, dist_ctx.rank)
-        acc = torch.zeros((pred.num_classes, *vol.shape), dtype=torch.float32, device=pred.device)
-        if e > b:
-            pred.accumulate(vol, origins[b:e], acc)
-        _exchange_accumulators(acc, dist_ctx)
+        plan = plan_shards(origins, pred.patch_size[0], vol.shape[0], dist_ctx.world_size, dist_ctx.rank)
+        acc = torch.zeros((pred.num_classes, plan.zhi - plan.zlo, *vol.shape[1:]), dtype=torch.float32,
+                          device=pred.device)
+        if plan.end > plan.begin:
+            local = origins[plan.begin:plan.end].copy()
+            local[:, 0] -= plan.zlo
+            pred.accumulate(vol[plan.zlo:plan.zhi], local, acc)
+        slab = exchange_slabs(acc, plan, dist_ctx)
+        del acc
         w = weight_sum(vol.shape, pred.patch_size, origins, pred.gaussian())
-        lab = finalize_argmax(acc, w, lut)[unpad].contiguous()
+        lo, hi = plan.slabs[dist_ctx.rank]
+        lab_slab = finalize_argmax(slab, w[lo:hi], lut) if hi > lo else torch.zeros(
+            (0, *vol.shape[1:]), dtype=torch.uint8, device=pred.device)
+        lab = gather_label_slabs(lab_slab, plan, dist_ctx)[unpad].contiguous()
         if label_inout is None:
             return lab
         if overwrite_nonzero_only:
-            nz = lab != 0
-            label_inout[nz] = lab[nz]
+            label_inout.copy_(torch.where(lab != 0, lab, label_inout))
         else:
             label_inout.copy_(lab)
         return label_inout

@@ -1,0 +1,165 @@
+"""GPU parity (bit-exact) of the HBM-bound passes against the oracle and the reference-generated golden vectors,
+through the C ABI."""
+import json
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from boa_b200 import passes
+from boa_b200.predictor import finalize_argmax, weight_sum
+from oracle import passes as op
+
+G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def _dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+
+
+def test_ct_normalize_golden(cuda):
+    z = np.load(os.path.join(G, "ct_norm.npz"))
+    p = json.loads(str(z["props"]))
+    for x in (z["x"], z["x"].astype(np.float32)):
+        y = passes.ct_normalize(_dev(x), p["percentile_00_5"], p["percentile_99_5"], p["mean"], p["std"])
+        assert np.array_equal(y.cpu().numpy(), z["y"])
+
+
+@pytest.mark.parametrize("n", [0, 1, 7, 16, 1000, 4099, 1 << 20])
+def test_ct_normalize_ragged(cuda, n):
+    rng = np.random.default_rng(n)
+    x = rng.integers(-2000, 4000, size=n).astype(np.int16)
+    props = {"mean": 12.5, "std": 300.25, "percentile_00_5": -900.0, "percentile_99_5": 1500.0}
+    y = passes.ct_normalize(_dev(x), -900.0, 1500.0, 12.5, 300.25) if n else torch.empty(0)
+    assert np.array_equal(y.cpu().numpy(), op.ct_normalize(x, props))
+
+
+def test_tissue_golden_and_random(cuda):
+    z = np.load(os.path.join(G, "tissue.npz"))
+    t = passes.tissue_subclassify(_dev(z["ct"]), _dev(z["regions"]))
+    assert np.array_equal(t.cpu().numpy(), z["tissues"])
+    rng = np.random.default_rng(1)
+    for shape in [(3, 5, 7), (16, 64, 64), (9, 33, 31)]:
+        ct = rng.integers(-1100, 3100, size=shape).astype(np.int16)
+        reg = rng.integers(0, 12, size=shape).astype(np.uint8)
+        for c in (ct, ct.astype(np.float32)):
+            t = passes.tissue_subclassify(_dev(c), _dev(reg))
+            assert np.array_equal(t.cpu().numpy(), op.subclassify_tissues(ct, reg))
+
+
+@pytest.mark.parametrize("shape,L", [((5, 16, 16), 8), ((7, 33, 29), 12), ((3, 300, 300), 118), ((2, 512, 512), 8)])
+def test_slice_label_stats(cuda, shape, L):
+    rng = np.random.default_rng(2)
+    lab = rng.integers(0, L + 3, size=shape).astype(np.uint8)   # labels >= L are ignored
+    ct = rng.integers(-1024, 3071, size=shape).astype(np.int16)
+    mask = rng.integers(0, 3, size=shape).astype(np.uint8)
+    for m in (None, mask):
+        c, s = passes.slice_label_stats(_dev(lab), L, ct=_dev(ct), mask=None if m is None else _dev(m), mask_value=1)
+        oc, osum = op.slice_label_stats(lab, L, ct, m, 1)
+        assert np.array_equal(c.cpu().numpy(), oc) and np.array_equal(s.cpu().numpy(), osum)
+    c, s = passes.slice_label_stats(_dev(lab), L)
+    assert s is None and np.array_equal(c.cpu().numpy(), op.slice_label_stats(lab, L)[0])
+
+
+def test_label_hist_and_measurements_golden(cuda):
+    from boa_b200.measurements import compute_measurements_on_device
+    z = np.load(os.path.join(G, "phantom.npz"))
+    gold = json.load(open(os.path.join(G, "measurements.json")))
+    ct, total = _dev(z["ct"]), _dev(z["total"])
+    got, pfav = compute_measurements_on_device(ct, {"total": total}, tuple(z["spacing"]), cnr_adjustment=True,
+                                               return_ct_pfav_mask=True)
+    assert np.array_equal(pfav.cpu().numpy(), z["ct_pfav"])
+    from test_oracle_golden import _close
+    _close(gold, got)
+
+
+def test_erode_matches_oracle(cuda):
+    rng = np.random.default_rng(3)
+    for shape in [(20, 20, 20), (9, 31, 17), (6, 6, 6), (40, 12, 50)]:
+        m = (rng.random(shape) < 0.97).astype(np.uint8)
+        got = passes.erode_box(_dev(m), 3, 2).cpu().numpy()
+        assert np.array_equal(got.astype(bool), op.erode_region(m.astype(bool)))
+
+
+def test_bca_report_golden(cuda):
+    from boa_b200 import bca
+    z = np.load(os.path.join(G, "phantom.npz"))
+    zb = np.load(os.path.join(G, "phantom_bca.npz"))
+    gold = json.load(open(os.path.join(G, "bca.json")))
+    ct, regions, parts, total = _dev(z["ct"]), _dev(z["regions"]), _dev(z["parts"]), _dev(z["total"])
+    tissues = bca.subclassify_tissues(ct, regions)
+    assert np.array_equal(tissues.cpu().numpy(), zb["tissues"])
+    js, vert, _ = bca.build_bca_measurements(ct, tissues, parts, regions, total, tuple(zb["spacing"]))
+    from test_oracle_golden import _close
+    _close(gold["json"], js)
+    assert {k: list(v) for k, v in vert.items()} == gold["vertebrae"]
+
+
+def test_finalize_argmax_ties_lut_merge_and_inf(cuda):
+    rng = np.random.default_rng(4)
+    C, shape = 6, (8, 12, 16)
+    acc = rng.standard_normal((C, *shape)).astype(np.float32)
+    acc[3][acc[1] > 0.5] = acc[1][acc[1] > 0.5]          # exact ties: first maximum must win
+    acc[:, 0, 0, :] = 0.0                                  # all equal -> class 0
+    w = rng.uniform(0.1, 10.0, size=shape).astype(np.float32)
+    ref = (acc / w).argmax(0).astype(np.uint8)
+    lab = finalize_argmax(_dev(acc), _dev(w)).cpu().numpy()
+    assert np.array_equal(lab, ref)
+    lut = [0, 10, 0, 30, 40, 50]
+    prev = rng.integers(0, 5, size=shape).astype(np.uint8)
+    merged = prev.copy()
+    mapped = np.array(lut, dtype=np.uint8)[ref]
+    merged[mapped != 0] = mapped[mapped != 0]
+    got = finalize_argmax(_dev(acc), _dev(w), lut, _dev(prev), True).cpu().numpy()
+    assert np.array_equal(got, merged)
+    bad = acc.copy()
+    bad[2, 1, 1, 1] = np.inf
+    with pytest.raises(RuntimeError, match="inf"):
+        finalize_argmax(_dev(bad), _dev(w))
+
+
+def test_weight_sum_and_accumulate_patch(cuda):
+    from boa_b200 import _lib
+    from boa_b200.geometry import compute_gaussian, sliding_window_origins
+    import ctypes as C
+    patch, shape = (16, 16, 16), (40, 24, 33)
+    origins = sliding_window_origins(shape, patch, 0.5)
+    g = compute_gaussian(patch).astype(np.float32)
+    gd = _dev(g)
+    w = weight_sum(shape, patch, origins, gd).cpu().numpy()
+    ref = np.zeros(shape, dtype=np.float32)
+    for o in origins:
+        ref[o[0]:o[0] + 16, o[1]:o[1] + 16, o[2]:o[2] + 16] += g
+    assert np.array_equal(w, ref)
+    rng = np.random.default_rng(5)
+    Cn = 3
+    acc = torch.zeros((Cn, *shape), device="cuda")
+    racc = np.zeros((Cn, *shape), dtype=np.float32)
+    for o in origins[:5]:
+        lg = rng.standard_normal((Cn, *patch)).astype(np.float32)
+        _lib.check(_lib.lib().boa_accumulate_patch(_lib.ptr(_dev(lg)), Cn, _lib.i32x3(patch), _lib.i32x3(o), _lib.ptr(gd),
+                                                   _lib.ptr(acc), _lib.i32x3(shape), _lib.stream_ptr()))
+        racc[:, o[0]:o[0] + 16, o[1]:o[1] + 16, o[2]:o[2] + 16] += lg * g
+    assert np.array_equal(acc.cpu().numpy(), racc)
+
+
+def test_resample_thickness_vs_scipy(cuda):
+    from scipy import ndimage
+    from boa_b200.resample import resample_thickness, upsample_labels_nearest
+    rng = np.random.default_rng(6)
+    ct = rng.integers(-1000, 2000, size=(47, 20, 24)).astype(np.int16)
+    ref = ndimage.zoom(ct.astype(np.float64), (np.float64(np.float32(1.5)) / 5.0, 1, 1), order=3, mode="nearest")
+    got = resample_thickness(_dev(ct), 1.5, 5.0).cpu().numpy()
+    assert got.shape == ref.shape
+    # fp64 spline as scipy; values agree to ~1e-12 before truncation, so integers differ by at most 1 and only where
+    # the spline value is (numerically) an integer
+    diff = np.abs(got.astype(np.int64) - ref.astype(np.int32))
+    assert diff.max() <= 1 and (diff != 0).mean() < 0.08
+    inner = (np.abs(ref - np.rint(ref)) > 1e-6)
+    assert np.array_equal(got[inner], ref.astype(np.int32)[inner])
+    lab = rng.integers(0, 7, size=ref.shape).astype(np.uint8)
+    up = upsample_labels_nearest(_dev(lab), 47).cpu().numpy()
+    assert np.array_equal(up, ndimage.zoom(lab, (47 / lab.shape[0], 1, 1), order=0, mode="nearest"))

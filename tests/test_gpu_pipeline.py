@@ -1,0 +1,103 @@
+"""GPU: the whole per-volume path (`total+bca`) on a small synthetic CT against the oracle."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+from boa_b200 import zoo
+from boa_b200.labels import part_luts
+from boa_b200.pipeline import ModelZoo, analyze_volume
+from oracle import passes as op
+from oracle.report import bca_json, compute_measurements
+from oracle.sliding_window import convert_logits_to_segmentation, merge_parts, predict_sliding_window_return_logits
+
+
+@pytest.fixture(scope="module")
+def small_zoo():
+    specs = zoo.synthetic_specs((32, 32, 32), 32, 64, 3, bca_folds=5, seed=1)
+    return specs, ModelZoo.from_specs(specs, device=torch.device("cuda", 0), max_batch=3)
+
+
+def _oracle_labels(spec, ct, step, folds):
+    data = op.ct_normalize(ct, spec.intensity)[None]
+    sds = [spec.fold_weights[f] for f in folds]
+    logits = predict_sliding_window_return_logits(spec.arch, sds, data, step, emulate_fp16=True)
+    return convert_logits_to_segmentation(logits), logits
+
+
+def test_total_and_bca_against_oracle(cuda, small_zoo):
+    specs, mz = small_zoo
+    ct = zoo.synthetic_ct((48, 64, 56), seed=2)
+    res = analyze_volume(torch.from_numpy(ct).cuda(), (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=False,
+                         cnr_adjustment=True)
+    # ---- total: 5 part networks, merged
+    segs, margins = [], []
+    for tid in (291, 292, 293, 294, 295):
+        seg, logits = _oracle_labels(specs[tid], ct, 0.8, [0])
+        segs.append(seg)
+        top2 = np.sort(logits, axis=0)[-2:]
+        margins.append(top2[1] - top2[0])
+    ref_total = merge_parts(segs, part_luts(), ct.shape)
+    total = res.total.cpu().numpy()
+    agree = (total == ref_total).mean()
+    # voxels whose top-2 margin exceeds the fp16 noise in EVERY part model must agree exactly
+    safe = np.all(np.stack(margins) > 0.05, axis=0)
+    print(f"total: agreement {agree:.5f}, safe voxels {safe.mean():.3f}")
+    assert agree > 0.99
+    assert np.array_equal(total[safe], ref_total[safe])
+    # ---- everything downstream is integer / exact: recompute with the oracle FROM OUR label maps
+    ref_meas = compute_measurements(ct, total, (1.5, 1.5, 1.5), cnr_adjustment=True)
+    assert np.array_equal(res.ct_pfav.cpu().numpy(), ref_meas.pop("_ct_pfav_mask"))
+    from test_oracle_golden import _close
+    _close(ref_meas, res.total_measurements)
+    regions, parts = res.body_regions.cpu().numpy(), res.body_parts.cpu().numpy()
+    assert regions.shape == ct.shape and parts.shape == ct.shape
+    tissues = res.tissues.cpu().numpy()
+    assert np.array_equal(tissues, op.subclassify_tissues(ct, regions))
+    js, vert = bca_json(ct, tissues, parts, regions, total, (1.5, 1.5, 1.5))
+    _close(js, res.bca_measurements)
+    assert {k: tuple(v) for k, v in vert.items()} == {k: tuple(v) for k, v in res.vertebrae.items()}
+
+
+def test_bca_nets_against_oracle(cuda, small_zoo):
+    """5 mm path: thickness resampling (scipy restated on the device) -> fold ensemble -> nearest up-sampling."""
+    from scipy import ndimage
+    from boa_b200.pipeline import segment_bca_net
+    from boa_b200.resample import resample_thickness, upsample_labels_nearest
+    specs, mz = small_zoo
+    ct = zoo.synthetic_ct((120, 40, 48), seed=4)
+    ct5 = resample_thickness(torch.from_numpy(ct).cuda(), 1.5, 5.0)
+    ct5_np = ct5.cpu().numpy()
+    assert ct5_np.shape[0] == 36
+    for task, tid in (("body_regions", 542), ("body_parts", 543)):
+        for fast, folds in ((True, [0]), (False, [0, 1, 2, 3, 4])):  # --fast-bca / 5-fold logit ensemble
+            lab = segment_bca_net(ct5, mz, task, fast=fast).cpu().numpy()
+            ref, _ = _oracle_labels(specs[tid], ct5_np, 0.5, folds)
+            agree = (lab == ref).mean()
+            print(f"{task} folds {folds}: agreement {agree:.5f}")
+            assert agree > 0.99
+        up = upsample_labels_nearest(torch.from_numpy(lab).cuda(), 120).cpu().numpy()
+        assert np.array_equal(up, ndimage.zoom(lab, (120 / 36, 1, 1), order=0, mode="nearest"))
+
+
+def test_volume_smaller_than_patch_is_padded(cuda, small_zoo):
+    specs, mz = small_zoo
+    from boa_b200.pipeline import segment_task
+    ct = zoo.synthetic_ct((20, 40, 24), seed=5)
+    lab = segment_task(torch.from_numpy(ct).cuda(), mz, [291], [0], 0.5).cpu().numpy()
+    ref, _ = _oracle_labels(specs[291], ct, 0.5, [0])
+    assert lab.shape == ct.shape
+    assert (lab == ref).mean() > 0.99
+
+
+def test_crop_to_nonzero(cuda, small_zoo):
+    specs, mz = small_zoo
+    from boa_b200.pipeline import nonzero_bbox, segment_task
+    ct = zoo.synthetic_ct((40, 40, 40), seed=6)
+    ct[:4] = 0; ct[:, :3] = 0; ct[:, :, 37:] = 0
+    assert nonzero_bbox(torch.from_numpy(ct).cuda()) == [(4, 40), (3, 40), (0, 37)]
+    lab = segment_task(torch.from_numpy(ct).cuda(), mz, [291], [0], 0.5).cpu().numpy()
+    assert (lab[:4] == 0).all() and (lab[:, :3] == 0).all() and (lab[:, :, 37:] == 0).all()
+    ref, _ = _oracle_labels(specs[291], ct[4:, 3:, :37], 0.5, [0])
+    assert (lab[4:, 3:, :37] == ref).mean() > 0.99
