@@ -189,13 +189,16 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
           const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
           const int cgroups = p.Cout / 8;
           float bs[32];
-#pragma unroll
-          for (int c = 0; c < 32; ++c) bs[c] = __ldg(p.bias + (((nbase + c) >> 4) % cgroups) * 8 + (c & 7));
           uint4* d[2];
 #pragma unroll
           for (int jj = 0; jj < 2; ++jj) {
-            const int n = nbase + 16 * jj;
-            const int cg = (n >> 4) % cgroups, pzpy = n / (2 * p.Cout);
+            const int q16 = (nbase >> 4) + jj;                 // 16-column block = (pzpy, channel group)
+            const int pzpy = q16 / cgroups, cg = q16 - pzpy * cgroups;
+            const float4 b0 = __ldg(reinterpret_cast<const float4*>(p.bias + cg * 8));
+            const float4 b1 = __ldg(reinterpret_cast<const float4*>(p.bias + cg * 8) + 1);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { bs[16 * jj + e] = bb[e]; bs[16 * jj + 8 + e] = bb[e]; }
             const int zo = 2 * (tz * p.zt) + (pzpy >> 1), yo = 2 * y + (pzpy & 1);
             d[jj] = reinterpret_cast<uint4*>(p.out) +
                     ((((size_t)b * p.out_groups_total + p.out_group_off + cg) * Do + zo) * Ho + yo) * Wo + 2 * x;
