@@ -1,0 +1,84 @@
+"""Orchestrator: mirror of analyze_ct (body_organ_analysis/commands.py:73-288) and compute_all_models
+(body_organ_analysis/compute/inference.py:50-143) for the NIfTI fast path and the models on the hot path.
+Output-directory contract (README.md:239-257, tests/test_generated_files.py:42-57): total.nii.gz, body_parts.nii.gz,
+body_regions.nii.gz, tissues.nii.gz, ct_pfav.nii.gz, total-measurements.json, bca-measurements.json, vertebrae.json,
+debug_information.txt.  DICOM conversion, contrast prediction, Excel and PDF reporting are out of scope."""
+from __future__ import annotations
+
+import json
+import logging
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+
+from . import nifti
+from .config import IMPLEMENTED_MODELS
+from .labels import class_map
+from .pipeline import ModelZoo, analyze_volume
+
+logger = logging.getLogger(__name__)
+
+
+def range_warning(ct: np.ndarray) -> None:
+    """compute/inference.py:21-30."""
+    lo, hi = int(ct.min()), int(ct.max())
+    if lo < -1024 or hi > 3071:
+        logger.warning("The CT has HU values outside of the usual range [-1024, 3071]: [%s, %s]", lo, hi)
+
+
+def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_folder: Path | None = None,
+               models=("total", "bca"), fast_bca: bool = False, cnr_adjustment: bool = True, device: str = "gpu",
+               recompute: bool = True, weights_root: str | None = None, zoo: ModelZoo | None = None, **_ignored):
+    """NIfTI in -> segmentations + measurement JSONs out.  Returns (output folder, stats dict) like the reference."""
+    start = time.time()
+    models = set(models)
+    todo = models - IMPLEMENTED_MODELS
+    if todo:
+        raise NotImplementedError(f"models {sorted(todo)} are outside the accelerated hot path (total, bca, "
+                                  "body_regions, body_parts)")
+    dev_str, _, gpu_id = device.partition(":")
+    if dev_str != "gpu":
+        raise RuntimeError(f"device '{device}': boa_b200 has no CPU/MPS implementation, use -d gpu[:id]")
+    dev = torch.device("cuda", int(gpu_id) if gpu_id else 0)
+    out_dir = Path(processed_output_folder)
+    out_dir.mkdir(parents=True, exist_ok=True)
+    img = nifti.load(input_folder)
+    data, zooms, order = nifti.to_canonical(img.data, img.affine)
+    ct_np = np.ascontiguousarray(np.trunc(data).astype(np.int16)) if data.dtype.kind == "f" else data.astype(np.int16)
+    range_warning(ct_np)
+    stats = {"num_voxels": int(ct_np.size), "num_slices": int(ct_np.shape[0])}
+    zoo = zoo or ModelZoo(weights_root, device=dev)
+    t0 = time.time()
+    ct = torch.from_numpy(ct_np).pin_memory().to(dev, non_blocking=True)
+    res = analyze_volume(ct, (zooms[2], zooms[1], zooms[0]), zoo, models=tuple(models), fast_bca=fast_bca,
+                         cnr_adjustment=cnr_adjustment)
+    stats["inference_time"] = time.time() - t0
+
+    def write(name, tensor, labels=None):
+        arr = nifti.from_canonical(tensor.cpu().numpy(), order)
+        nifti.save(out_dir / f"{name}.nii.gz", arr, img.affine, labels)
+
+    if res.total is not None:
+        write("total", res.total, class_map("total"))
+        write("ct_pfav", res.ct_pfav)
+        with (out_dir / "total-measurements.json").open("w") as f:
+            json.dump(res.total_measurements, f, indent=2)
+    if res.body_parts is not None:
+        write("body_parts", res.body_parts, class_map("body_parts"))
+    if res.body_regions is not None:
+        write("body_regions", res.body_regions, class_map("body_regions"))
+    if res.tissues is not None:
+        write("tissues", res.tissues)
+        with (out_dir / "bca-measurements.json").open("w") as f:
+            json.dump(res.bca_measurements, f, indent=2)
+        if res.vertebrae:
+            with (out_dir / "vertebrae.json").open("w") as f:
+                json.dump(res.vertebrae, f, indent=2)
+    stats["total_time"] = time.time() - start
+    stats.update({f"gpu_{k}_seconds": v for k, v in res.timings.items()})
+    with (out_dir / "debug_information.txt").open("w") as f:
+        for k, v in stats.items():
+            f.write(f"{k}: {v}\n")
+    return out_dir, stats
