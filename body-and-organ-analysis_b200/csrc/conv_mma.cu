@@ -24,7 +24,8 @@
 
 namespace boa {
 
-constexpr int MMA_THREADS = 192;
+constexpr int MMA_THREADS = 192;        // producer warp, MMA warp, 4 epilogue warps
+constexpr int MMA_THREADS_FUSED = 320;  // + 4 operand-transform warps (normalise + LeakyReLU of the INPUT)
 constexpr int TILE_X = 8, TILE_Y = 16;
 constexpr int XB = TILE_X + 2, YB = TILE_Y + 2, SLAB = XB * YB;  // 180 halo positions per z-plane
 
@@ -36,6 +37,12 @@ struct ConvMmaParams {
   int B, kc_count, Cout, D, H, W, zt;
   int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
   int in_groups_total, in_group_off;
+  // fused input transform: the source tensor holds the producer's RAW conv output; y = lrelu(x * scale + shift) is
+  // applied to the A tile in shared memory between TMA arrival and MMA issue (per (batch item, input channel))
+  const float* in_scale;  // [B][in_channels] or nullptr
+  const float* in_shift;
+  int in_channels;
+  float slope;
   int ntaps;  // 9: (dy,dx) taps as address shifts; 1: the in-plane taps already sit on K (first layer), centre only
 };
 
@@ -48,8 +55,8 @@ __device__ __forceinline__ void decode_tile(int t, const ConvMmaParams& p, int& 
   nt = t / p.B;
 }
 
-template <int NC>
-__global__ void __launch_bounds__(MMA_THREADS, 1)
+template <int NC, bool FUSE>
+__global__ void __launch_bounds__(FUSE ? MMA_THREADS_FUSED : MMA_THREADS, 1)
 conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int zb = p.zt + 2;
@@ -62,7 +69,8 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
   uint64_t* empty = bars + 2;   // [2] MMA -> TMA
   uint64_t* tfull = bars + 4;   // [2] MMA -> epilogue
   uint64_t* tempty = bars + 6;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+  uint64_t* ready = bars + 8;   // [2] transform warps -> MMA (FUSE only)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nbuf = (p.zt * NC <= 256) ? 2 : 1;
 
@@ -72,6 +80,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
       mbar_init(&empty[i], 1);
       mbar_init(&tfull[i], 1);
       mbar_init(&tempty[i], 4);
+      mbar_init(&ready[i], 128);
     }
     fence_barrier_init();
     tma_prefetch_desc(&tmapA);
@@ -124,7 +133,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
         const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
         for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
           const int st = it & 1;
-          mbar_wait(&full[st], (it >> 1) & 1);
+          mbar_wait(FUSE ? &ready[st] : &full[st], (it >> 1) & 1);
           tc_fence_after();
           const uint32_t a0 = smem_u32(smem + st * stage_bytes);
           const uint64_t a_base = a_desc0 + (uint64_t)(a0 >> 4);
@@ -156,6 +165,56 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
       }
     }
     __syncwarp();
+  } else if (FUSE && warp >= 6) {
+    // ===================================================================== operand transform (warps 6..9)
+    // InstanceNorm affine + LeakyReLU of the producer layer, applied in place to the A tile (the zero halo outside the
+    // volume stays zero: padding applies to the ACTIVATED tensor).  Same fp32 operations as norm_lrelu_kernel.
+    const int tid = threadIdx.x - 192;
+    const int per_group = zb * SLAB;
+    uint32_t it = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int nt, b, tz, ty, tx;
+      decode_tile(tile, p, nt, b, tz, ty, tx);
+      const int z0 = tz * p.zt - 1, y0 = ty * TILE_Y - 1, x0 = tx * TILE_X - 1;
+      for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
+        const int st = it & 1;
+        float a[2][8], sh[2][8];
+#pragma unroll
+        for (int g = 0; g < 2; ++g) {
+          const float4* ps = reinterpret_cast<const float4*>(p.in_scale + (size_t)b * p.in_channels + kc * 16 + g * 8);
+          const float4* pf = reinterpret_cast<const float4*>(p.in_shift + (size_t)b * p.in_channels + kc * 16 + g * 8);
+          const float4 a0 = __ldg(ps), a1 = __ldg(ps + 1), s0 = __ldg(pf), s1 = __ldg(pf + 1);
+          a[g][0] = a0.x; a[g][1] = a0.y; a[g][2] = a0.z; a[g][3] = a0.w;
+          a[g][4] = a1.x; a[g][5] = a1.y; a[g][6] = a1.z; a[g][7] = a1.w;
+          sh[g][0] = s0.x; sh[g][1] = s0.y; sh[g][2] = s0.z; sh[g][3] = s0.w;
+          sh[g][4] = s1.x; sh[g][5] = s1.y; sh[g][6] = s1.z; sh[g][7] = s1.w;
+        }
+        mbar_wait(&full[st], (it >> 1) & 1);
+        uint4* tile_a = reinterpret_cast<uint4*>(smem + st * stage_bytes);
+        for (int pos = tid; pos < per_group; pos += 128) {
+          const int z = pos / SLAB, r = pos - z * SLAB, y = r / XB, x = r - y * XB;
+          const int gz = z0 + z, gy = y0 + y, gx = x0 + x;
+          if (gz < 0 || gz >= p.D || gy < 0 || gy >= p.H || gx < 0 || gx >= p.W) continue;
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            uint4 raw = tile_a[g * per_group + pos];
+            __half2* h = reinterpret_cast<__half2*>(&raw);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              float2 f = __half22float2(h[e]);
+              f.x = __fadd_rn(__fmul_rn(f.x, a[g][2 * e]), sh[g][2 * e]);
+              f.y = __fadd_rn(__fmul_rn(f.y, a[g][2 * e + 1]), sh[g][2 * e + 1]);
+              f.x = f.x > 0.f ? f.x : __fmul_rn(f.x, p.slope);
+              f.y = f.y > 0.f ? f.y : __fmul_rn(f.y, p.slope);
+              h[e] = __floats2half2_rn(f.x, f.y);
+            }
+            tile_a[g * per_group + pos] = raw;
+          }
+        }
+        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&ready[st]);
+      }
+    }
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
@@ -201,13 +260,15 @@ struct ConvMmaPlan {
   __half* d_bpacked = nullptr;
   float* d_bias = nullptr;
   int nc = 32;
+  bool fused = false;
   size_t smem = 0;
   int grid = 0;
   double macs = 0;
 };
 
 ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin_w, int cin_padded, int Cout,
-                                  const ActView& src, int B, __half* d_raw_out, double* d_stats, bool taps_on_k) {
+                                  const ActView& src, int B, __half* d_raw_out, double* d_stats, bool taps_on_k,
+                                  const float* d_in_scale, const float* d_in_shift, float slope) {
   // taps_on_k (first layer, Cin = 1): the source tensor carries the 9 in-plane neighbours of every voxel as its
   // channels 0..8, h_w is [Cout][1][27]; only the dz taps remain as (folded) taps.
   const int ntaps = taps_on_k ? 1 : 9;
@@ -235,6 +296,13 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   p.in_groups_total = src.groups_total; p.in_group_off = src.group_off;
   p.out = d_raw_out; p.stats = d_stats;
   p.ntaps = ntaps;
+  p.in_scale = d_in_scale; p.in_shift = d_in_shift; p.in_channels = cin_w; p.slope = slope;
+  pl->fused = d_in_scale != nullptr;
+  if (pl->fused && (cin_w % 16 != 0 || taps_on_k)) {
+    set_error("conv_mma: fused input transform needs Cin %% 16 == 0");
+    conv_mma_plan_destroy(pl);
+    return nullptr;
+  }
   pl->macs = 27.0 * (taps_on_k ? 1 : cin_w) * Cout * (double)src.voxels() * B;
 
   // pack weights: [nt][kc][g=(dy,dx)][kchunk][n = j*NC + co, j <-> dz = 2-j][8 cin]
@@ -275,8 +343,12 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   }
   const size_t stage = 2 * (size_t)(zt + 2) * SLAB * 16 + (size_t)ntaps * 96 * (size_t)NC;
   pl->smem = 2 * stage + 128;
-  cudaError_t e = NC == 64 ? cudaFuncSetAttribute(conv3_fold_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)
-                           : cudaFuncSetAttribute(conv3_fold_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+  cudaError_t e = cudaSuccess;
+  for (const void* fn : {(const void*)conv3_fold_kernel<64, false>, (const void*)conv3_fold_kernel<32, false>,
+                         (const void*)conv3_fold_kernel<64, true>, (const void*)conv3_fold_kernel<32, true>}) {
+    cudaError_t e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+    if (e2 != cudaSuccess) e = e2;
+  }
   if (e != cudaSuccess) {
     set_error("conv_mma: cannot opt in to %zu bytes of shared memory: %s", pl->smem, cudaGetErrorString(e));
     conv_mma_plan_destroy(pl);
@@ -296,10 +368,17 @@ void conv_mma_plan_destroy(ConvMmaPlan* p) {
 double conv_mma_plan_macs(const ConvMmaPlan* p) { return p->macs; }
 
 int conv_mma_launch(ConvMmaPlan* pl, cudaStream_t s) {
-  if (pl->nc == 64)
-    conv3_fold_kernel<64><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
-  else
-    conv3_fold_kernel<32><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
+  if (pl->fused) {
+    if (pl->nc == 64)
+      conv3_fold_kernel<64, true><<<pl->grid, MMA_THREADS_FUSED, pl->smem, s>>>(pl->tmap, pl->prm);
+    else
+      conv3_fold_kernel<32, true><<<pl->grid, MMA_THREADS_FUSED, pl->smem, s>>>(pl->tmap, pl->prm);
+  } else {
+    if (pl->nc == 64)
+      conv3_fold_kernel<64, false><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
+    else
+      conv3_fold_kernel<32, false><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
+  }
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }

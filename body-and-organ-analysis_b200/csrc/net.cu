@@ -44,6 +44,8 @@ struct ConvStep {  // conv -> (stats) -> norm + lrelu   |   transposed conv
   ConvTapsPlan* taps = nullptr;
   double macs = 0;
   std::string name;
+  bool norm_fused_downstream = false;  // (tensor-core mode) the consumer normalises this step's raw output itself
+  ActView raw_view;                    // this step's raw output as a C8 tensor
 };
 
 // Scratch memory of one forward (activations, statistics, staging).  Networks of identical geometry run one at a
@@ -69,10 +71,15 @@ struct boa_net {
   // head
   float *d_head_w = nullptr, *d_head_b = nullptr;
   ActView head_src;
+  ActView head_src_raw;  // raw output of the last conv + its scale/shift (fused head normalisation)
+  const float *head_scale = nullptr, *head_shift = nullptr;
   __half* d_patch = nullptr;  // [B][2][P] C8 input, or plain fp16 [B][P] when the first layer is the direct kernel
   int input_mode = 0;  // 0: C8 16ch, 1: plain fp16 (direct first layer), 2: C8 with the 9 in-plane neighbours on K
   FwdCall* d_call = nullptr;
-  FwdCall* h_call = nullptr;  // pinned
+  static constexpr int CALL_RING = 8;
+  FwdCall* h_call = nullptr;  // pinned ring of staging slots, one per batch in flight
+  cudaEvent_t call_ev[CALL_RING] = {};
+  int call_slot = 0;
   double* d_stats_all = nullptr;
   size_t stats_bytes = 0;
   int64_t macs_per_patch = 0;
@@ -188,6 +195,7 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
   if ((r = launch_stats_finalize(st.d_stats, st.d_gamma, st.d_beta, B, st.cout, (double)st.Do * st.Ho * st.Wo, a.eps,
                                  st.d_scale, st.d_shift, s)))
     return r;
+  if (st.norm_fused_downstream && net->mode == 0) return BOA_OK;
   return launch_norm_lrelu(st.raw, B, st.cout / 8, st.Do, st.Ho, st.Wo, st.d_scale, st.d_shift, a.leaky_slope, st.dst,
                            st.s2d, s);
 }
@@ -205,9 +213,11 @@ int run_accumulate(boa_net* net, cudaStream_t s) {
   if (int r = launch_extract_patches(net->d_call, net->B, a.patch[0], a.patch[1], a.patch[2], net->d_patch,
                                      net->input_mode, s)) return r;
   if (int r = run_body(net, s)) return r;
+  const bool fh = net->head_scale && net->mode == 0;
   for (int b = 0; b < net->B; ++b)
-    if (int r = launch_head(net->head_src, b, net->d_head_w, net->d_head_b, a.features[0], a.num_classes, nullptr,
-                            net->d_call, s))
+    if (int r = launch_head(fh ? net->head_src_raw : net->head_src, b, net->d_head_w, net->d_head_b, a.features[0],
+                            a.num_classes, nullptr, net->d_call, fh ? net->head_scale : nullptr,
+                            fh ? net->head_shift : nullptr, a.leaky_slope, s))
       return r;
   return BOA_OK;
 }
@@ -326,11 +336,12 @@ extern "C" int boa_net_finalize(boa_net* net) {
   // ---- buffers
   net->d_patch = wsalloc<__half>(net, (size_t)B * 16 * vox(0));
   if (!net->d_patch) return BOA_ERR_CUDA;
-  __half *raw[BOA_MAX_STAGES], *mid[BOA_MAX_STAGES][2], *outb[BOA_MAX_STAGES], *cat[BOA_MAX_STAGES],
+  __half *raw[BOA_MAX_STAGES][2], *mid[BOA_MAX_STAGES][2], *outb[BOA_MAX_STAGES], *cat[BOA_MAX_STAGES],
       *s2d[BOA_MAX_STAGES];
   for (int s = 0; s < n; ++s) {
     const size_t f = (size_t)a.features[s];
-    raw[s] = wsalloc<__half>(net, B * f * vox(s));
+    raw[s][0] = wsalloc<__half>(net, B * f * vox(s));
+    raw[s][1] = wsalloc<__half>(net, B * f * vox(s));
     mid[s][0] = wsalloc<__half>(net, B * f * vox(s));
     mid[s][1] = wsalloc<__half>(net, B * f * vox(s));
     outb[s] = wsalloc<__half>(net, B * f * vox(s));
@@ -338,7 +349,7 @@ extern "C" int boa_net_finalize(boa_net* net) {
     const bool iso2 = s < n - 1 && is3(a.strides[s + 1], 2) && dims[s][0] % 2 == 0 && dims[s][1] % 2 == 0 &&
                       dims[s][2] % 2 == 0;
     s2d[s] = iso2 ? wsalloc<__half>(net, B * f * vox(s)) : nullptr;
-    if (!raw[s] || !mid[s][0] || !mid[s][1] || !outb[s] || (s < n - 1 && !cat[s]) || (iso2 && !s2d[s]))
+    if (!raw[s][0] || !raw[s][1] || !mid[s][0] || !mid[s][1] || !outb[s] || (s < n - 1 && !cat[s]) || (iso2 && !s2d[s]))
       return BOA_ERR_CUDA;
   }
   // ---- schedule
@@ -360,14 +371,17 @@ extern "C" int boa_net_finalize(boa_net* net) {
   net->input_mode = (first33 && a.features[0] % 32 == 0) ? 2 : (first33 && conv_first_supported(a.features[0]) ? 1 : 0);
   bool first_plain = net->input_mode == 1;
   bool first_nb9 = net->input_mode == 2;
+  int raw_flip = 0;
   auto add_conv = [&](const std::string& prefix, ActView src, ActView src_s2d, int cin, int cout, const int* ks,
-                      const int* stride, int s_out, ActView dst, __half* s2d_out) -> int {
+                      const int* stride, int s_out, ActView dst, __half* s2d_out, ConvStep* producer) -> int {
     ConvStep st;
     st.name = prefix;
     st.cin = cin; st.cout = cout;
     for (int k = 0; k < 3; ++k) { st.ks[k] = ks[k]; st.stride[k] = stride[k]; }
     st.Do = dims[s_out][0]; st.Ho = dims[s_out][1]; st.Wo = dims[s_out][2];
-    st.raw = raw[s_out];
+    st.raw = raw[s_out][raw_flip & 1];
+    ++raw_flip;
+    st.raw_view = view(st.raw, cout / 8, 0, cout / 8, s_out);
     st.dst = dst;
     st.s2d = s2d_out;
     st.src_plain = src;
@@ -399,7 +413,19 @@ extern "C" int boa_net_finalize(boa_net* net) {
       if (!st.fold) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_FOLD;
     } else if (is3(ks, 3) && is3(stride, 1) && cout % 32 == 0 && cin_padded <= src.groups * 8) {
-      st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats);
+      // the producer is the previous conv of this stage: read its RAW output and normalise it while staging the
+      // operand (no standalone InstanceNorm / LeakyReLU pass for that tensor)
+      // Measured (profiles/r01_fused_norm.txt): the in-place transform costs the consumer exactly what the standalone
+      // pass saves, because the N = 96 / 192 MMAs already saturate the shared-memory port - so it is opt-in.
+      const bool fuse = producer && !producer->is_tconv && cin % 16 == 0 && producer->cout == cin &&
+                        getenv("BOA_B200_FUSE_NORM") != nullptr;
+      if (fuse) {
+        st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, producer->raw_view, B, st.raw,
+                                       st.d_stats, false, producer->d_scale, producer->d_shift, a.leaky_slope);
+        if (st.fold) producer->norm_fused_downstream = true;
+      } else {
+        st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats);
+      }
       if (!st.fold) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_FOLD;
     } else if (is3(ks, 3) && is3(stride, 2) && src_s2d.base && cin % 16 == 0 && cout % 64 == 0) {
@@ -432,7 +458,9 @@ extern "C" int boa_net_finalize(boa_net* net) {
       __half* s2d_out = (last && s < n - 1) ? s2d[s] : nullptr;
       char name[64];
       snprintf(name, sizeof(name), "encoder.stages.%d.0.convs.%d", s, i);
-      if (int r = add_conv(name, cur, i == 0 ? cur_s2d : ActView(), cur_c, f, a.kernels[s], stride, s, dst, s2d_out))
+      ConvStep* producer = i > 0 ? &net->steps.back() : nullptr;
+      if (int r = add_conv(name, cur, i == 0 ? cur_s2d : ActView(), cur_c, f, a.kernels[s], stride, s, dst, s2d_out,
+                           producer))
         return r;
       cur = dst;
       cur_c = f;
@@ -481,7 +509,8 @@ extern "C" int boa_net_finalize(boa_net* net) {
       const int one[3] = {1, 1, 1};
       ActView dst = last ? view(outb[s], f / 8, 0, f / 8, s) : view(mid[s][i & 1], f / 8, 0, f / 8, s);
       snprintf(name, sizeof(name), "decoder.stages.%d.convs.%d", j, i);
-      if (int r = add_conv(name, cur, ActView(), cur_c, f, a.kernels[s], one, s, dst, nullptr)) return r;
+      ConvStep* producer = i > 0 ? &net->steps.back() : nullptr;
+      if (int r = add_conv(name, cur, ActView(), cur_c, f, a.kernels[s], one, s, dst, nullptr, producer)) return r;
       cur = dst;
       cur_c = f;
     }
@@ -497,12 +526,19 @@ extern "C" int boa_net_finalize(boa_net* net) {
     net->d_head_b = upload(net, bi->data);
     if (!net->d_head_w || !net->d_head_b) return BOA_ERR_CUDA;
     net->head_src = cur;
+    ConvStep& last = net->steps.back();
+    if (!last.is_tconv && last.cout == a.features[0] && getenv("BOA_B200_NO_FUSE_HEAD") == nullptr) {
+      net->head_src_raw = last.raw_view;
+      net->head_scale = last.d_scale; net->head_shift = last.d_shift;
+      last.norm_fused_downstream = true;
+    }
     macs += (double)a.num_classes * a.features[0] * vox(0);
   }
   net->macs_per_patch = (int64_t)macs;
   net->d_call = wsalloc<FwdCall>(net, 1);
   if (!net->d_call) return BOA_ERR_CUDA;
-  BOA_CUDA(cudaMallocHost(&net->h_call, sizeof(FwdCall)));
+  BOA_CUDA(cudaMallocHost(&net->h_call, sizeof(FwdCall) * boa_net::CALL_RING));
+  for (int i = 0; i < boa_net::CALL_RING; ++i) BOA_CUDA(cudaEventCreateWithFlags(&net->call_ev[i], cudaEventDisableTiming));
   net->tensors.clear();
   net->finalized = true;
   return BOA_OK;
@@ -522,15 +558,18 @@ extern "C" int boa_net_forward_accumulate(boa_net* net, const float* d_vol, cons
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   for (int p0 = 0; p0 < n_patches; p0 += net->B) {
     const int nb = std::min(net->B, n_patches - p0);
-    // the pinned staging struct is reused: wait until the previous copy has been consumed
-    BOA_CUDA(cudaStreamSynchronize(s));
-    FwdCall* c = net->h_call;
+    // pinned staging slots are recycled round-robin: wait only for the copy that last used this slot
+    const int slot = net->call_slot;
+    net->call_slot = (slot + 1) % boa_net::CALL_RING;
+    BOA_CUDA(cudaEventSynchronize(net->call_ev[slot]));
+    FwdCall* c = net->h_call + slot;
     c->vol = d_vol; c->acc = d_logits_acc; c->gaussian = d_gaussian;
     c->d0 = vol_shape[0]; c->d1 = vol_shape[1]; c->d2 = vol_shape[2];
     c->n_valid = nb;
     for (int b = 0; b < MAX_BATCH; ++b)
       for (int k = 0; k < 3; ++k) c->origins[b][k] = b < nb ? h_origins[3 * (p0 + b) + k] : 0;
     BOA_CUDA(cudaMemcpyAsync(net->d_call, c, sizeof(FwdCall), cudaMemcpyHostToDevice, s));
+    BOA_CUDA(cudaEventRecord(net->call_ev[slot], s));
     size_t f0 = 0, f1 = 0;
     if (net->timing) cudaEventRecord(next_event(net, &f0), s);
     if (net->use_graph && !net->timing) {
@@ -585,9 +624,11 @@ extern "C" int boa_net_forward_logits(boa_net* net, const float* d_patches, int 
       return r;
     }
     if (int r = run_body(net, s)) return r;
+    const bool fh = net->head_scale && net->mode == 0;
     for (int b = 0; b < nb; ++b)
-      if (int r = launch_head(net->head_src, b, net->d_head_w, net->d_head_b, a.features[0], a.num_classes,
-                              d_logits + (size_t)(p0 + b) * a.num_classes * pv, nullptr, s))
+      if (int r = launch_head(fh ? net->head_src_raw : net->head_src, b, net->d_head_w, net->d_head_b, a.features[0],
+                              a.num_classes, d_logits + (size_t)(p0 + b) * a.num_classes * pv, nullptr,
+                              fh ? net->head_scale : nullptr, fh ? net->head_shift : nullptr, a.leaky_slope, s))
         return r;
   }
   return BOA_OK;
@@ -678,5 +719,7 @@ extern "C" void boa_net_destroy(boa_net* net) {
   }
   for (cudaEvent_t e : net->ev) cudaEventDestroy(e);
   if (net->h_call) cudaFreeHost(net->h_call);
+  for (cudaEvent_t e : net->call_ev)
+    if (e) cudaEventDestroy(e);
   delete net;
 }

@@ -65,14 +65,17 @@ int launch_tconv_simt(const ActView& src, int B, const float* d_w, const float* 
 // 1x1x1 head. If d_logits_b != nullptr: write raw logits fp32 [C][P] of batch item b. Else accumulate logits*g into
 // the volume accumulator at the origin of batch item b (skipped when b >= call->n_valid); one launch per patch keeps
 // the reference's patch order (predict_from_raw_data.py:603-616).
+// in_scale / in_shift != nullptr: src holds the RAW output of the last conv; its InstanceNorm affine + LeakyReLU are
+// applied on the fly ([B][Cin] arrays).
 int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias, int Cin, int C, float* d_logits_b,
-                const FwdCall* d_call, cudaStream_t s);
+                const FwdCall* d_call, const float* d_in_scale, const float* d_in_shift, float slope, cudaStream_t s);
 
 // ---- tcgen05 implicit GEMM, 3x3x3 stride 1 with the dz taps folded into N (conv_mma.cu)
 struct ConvMmaPlan;
 ConvMmaPlan* conv_mma_plan_create(const float* h_w /*[Cout][Cin_w][27] fp32*/, const float* h_bias, int cin_w,
                                   int cin_padded, int Cout, const ActView& src, int B, __half* d_raw_out,
-                                  double* d_stats, bool taps_on_k = false);
+                                  double* d_stats, bool taps_on_k = false, const float* d_in_scale = nullptr,
+                                  const float* d_in_shift = nullptr, float slope = 0.01f);
 void conv_mma_plan_destroy(ConvMmaPlan* p);
 int conv_mma_launch(ConvMmaPlan* p, cudaStream_t s);
 

@@ -418,11 +418,16 @@ template <int CIN>
 __global__ void __launch_bounds__(256)
 head_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off, int b, int D, int H, int W,
             const float* __restrict__ w, const float* __restrict__ bias, int C, float* __restrict__ logits_b,
-            const FwdCall* __restrict__ call) {
+            const FwdCall* __restrict__ call, const float* __restrict__ in_scale, const float* __restrict__ in_shift,
+            float slope) {
   extern __shared__ __align__(16) float sw[];  // [C][CIN] then [C] bias
   float* sb = sw + C * CIN;
+  float* ssc = sb + C;        // [CIN] input scale / shift of batch item b (fused normalisation)
+  float* ssh = ssc + CIN;
   for (int i = threadIdx.x; i < CIN * C; i += blockDim.x) sw[i] = w[i];
   for (int i = threadIdx.x; i < C; i += blockDim.x) sb[i] = bias[i];
+  if (in_scale)
+    for (int i = threadIdx.x; i < CIN; i += blockDim.x) { ssc[i] = in_scale[(size_t)b * CIN + i]; ssh[i] = in_shift[(size_t)b * CIN + i]; }
   __syncthreads();
   float* __restrict__ acc = nullptr;
   const float* __restrict__ g = nullptr;
@@ -445,6 +450,15 @@ head_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off,
       unpack8(__ldg(in + ((size_t)b * in_groups_total + in_group_off + gi) * vox + v), f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) x[gi * 8 + e] = f[e];
+    }
+    if (in_scale) {
+      // the source is the RAW output of the last conv: apply its InstanceNorm affine + LeakyReLU and the fp16
+      // rounding the standalone pass would have stored (same operations as norm_lrelu_kernel)
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) {
+        const float z = __fadd_rn(__fmul_rn(x[c], ssc[c]), ssh[c]);
+        x[c] = __half2float(__float2half_rn(z > 0.f ? z : __fmul_rn(z, slope)));
+      }
     }
     float* a = nullptr;
     float gw = 0.f;
@@ -589,18 +603,18 @@ int launch_tconv_simt(const ActView& src, int B, const float* d_w, const float* 
 }
 
 int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias, int Cin, int C, float* d_logits_b,
-                const FwdCall* d_call, cudaStream_t s) {
+                const FwdCall* d_call, const float* d_in_scale, const float* d_in_shift, float slope, cudaStream_t s) {
   if (Cin > HEAD_MAX_CIN || Cin % 8 || C > HEAD_MAX_C) {
     set_error("head: Cin=%d C=%d exceed the head kernel limits (%d, %d)", Cin, C, HEAD_MAX_CIN, HEAD_MAX_C);
     return BOA_ERR_UNSUPPORTED;
   }
   const size_t vox = src.voxels();
-  const size_t smem = ((size_t)C * Cin + C) * sizeof(float);
+  const size_t smem = ((size_t)C * Cin + C + 2 * Cin) * sizeof(float);
   const uint4* in = reinterpret_cast<const uint4*>(src.base);
   const int grid = grid_for(vox, 256, 8);
 #define BOA_HEAD(CIN_)                                                                                              \
   head_kernel<CIN_><<<grid, 256, smem, s>>>(in, src.groups_total, src.group_off, b, src.D, src.H, src.W, d_w, d_bias, \
-                                            C, d_logits_b, d_call)
+                                            C, d_logits_b, d_call, d_in_scale, d_in_shift, slope)
   switch (Cin) {
     case 8: BOA_HEAD(8); break;
     case 16: BOA_HEAD(16); break;
