@@ -124,26 +124,34 @@ def cpu_reference_sample(a, n_patches: int = 2) -> dict:
     for _ in range(n_patches):
         unet_forward(arch, sd, x)
     t_patch = (time.perf_counter() - t0) / n_patches
-    # memory-bound passes on a slab of 16 slices, scaled to the volume
+    # memory-bound passes on a slab of 16 slices, scaled to the volume (numpy, one core, as the reference runs them)
     zs = 16
+    scale = a.shape[0] / zs
     rng = np.random.default_rng(0)
     logits = rng.standard_normal((25, zs, a.shape[1], a.shape[2]), dtype=np.float32)
     ct = rng.integers(-1024, 2047, size=(zs, a.shape[1], a.shape[2])).astype(np.int16)
     t0 = time.perf_counter()
-    seg = logits.argmax(0).astype(np.uint8)
+    seg = logits.argmax(0).astype(np.uint8)                      # export_prediction.py:38, once per network
+    t_argmax = (time.perf_counter() - t0) * scale
     regions = (seg % 12).astype(np.uint8)
-    tissues = op.subclassify_tissues(ct, regions)
-    op.slice_label_stats(tissues, 8, ct)
-    for lab in range(1, 25):
+    t0 = time.perf_counter()
+    tissues = op.subclassify_tissues(ct, regions)                # subclassification.py:38-53
+    op.slice_label_stats(tissues, 8, ct)                         # builder.py:403-444
+    t_bca = (time.perf_counter() - t0) * scale
+    t0 = time.perf_counter()
+    n_lab = 8
+    for lab in range(1, 1 + n_lab):                              # measurements.py:203-241, 304 names per volume
         op.metrics_for_region(ct, seg == lab, 30.0, 10.0, (1.5, 1.5, 1.5))
-    t_pass = (time.perf_counter() - t0) * (a.shape[0] / zs)
+    t_label = (time.perf_counter() - t0) / n_lab * scale
     n = count_forwards(a)
-    # 5 `total` models: argmax each; 117 labels of statistics (24 timed -> scale)
-    t_volume = (n["total"] + n["bca"]) * t_patch + t_pass * (5 + 117 / 24) / 2
+    n_nets = (5 if n["total"] else 0) + (2 if n["bca"] else 0)
+    t_volume = (n["total"] + n["bca"]) * t_patch + n_nets * t_argmax + (t_bca if n["bca"] else 0) + 304 * t_label
     return {"value": 1.0 / t_volume, "unit": UNIT, "cores": threads, "kind": "port",
             "sample": (f"{n_patches} patch forwards of the fp32 oracle network ({t_patch:.2f} s each) scaled to "
-                       f"{n['total'] + n['bca']} forwards + numpy argmax/tissue/statistics on a {zs}-slice slab scaled "
-                       f"to the volume; {ncpu} host cores visible, {threads} torch threads (reference cap)"),
+                       f"{n['total'] + n['bca']} forwards; numpy argmax ({t_argmax:.1f} s/net x {n_nets}), tissue + slice "
+                       f"tables ({t_bca:.1f} s) and per-label statistics ({t_label:.2f} s x 304 names) timed on a "
+                       f"{zs}-slice slab and scaled to the volume; {ncpu} host cores visible, {threads} torch threads "
+                       f"(the reference's cap)"),
             "seconds_per_volume": t_volume}
 
 
@@ -266,8 +274,14 @@ def run_ours(a):
         k["tflops"] = k["flop"] / (k["ms"] * 1e-3) / 1e12 if k["ms"] > 0 else None
     dom = per_kind[kinds[0]]
     peak = peaks.get("bf16_tflops_sustained") or 1400.0
+    traffic = None
+    try:  # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        with open(os.path.join(ROOT, "profiles", "r01_fold_traffic.json")) as f:
+            traffic = json.load(f)
+    except Exception:
+        pass
     roofline = {"bound": "tensor", "kernel": kinds[0], "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",
-                "frac": dom["tflops"] / peak, "traffic": None,
+                "frac": dom["tflops"] / peak, "traffic": traffic,
                 "peak_source": ("MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), of measured"
                                 if peaks else "fallback 1.4 PFLOP/s sustained, of fallback"),
                 "per_launch": {"avg_ms": dom["ms"] / dom["launches"], "avg_flop": dom["flop"] / dom["launches"],

@@ -43,6 +43,22 @@ inline void count_launch(int n = 1) { g_launches.fetch_add((uint64_t)n, std::mem
 
 constexpr int MAX_DYN_SMEM = 232448;  // 227 KB: the per-CTA opt-in maximum on sm_100
 
+// Kernels can only share an SM with the persistent tcgen05 conv CTAs (227 KB of dynamic shared memory) when they ask
+// for the same L1 / shared-memory split: the HBM-bound passes of one lane overlap the convolutions of the other only
+// with the carve-out preference set to "all shared".
+template <typename K>
+inline void prefer_max_smem_carveout(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+#define BOA_CARVEOUT_ONCE(kernel)            \
+  do {                                       \
+    static bool done_ = false;               \
+    if (!done_) {                            \
+      boa::prefer_max_smem_carveout(kernel); \
+      done_ = true;                          \
+    }                                        \
+  } while (0)
+
 // Number of SMs of the current device (cached) - grids are sized in multiples of it.
 int sm_count();
 

@@ -50,9 +50,30 @@ struct ConvStep {  // conv -> (stats) -> norm + lrelu   |   transposed conv
 
 // Scratch memory of one forward (activations, statistics, staging).  Networks of identical geometry run one at a
 // time on a stream and may share it (fold ensembles, the five `total` part models).
+// Two LANES: consecutive batches of patches alternate between two complete sets of scratch buffers on two internal
+// streams, so the HBM-bound passes of one batch overlap the tensor-bound convolutions of the other and kernel
+// boundaries stop draining the machine; only the head (the ordered `logits[sl] += pred * g`) is serialised between
+// lanes with an event.  The streams belong to the workspace, so networks that share it stay ordered.
+constexpr int MAX_LANES = 2;
 struct Workspace {
-  std::vector<std::pair<void*, size_t>> bufs;
+  std::vector<std::pair<void*, size_t>> bufs[MAX_LANES];
+  cudaStream_t stream[MAX_LANES] = {};
+  cudaEvent_t head_done = nullptr;   // last head enqueued on any lane
+  cudaEvent_t fork = nullptr, join[MAX_LANES] = {};
+  int last_lane = -1;
   int refs = 1;
+};
+
+struct Lane {
+  std::vector<ConvStep> steps;
+  __half* d_patch = nullptr;  // [B][2][P] C8 input (or plain fp16 [B][P], see input_mode)
+  FwdCall* d_call = nullptr;
+  double* d_stats_all = nullptr;
+  ActView head_src, head_src_raw;  // normalised / raw output of the last conv (fused head normalisation)
+  const float *head_scale = nullptr, *head_shift = nullptr;
+  cudaGraphExec_t g_body = nullptr, g_head = nullptr;
+  int launches_body = 0, launches_head = 0;
+  size_t ws_cursor = 0;
 };
 
 }  // namespace boa
@@ -66,21 +87,16 @@ struct boa_net {
   std::map<std::string, HostTensor> tensors;
   std::vector<void*> allocs;  // per-network memory (weights)
   Workspace* ws = nullptr;    // shared scratch
-  size_t ws_cursor = 0;
-  std::vector<ConvStep> steps;
+  Lane lane[MAX_LANES];
+  int n_lanes = 2;
+  std::map<std::string, float*> wcache;  // device copies of the fp32 parameters, shared by the lanes
   // head
   float *d_head_w = nullptr, *d_head_b = nullptr;
-  ActView head_src;
-  ActView head_src_raw;  // raw output of the last conv + its scale/shift (fused head normalisation)
-  const float *head_scale = nullptr, *head_shift = nullptr;
-  __half* d_patch = nullptr;  // [B][2][P] C8 input, or plain fp16 [B][P] when the first layer is the direct kernel
   int input_mode = 0;  // 0: C8 16ch, 1: plain fp16 (direct first layer), 2: C8 with the 9 in-plane neighbours on K
-  FwdCall* d_call = nullptr;
   static constexpr int CALL_RING = 8;
   FwdCall* h_call = nullptr;  // pinned ring of staging slots, one per batch in flight
   cudaEvent_t call_ev[CALL_RING] = {};
   int call_slot = 0;
-  double* d_stats_all = nullptr;
   size_t stats_bytes = 0;
   int64_t macs_per_patch = 0;
   // timing
@@ -91,8 +107,6 @@ struct boa_net {
   std::vector<std::pair<size_t, size_t>> fwd_spans;
   double ms_convs = 0, ms_total = 0;
   int64_t n_conv_launches = 0;
-  // graph
-  cudaGraphExec_t graph_accum = nullptr;
   int use_graph = 1;
 };
 
@@ -112,17 +126,19 @@ T* dalloc(boa_net* net, size_t n) {
 // Workspace allocation: buffers are requested in a deterministic order, so a network that shares a donor's workspace
 // walks the donor's list and must find the same sizes.
 template <typename T>
-T* wsalloc(boa_net* net, size_t n) {
+T* wsalloc(boa_net* net, int li, size_t n) {
   const size_t bytes = n * sizeof(T);
   Workspace* ws = net->ws;
-  if (net->ws_cursor < ws->bufs.size()) {
-    auto& b = ws->bufs[net->ws_cursor];
+  size_t& cursor = net->lane[li].ws_cursor;
+  std::vector<std::pair<void*, size_t>>& bufs = ws->bufs[li];
+  if (cursor < bufs.size()) {
+    auto& b = bufs[cursor];
     if (b.second != bytes) {
       set_error("shared workspace mismatch at buffer %zu: have %zu bytes, need %zu (different network geometry)",
-                net->ws_cursor, b.second, bytes);
+                cursor, b.second, bytes);
       return nullptr;
     }
-    ++net->ws_cursor;
+    ++cursor;
     return static_cast<T*>(b.first);
   }
   void* p = nullptr;
@@ -130,14 +146,18 @@ T* wsalloc(boa_net* net, size_t n) {
     set_error("cudaMalloc of %zu bytes failed: %s", bytes, cudaGetErrorString(cudaGetLastError()));
     return nullptr;
   }
-  ws->bufs.push_back({p, bytes});
-  ++net->ws_cursor;
+  bufs.push_back({p, bytes});
+  ++cursor;
   return static_cast<T*>(p);
 }
 
-float* upload(boa_net* net, const std::vector<float>& v) {
+// fp32 parameters are uploaded once and shared by the lanes
+float* upload(boa_net* net, const std::string& key, const std::vector<float>& v) {
+  auto it = net->wcache.find(key);
+  if (it != net->wcache.end()) return it->second;
   float* d = dalloc<float>(net, v.size());
   if (d) cudaMemcpy(d, v.data(), v.size() * sizeof(float), cudaMemcpyHostToDevice);
+  net->wcache[key] = d;
   return d;
 }
 
@@ -201,24 +221,58 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
 }
 
 // everything of one forward except the input staging and the head
-int run_body(boa_net* net, cudaStream_t s) {
-  BOA_CUDA(cudaMemsetAsync(net->d_stats_all, 0, net->stats_bytes, s));
-  for (ConvStep& st : net->steps)
+int run_body(boa_net* net, Lane& L, cudaStream_t s) {
+  BOA_CUDA(cudaMemsetAsync(L.d_stats_all, 0, net->stats_bytes, s));
+  for (ConvStep& st : L.steps)
     if (int r = run_step(net, st, s)) return r;
   return BOA_OK;
 }
 
-int run_accumulate(boa_net* net, cudaStream_t s) {
+// input staging + network body of one batch
+int run_front(boa_net* net, Lane& L, cudaStream_t s) {
   const boa_arch& a = net->arch;
-  if (int r = launch_extract_patches(net->d_call, net->B, a.patch[0], a.patch[1], a.patch[2], net->d_patch,
-                                     net->input_mode, s)) return r;
-  if (int r = run_body(net, s)) return r;
-  const bool fh = net->head_scale && net->mode == 0;
-  for (int b = 0; b < net->B; ++b)
-    if (int r = launch_head(fh ? net->head_src_raw : net->head_src, b, net->d_head_w, net->d_head_b, a.features[0],
-                            a.num_classes, nullptr, net->d_call, fh ? net->head_scale : nullptr,
-                            fh ? net->head_shift : nullptr, a.leaky_slope, s))
+  if (int r = launch_extract_patches(L.d_call, net->B, a.patch[0], a.patch[1], a.patch[2], L.d_patch, net->input_mode, s))
+    return r;
+  return run_body(net, L, s);
+}
+
+// heads of one batch, one launch per patch in slicer order; d_logits != nullptr: raw logits of nb patches instead
+int run_heads(boa_net* net, Lane& L, int nb, float* d_logits, cudaStream_t s) {
+  const boa_arch& a = net->arch;
+  const bool fh = L.head_scale && net->mode == 0;
+  const size_t pv = (size_t)a.patch[0] * a.patch[1] * a.patch[2];
+  for (int b = 0; b < nb; ++b)
+    if (int r = launch_head(fh ? L.head_src_raw : L.head_src, b, net->d_head_w, net->d_head_b, a.features[0],
+                            a.num_classes, d_logits ? d_logits + (size_t)b * a.num_classes * pv : nullptr, L.d_call,
+                            fh ? L.head_scale : nullptr, fh ? L.head_shift : nullptr, a.leaky_slope, s))
       return r;
+  return BOA_OK;
+}
+
+void destroy_graphs(boa_net* net) {
+  for (Lane& L : net->lane) {
+    if (L.g_body) cudaGraphExecDestroy(L.g_body);
+    if (L.g_head) cudaGraphExecDestroy(L.g_head);
+    L.g_body = L.g_head = nullptr;
+  }
+}
+
+template <typename F>
+int capture_graph(cudaGraphExec_t* out, int* launches, F&& body) {
+  cudaStream_t cs;
+  BOA_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+  cudaGraph_t g = nullptr;
+  BOA_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+  const uint64_t before = g_launches.load();
+  const int r = body(cs);
+  *launches = (int)(g_launches.load() - before);
+  const cudaError_t ce = cudaStreamEndCapture(cs, &g);
+  cudaStreamDestroy(cs);
+  g_launches.fetch_sub((uint64_t)*launches);  // the capture enqueued nothing
+  if (r) return r;
+  BOA_CUDA(ce);
+  BOA_CUDA(cudaGraphInstantiate(out, g, 0));
+  cudaGraphDestroy(g);
   return BOA_OK;
 }
 
@@ -249,6 +303,8 @@ extern "C" int boa_net_create(const boa_arch* arch, int device, int max_batch, b
   net->device = device;
   net->B = max_batch;
   net->ws = new Workspace();
+  const char* nl = getenv("BOA_B200_LANES");
+  net->n_lanes = (nl && atoi(nl) == 1) ? 1 : MAX_LANES;
   *out = net;
   return BOA_OK;
 }
@@ -272,7 +328,7 @@ extern "C" int boa_net_set_tensor(boa_net* net, const char* key, const float* h_
 
 extern "C" int boa_net_share_workspace(boa_net* net, boa_net* donor) {
   BOA_REQUIRE(net && donor && net != donor, "boa_net_share_workspace: bad argument");
-  BOA_REQUIRE(!net->finalized && net->ws->bufs.empty(), "boa_net_share_workspace: must be called before finalize");
+  BOA_REQUIRE(!net->finalized && net->ws->bufs[0].empty(), "boa_net_share_workspace: must be called before finalize");
   BOA_REQUIRE(net->device == donor->device && net->B == donor->B, "boa_net_share_workspace: device / batch differ");
   if (--net->ws->refs == 0) delete net->ws;
   net->ws = donor->ws;
@@ -282,10 +338,7 @@ extern "C" int boa_net_share_workspace(boa_net* net, boa_net* donor) {
 
 extern "C" int boa_net_set_mode(boa_net* net, int mode) {
   BOA_REQUIRE(net && (mode == 0 || mode == 1), "boa_net_set_mode: bad argument");
-  if (net->mode != mode && net->graph_accum) {
-    cudaGraphExecDestroy(net->graph_accum);
-    net->graph_accum = nullptr;
-  }
+  if (net->mode != mode) destroy_graphs(net);
   net->mode = mode;
   return BOA_OK;
 }
@@ -310,9 +363,8 @@ static int need(boa_net* net, const std::string& key, const HostTensor** out, si
   return BOA_OK;
 }
 
-extern "C" int boa_net_finalize(boa_net* net) {
-  BOA_REQUIRE(net && !net->finalized, "boa_net_finalize: bad state");
-  BOA_CUDA(cudaSetDevice(net->device));
+static int build_lane(boa_net* net, int li) {
+  Lane& L = net->lane[li];
   const boa_arch& a = net->arch;
   const int n = a.n_stages, B = net->B;
   // ---- spatial dims per stage
@@ -334,21 +386,21 @@ extern "C" int boa_net_finalize(boa_net* net) {
     return v;
   };
   // ---- buffers
-  net->d_patch = wsalloc<__half>(net, (size_t)B * 16 * vox(0));
-  if (!net->d_patch) return BOA_ERR_CUDA;
+  L.d_patch = wsalloc<__half>(net, li, (size_t)B * 16 * vox(0));
+  if (!L.d_patch) return BOA_ERR_CUDA;
   __half *raw[BOA_MAX_STAGES][2], *mid[BOA_MAX_STAGES][2], *outb[BOA_MAX_STAGES], *cat[BOA_MAX_STAGES],
       *s2d[BOA_MAX_STAGES];
   for (int s = 0; s < n; ++s) {
     const size_t f = (size_t)a.features[s];
-    raw[s][0] = wsalloc<__half>(net, B * f * vox(s));
-    raw[s][1] = wsalloc<__half>(net, B * f * vox(s));
-    mid[s][0] = wsalloc<__half>(net, B * f * vox(s));
-    mid[s][1] = wsalloc<__half>(net, B * f * vox(s));
-    outb[s] = wsalloc<__half>(net, B * f * vox(s));
-    cat[s] = s < n - 1 ? wsalloc<__half>(net, B * 2 * f * vox(s)) : nullptr;
+    raw[s][0] = wsalloc<__half>(net, li, B * f * vox(s));
+    raw[s][1] = wsalloc<__half>(net, li, B * f * vox(s));
+    mid[s][0] = wsalloc<__half>(net, li, B * f * vox(s));
+    mid[s][1] = wsalloc<__half>(net, li, B * f * vox(s));
+    outb[s] = wsalloc<__half>(net, li, B * f * vox(s));
+    cat[s] = s < n - 1 ? wsalloc<__half>(net, li, B * 2 * f * vox(s)) : nullptr;
     const bool iso2 = s < n - 1 && is3(a.strides[s + 1], 2) && dims[s][0] % 2 == 0 && dims[s][1] % 2 == 0 &&
                       dims[s][2] % 2 == 0;
-    s2d[s] = iso2 ? wsalloc<__half>(net, B * f * vox(s)) : nullptr;
+    s2d[s] = iso2 ? wsalloc<__half>(net, li, B * f * vox(s)) : nullptr;
     if (!raw[s][0] || !raw[s][1] || !mid[s][0] || !mid[s][1] || !outb[s] || (s < n - 1 && !cat[s]) || (iso2 && !s2d[s]))
       return BOA_ERR_CUDA;
   }
@@ -359,8 +411,8 @@ extern "C" int boa_net_finalize(boa_net* net) {
   int cmax = 0;
   for (int s = 0; s < n; ++s) cmax = std::max(cmax, a.features[s]);
   net->stats_bytes = (size_t)n_norm_layers * B * cmax * 2 * sizeof(double);
-  net->d_stats_all = wsalloc<double>(net, (size_t)n_norm_layers * B * cmax * 2);
-  if (!net->d_stats_all) return BOA_ERR_CUDA;
+  L.d_stats_all = wsalloc<double>(net, li, (size_t)n_norm_layers * B * cmax * 2);
+  if (!L.d_stats_all) return BOA_ERR_CUDA;
   int layer_idx = 0;
   double macs = 0;
 
@@ -392,13 +444,13 @@ extern "C" int boa_net_finalize(boa_net* net) {
     if (int r = need(net, prefix + ".norm.weight", &g, cout)) return r;
     if (int r = need(net, prefix + ".norm.bias", &be, cout)) return r;
     const std::vector<float> wr = round_fp16(w->data);
-    st.d_w = upload(net, wr);
-    st.d_bias = upload(net, bi->data);
-    st.d_gamma = upload(net, g->data);
-    st.d_beta = upload(net, be->data);
-    st.d_stats = net->d_stats_all + (size_t)layer_idx * B * cmax * 2;
-    st.d_scale = wsalloc<float>(net, (size_t)B * cout);
-    st.d_shift = wsalloc<float>(net, (size_t)B * cout);
+    st.d_w = upload(net, prefix + ".conv.weight", wr);
+    st.d_bias = upload(net, prefix + ".conv.bias", bi->data);
+    st.d_gamma = upload(net, prefix + ".norm.weight", g->data);
+    st.d_beta = upload(net, prefix + ".norm.bias", be->data);
+    st.d_stats = L.d_stats_all + (size_t)layer_idx * B * cmax * 2;
+    st.d_scale = wsalloc<float>(net, li, (size_t)B * cout);
+    st.d_shift = wsalloc<float>(net, li, (size_t)B * cout);
     if (!st.d_w || !st.d_bias || !st.d_gamma || !st.d_beta || !st.d_scale || !st.d_shift) return BOA_ERR_CUDA;
     ++layer_idx;
     st.macs = (double)k3 * cin * cout * st.Do * st.Ho * st.Wo;
@@ -439,12 +491,12 @@ extern "C" int boa_net_finalize(boa_net* net) {
     }
     first_plain = false;
     first_nb9 = false;
-    net->steps.push_back(st);
+    L.steps.push_back(st);
     return BOA_OK;
   };
 
   // encoder
-  ActView cur = view(net->d_patch, 2, 0, 2, 0);
+  ActView cur = view(L.d_patch, 2, 0, 2, 0);
   ActView cur_s2d;  // s2d copy of `cur` when it exists
   int cur_c = a.in_channels;
   for (int s = 0; s < n; ++s) {
@@ -458,7 +510,7 @@ extern "C" int boa_net_finalize(boa_net* net) {
       __half* s2d_out = (last && s < n - 1) ? s2d[s] : nullptr;
       char name[64];
       snprintf(name, sizeof(name), "encoder.stages.%d.0.convs.%d", s, i);
-      ConvStep* producer = i > 0 ? &net->steps.back() : nullptr;
+      ConvStep* producer = i > 0 ? &L.steps.back() : nullptr;
       if (int r = add_conv(name, cur, i == 0 ? cur_s2d : ActView(), cur_c, f, a.kernels[s], stride, s, dst, s2d_out,
                            producer))
         return r;
@@ -490,8 +542,8 @@ extern "C" int boa_net_finalize(boa_net* net) {
     if (int r = need(net, up.name + ".weight", &w, (size_t)cb * f * nph)) return r;
     if (int r = need(net, up.name + ".bias", &bi, f)) return r;
     const std::vector<float> wr = round_fp16(w->data);
-    up.d_w = upload(net, wr);
-    up.d_bias = upload(net, bi->data);
+    up.d_w = upload(net, up.name + ".weight", wr);
+    up.d_bias = upload(net, up.name + ".bias", bi->data);
     if (!up.d_w || !up.d_bias) return BOA_ERR_CUDA;
     up.macs = (double)nph * cb * f * vox(s_below);
     macs += up.macs;
@@ -501,7 +553,7 @@ extern "C" int boa_net_finalize(boa_net* net) {
       if (!up.taps) return BOA_ERR_CUDA;
       up.kind = STEP_TCONV_TAPS;
     }
-    net->steps.push_back(up);
+    L.steps.push_back(up);
     cur = view(cat[s], 2 * f / 8, 0, 2 * f / 8, s);
     cur_c = 2 * f;
     for (int i = 0; i < a.n_conv_dec[j]; ++i) {
@@ -509,7 +561,7 @@ extern "C" int boa_net_finalize(boa_net* net) {
       const int one[3] = {1, 1, 1};
       ActView dst = last ? view(outb[s], f / 8, 0, f / 8, s) : view(mid[s][i & 1], f / 8, 0, f / 8, s);
       snprintf(name, sizeof(name), "decoder.stages.%d.convs.%d", j, i);
-      ConvStep* producer = i > 0 ? &net->steps.back() : nullptr;
+      ConvStep* producer = i > 0 ? &L.steps.back() : nullptr;
       if (int r = add_conv(name, cur, ActView(), cur_c, f, a.kernels[s], one, s, dst, nullptr, producer)) return r;
       cur = dst;
       cur_c = f;
@@ -522,21 +574,38 @@ extern "C" int boa_net_finalize(boa_net* net) {
     const HostTensor *w, *bi;
     if (int r = need(net, std::string(name) + ".weight", &w, (size_t)a.num_classes * a.features[0])) return r;
     if (int r = need(net, std::string(name) + ".bias", &bi, a.num_classes)) return r;
-    net->d_head_w = upload(net, round_fp16(w->data));
-    net->d_head_b = upload(net, bi->data);
+    net->d_head_w = upload(net, std::string(name) + ".weight", round_fp16(w->data));
+    net->d_head_b = upload(net, std::string(name) + ".bias", bi->data);
     if (!net->d_head_w || !net->d_head_b) return BOA_ERR_CUDA;
-    net->head_src = cur;
-    ConvStep& last = net->steps.back();
+    L.head_src = cur;
+    ConvStep& last = L.steps.back();
     if (!last.is_tconv && last.cout == a.features[0] && getenv("BOA_B200_NO_FUSE_HEAD") == nullptr) {
-      net->head_src_raw = last.raw_view;
-      net->head_scale = last.d_scale; net->head_shift = last.d_shift;
+      L.head_src_raw = last.raw_view;
+      L.head_scale = last.d_scale; L.head_shift = last.d_shift;
       last.norm_fused_downstream = true;
     }
     macs += (double)a.num_classes * a.features[0] * vox(0);
   }
   net->macs_per_patch = (int64_t)macs;
-  net->d_call = wsalloc<FwdCall>(net, 1);
-  if (!net->d_call) return BOA_ERR_CUDA;
+  L.d_call = wsalloc<FwdCall>(net, li, 1);
+  if (!L.d_call) return BOA_ERR_CUDA;
+  return BOA_OK;
+}
+
+extern "C" int boa_net_finalize(boa_net* net) {
+  BOA_REQUIRE(net && !net->finalized, "boa_net_finalize: bad state");
+  BOA_CUDA(cudaSetDevice(net->device));
+  for (int li = 0; li < net->n_lanes; ++li)
+    if (int r = build_lane(net, li)) return r;
+  Workspace* ws = net->ws;
+  if (!ws->stream[0]) {
+    for (int li = 0; li < MAX_LANES; ++li) {
+      BOA_CUDA(cudaStreamCreateWithFlags(&ws->stream[li], cudaStreamNonBlocking));
+      BOA_CUDA(cudaEventCreateWithFlags(&ws->join[li], cudaEventDisableTiming));
+    }
+    BOA_CUDA(cudaEventCreateWithFlags(&ws->head_done, cudaEventDisableTiming));
+    BOA_CUDA(cudaEventCreateWithFlags(&ws->fork, cudaEventDisableTiming));
+  }
   BOA_CUDA(cudaMallocHost(&net->h_call, sizeof(FwdCall) * boa_net::CALL_RING));
   for (int i = 0; i < boa_net::CALL_RING; ++i) BOA_CUDA(cudaEventCreateWithFlags(&net->call_ev[i], cudaEventDisableTiming));
   net->tensors.clear();
@@ -555,9 +624,21 @@ extern "C" int boa_net_forward_accumulate(boa_net* net, const float* d_vol, cons
       BOA_REQUIRE(h_origins[3 * p + k] >= 0 && h_origins[3 * p + k] + a.patch[k] <= vol_shape[k],
                   "boa_net_forward_accumulate: patch %d outside the volume", p);
   BOA_CUDA(cudaSetDevice(net->device));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  for (int p0 = 0; p0 < n_patches; p0 += net->B) {
+  cudaStream_t user = static_cast<cudaStream_t>(stream);
+  Workspace* ws = net->ws;
+  const bool timing = net->timing;
+  const bool lanes = net->n_lanes > 1 && !timing;
+  if (lanes) {  // fork: both lane streams continue after everything enqueued on the caller's stream so far
+    BOA_CUDA(cudaEventRecord(ws->fork, user));
+    for (int li = 0; li < net->n_lanes; ++li) BOA_CUDA(cudaStreamWaitEvent(ws->stream[li], ws->fork, 0));
+    ws->last_lane = -1;
+  }
+  int batch = 0;
+  for (int p0 = 0; p0 < n_patches; p0 += net->B, ++batch) {
     const int nb = std::min(net->B, n_patches - p0);
+    const int li = lanes ? (batch % net->n_lanes) : 0;
+    Lane& L = net->lane[li];
+    cudaStream_t s = lanes ? ws->stream[li] : user;
     // pinned staging slots are recycled round-robin: wait only for the copy that last used this slot
     const int slot = net->call_slot;
     net->call_slot = (slot + 1) % boa_net::CALL_RING;
@@ -568,35 +649,45 @@ extern "C" int boa_net_forward_accumulate(boa_net* net, const float* d_vol, cons
     c->n_valid = nb;
     for (int b = 0; b < MAX_BATCH; ++b)
       for (int k = 0; k < 3; ++k) c->origins[b][k] = b < nb ? h_origins[3 * (p0 + b) + k] : 0;
-    BOA_CUDA(cudaMemcpyAsync(net->d_call, c, sizeof(FwdCall), cudaMemcpyHostToDevice, s));
+    BOA_CUDA(cudaMemcpyAsync(L.d_call, c, sizeof(FwdCall), cudaMemcpyHostToDevice, s));
     BOA_CUDA(cudaEventRecord(net->call_ev[slot], s));
     size_t f0 = 0, f1 = 0;
-    if (net->timing) cudaEventRecord(next_event(net, &f0), s);
-    if (net->use_graph && !net->timing) {
-      if (!net->graph_accum) {
-        cudaStream_t cs;
-        BOA_CUDA(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-        cudaGraph_t g = nullptr;
-        BOA_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-        const uint64_t before = g_launches.load();
-        int r = run_accumulate(net, cs);
-        net->n_conv_launches = (int64_t)(g_launches.load() - before);  // launches per graph replay
-        cudaError_t ce = cudaStreamEndCapture(cs, &g);
-        cudaStreamDestroy(cs);
-        if (r) return r;
-        BOA_CUDA(ce);
-        BOA_CUDA(cudaGraphInstantiate(&net->graph_accum, g, 0));
-        cudaGraphDestroy(g);
-        g_launches.fetch_sub((uint64_t)net->n_conv_launches);  // capture enqueued nothing
+    if (timing) cudaEventRecord(next_event(net, &f0), s);
+    const bool graph = net->use_graph && !timing;
+    if (graph) {
+      if (!L.g_body) {
+        if (int r = capture_graph(&L.g_body, &L.launches_body, [&](cudaStream_t cs) { return run_front(net, L, cs); }))
+          return r;
+        if (int r = capture_graph(&L.g_head, &L.launches_head,
+                                  [&](cudaStream_t cs) { return run_heads(net, L, net->B, nullptr, cs); }))
+          return r;
       }
-      BOA_CUDA(cudaGraphLaunch(net->graph_accum, s));
-      count_launch((int)net->n_conv_launches);
-    } else {
-      if (int r = run_accumulate(net, s)) return r;
+      BOA_CUDA(cudaGraphLaunch(L.g_body, s));
+      count_launch(L.launches_body);
+    } else if (int r = run_front(net, L, s)) {
+      return r;
     }
-    if (net->timing) {
+    // the accumulation is ordered: this batch's heads run after the previous batch's heads (other lane)
+    if (lanes && ws->last_lane >= 0 && ws->last_lane != li) BOA_CUDA(cudaStreamWaitEvent(s, ws->head_done, 0));
+    if (graph) {
+      BOA_CUDA(cudaGraphLaunch(L.g_head, s));
+      count_launch(L.launches_head);
+    } else if (int r = run_heads(net, L, net->B, nullptr, s)) {
+      return r;
+    }
+    if (lanes) {
+      BOA_CUDA(cudaEventRecord(ws->head_done, s));
+      ws->last_lane = li;
+    }
+    if (timing) {
       cudaEventRecord(next_event(net, &f1), s);
       net->fwd_spans.push_back({f0, f1});
+    }
+  }
+  if (lanes) {  // join: the caller's stream continues after both lanes
+    for (int li = 0; li < net->n_lanes; ++li) {
+      BOA_CUDA(cudaEventRecord(ws->join[li], ws->stream[li]));
+      BOA_CUDA(cudaStreamWaitEvent(user, ws->join[li], 0));
     }
   }
   return BOA_OK;
@@ -612,24 +703,20 @@ extern "C" int boa_net_forward_logits(boa_net* net, const float* d_patches, int 
   const size_t pv = (size_t)a.patch[0] * a.patch[1] * a.patch[2];
   for (int p0 = 0; p0 < n_patches; p0 += net->B) {
     const int nb = std::min(net->B, n_patches - p0);
-    if (nb < net->B) BOA_CUDA(cudaMemsetAsync(net->d_patch, 0, (size_t)net->B * 16 * pv * sizeof(__half), s));
+    Lane& L = net->lane[0];
+    if (nb < net->B) BOA_CUDA(cudaMemsetAsync(L.d_patch, 0, (size_t)net->B * 16 * pv * sizeof(__half), s));
     if (net->input_mode == 2) {
       if (int r = launch_pack_patches_nb9(d_patches + (size_t)p0 * pv, nb, a.patch[0], a.patch[1], a.patch[2],
-                                          net->d_patch, s))
+                                          L.d_patch, s))
         return r;
     } else if (net->input_mode == 1) {
-      if (int r = launch_pack_patches_plain(d_patches + (size_t)p0 * pv, (size_t)nb * pv, net->d_patch, s)) return r;
+      if (int r = launch_pack_patches_plain(d_patches + (size_t)p0 * pv, (size_t)nb * pv, L.d_patch, s)) return r;
     } else if (int r = launch_pack_patches(d_patches + (size_t)p0 * a.in_channels * pv, nb, a.in_channels,
-                                           a.patch[0], a.patch[1], a.patch[2], net->d_patch, 2, s)) {
+                                           a.patch[0], a.patch[1], a.patch[2], L.d_patch, 2, s)) {
       return r;
     }
-    if (int r = run_body(net, s)) return r;
-    const bool fh = net->head_scale && net->mode == 0;
-    for (int b = 0; b < nb; ++b)
-      if (int r = launch_head(fh ? net->head_src_raw : net->head_src, b, net->d_head_w, net->d_head_b, a.features[0],
-                              a.num_classes, d_logits + (size_t)(p0 + b) * a.num_classes * pv, nullptr,
-                              fh ? net->head_scale : nullptr, fh ? net->head_shift : nullptr, a.leaky_slope, s))
-        return r;
+    if (int r = run_body(net, L, s)) return r;
+    if (int r = run_heads(net, L, nb, d_logits + (size_t)p0 * a.num_classes * pv, s)) return r;
   }
   return BOA_OK;
 }
@@ -672,11 +759,12 @@ extern "C" int boa_net_read_timing(boa_net* net, double* ms_convs, double* ms_to
 // Per-layer description for profiling / DESIGN.md: writes up to `cap` entries, returns the number of steps.
 extern "C" int boa_net_describe(const boa_net* net, int cap, int32_t* kinds, double* macs, char* names, int name_stride) {
   if (!net) return 0;
-  const int n = (int)net->steps.size();
+  const std::vector<ConvStep>& steps = net->lane[0].steps;
+  const int n = (int)steps.size();
   for (int i = 0; i < n && i < cap; ++i) {
-    if (kinds) kinds[i] = (int)net->steps[i].kind;
-    if (macs) macs[i] = net->steps[i].macs;
-    if (names) snprintf(names + (size_t)i * name_stride, name_stride, "%s", net->steps[i].name.c_str());
+    if (kinds) kinds[i] = (int)steps[i].kind;
+    if (macs) macs[i] = steps[i].macs;
+    if (names) snprintf(names + (size_t)i * name_stride, name_stride, "%s", steps[i].name.c_str());
   }
   return n;
 }
@@ -692,7 +780,7 @@ extern "C" int boa_net_time_layers(boa_net* net, int cap, float* ms, void* strea
   net->fwd_spans.clear();
   net->ev_used = 0;
   net->timing = true;
-  int r = run_body(net, s);
+  int r = run_body(net, net->lane[0], s);
   net->timing = was;
   if (r) return r;
   BOA_CUDA(cudaDeviceSynchronize());
@@ -707,14 +795,22 @@ extern "C" void boa_net_destroy(boa_net* net) {
   if (!net) return;
   cudaSetDevice(net->device);
   cudaDeviceSynchronize();
-  if (net->graph_accum) cudaGraphExecDestroy(net->graph_accum);
-  for (ConvStep& st : net->steps) {
-    if (st.fold) conv_mma_plan_destroy(st.fold);
-    if (st.taps) conv_taps_plan_destroy(st.taps);
-  }
+  destroy_graphs(net);
+  for (Lane& L : net->lane)
+    for (ConvStep& st : L.steps) {
+      if (st.fold) conv_mma_plan_destroy(st.fold);
+      if (st.taps) conv_taps_plan_destroy(st.taps);
+    }
   for (void* p : net->allocs) cudaFree(p);
   if (--net->ws->refs == 0) {
-    for (auto& b : net->ws->bufs) cudaFree(b.first);
+    for (auto& bufs : net->ws->bufs)
+      for (auto& b : bufs) cudaFree(b.first);
+    for (int li = 0; li < MAX_LANES; ++li) {
+      if (net->ws->stream[li]) cudaStreamDestroy(net->ws->stream[li]);
+      if (net->ws->join[li]) cudaEventDestroy(net->ws->join[li]);
+    }
+    if (net->ws->head_done) cudaEventDestroy(net->ws->head_done);
+    if (net->ws->fork) cudaEventDestroy(net->ws->fork);
     delete net->ws;
   }
   for (cudaEvent_t e : net->ev) cudaEventDestroy(e);

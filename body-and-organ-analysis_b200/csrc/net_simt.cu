@@ -500,6 +500,7 @@ head_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off,
 // ================================================================================================ launchers
 int launch_pack_patches_nb9(const float* d_patches, int n, int p0, int p1, int p2, __half* d_out, cudaStream_t s) {
   const size_t total = (size_t)n * p0 * p1 * p2;
+  BOA_CARVEOUT_ONCE(extract_patches_nb9_kernel);
   extract_patches_nb9_kernel<<<grid_for(total, 256), 256, 0, s>>>(nullptr, d_patches, n, p0, p1, p2,
                                                                   reinterpret_cast<uint4*>(d_out));
   BOA_CHECK_LAUNCH();
@@ -510,6 +511,7 @@ int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2,
                            cudaStream_t s) {
   if (mode == 2) {
     const size_t total = (size_t)B * p0 * p1 * p2;
+    BOA_CARVEOUT_ONCE(extract_patches_nb9_kernel);
     extract_patches_nb9_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_call, nullptr, B, p0, p1, p2,
                                                                     reinterpret_cast<uint4*>(d_out));
   } else if (mode == 1) {
@@ -557,6 +559,7 @@ int launch_pack_patches(const float* d_patches, int n, int cin, int p0, int p1, 
 
 int launch_stats_finalize(const double* d_stats, const float* d_gamma, const float* d_beta, int B, int C,
                           double n_vox, float eps, float* d_scale, float* d_shift, cudaStream_t s) {
+  BOA_CARVEOUT_ONCE(stats_finalize_kernel);
   stats_finalize_kernel<<<(B * C + 127) / 128, 128, 0, s>>>(d_stats, d_gamma, d_beta, B, C, n_vox, eps, d_scale,
                                                             d_shift);
   BOA_CHECK_LAUNCH();
@@ -572,6 +575,7 @@ int launch_norm_lrelu(const __half* d_raw, int B, int groups, int D, int H, int 
   const int cap = (sm_count() * 8 + planes - 1) / planes;
   if (bx > cap) bx = cap;
   if (bx < 1) bx = 1;
+  BOA_CARVEOUT_ONCE(norm_lrelu_kernel);
   norm_lrelu_kernel<<<dim3(bx, planes), 256, 0, s>>>(
       reinterpret_cast<const uint4*>(d_raw), groups, D, H, W, d_scale, d_shift, slope,
       reinterpret_cast<uint4*>(dst.base), dst.groups_total, dst.group_off, reinterpret_cast<uint4*>(d_s2d));
@@ -613,6 +617,7 @@ int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias
   const uint4* in = reinterpret_cast<const uint4*>(src.base);
   const int grid = grid_for(vox, 256, 8);
 #define BOA_HEAD(CIN_)                                                                                              \
+  BOA_CARVEOUT_ONCE(head_kernel<CIN_>);                                                                               \
   head_kernel<CIN_><<<grid, 256, smem, s>>>(in, src.groups_total, src.group_off, b, src.D, src.H, src.W, d_w, d_bias, \
                                             C, d_logits_b, d_call, d_in_scale, d_in_shift, slope)
   switch (Cin) {

@@ -20,7 +20,7 @@ net.forward_logits(x[:1].contiguous()) if False else None
 vol = torch.randn(P + 64, P + 64, P + 64, device="cuda")
 g = torch.from_numpy(compute_gaussian((P, P, P)).astype(np.float32)).cuda()
 acc = torch.zeros(25, *vol.shape, device="cuda")
-origins = np.array([[0, 0, 0], [64, 64, 64], [0, 64, 0], [64, 0, 64]] * 4, dtype=np.int32)[: max(B, 4)]
+origins = np.array([[0, 0, 0], [64, 64, 64], [0, 64, 0], [64, 0, 64]] * (B + 1), dtype=np.int32)[: 4 * B]
 net.forward_accumulate(vol, origins, g, acc)
 torch.cuda.synchronize()
 desc = net.describe()
