@@ -59,6 +59,10 @@ inline void prefer_max_smem_carveout(K kernel) {
     }                                        \
   } while (0)
 
+// Co-resident ("thin") launch shapes for the HBM-bound passes of a forward (default on; BOA_B200_THIN=0 restores the
+// occupancy-style launches): see norm_lrelu_thin_kernel in net_simt.cu.
+bool thin_passes();
+
 // Number of SMs of the current device (cached) - grids are sized in multiples of it.
 int sm_count();
 

@@ -16,6 +16,8 @@
 // of the C8 tensor (zero filled out of bounds = conv padding), taps are 16-byte address offsets into it; B = weights
 // pre-packed on the host into the smem operand image, one bulk copy per chunk; accumulators: one TMEM slot of NC
 // columns per output z-plane of the tile, double buffered.
+#include <stdlib.h>
+#include <algorithm>
 #include <vector>
 #include "net_kernels.cuh"
 #include "conv_epilogue.cuh"
@@ -27,6 +29,7 @@ namespace boa {
 constexpr int TAPS_THREADS = 192;
 constexpr int TT_X = 8, TT_Y = 16;
 constexpr int TAPS_MAX_OPS = 27;
+constexpr int TAPS_MAX_STAGES = 12;  // smem ring depth: small stages (transposed conv, deep layers) prefetch several tiles ahead
 constexpr int TAB_STRIDE = 32;  // ints per class-table entry: [0] n_ops, [1] ops of all earlier chunks, [2..] a_off
 
 struct TapsParams {
@@ -61,18 +64,18 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t stage_bytes = p.a_bytes + p.b_stage_bytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
-  uint64_t* full = bars;         // [4] TMA -> MMA
-  uint64_t* empty = bars + 4;    // [4] MMA -> TMA
-  uint64_t* tfull = bars + 8;    // [2] MMA -> epilogue
-  uint64_t* tempty = bars + 10;  // [2] epilogue -> MMA
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 12);
-  int32_t* stab = reinterpret_cast<int32_t*>(bars + 14);  // [n_classes][TAB_STRIDE] tap table (<= 8 classes)
+  uint64_t* full = bars;                            // [TAPS_MAX_STAGES] TMA -> MMA
+  uint64_t* empty = bars + TAPS_MAX_STAGES;         // [TAPS_MAX_STAGES] MMA -> TMA
+  uint64_t* tfull = bars + 2 * TAPS_MAX_STAGES;     // [2] MMA -> epilogue
+  uint64_t* tempty = tfull + 2;                     // [2] epilogue -> MMA
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
+  int32_t* stab = reinterpret_cast<int32_t*>(tempty + 4);  // [n_classes][TAB_STRIDE] tap table (<= 8 classes)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nstage = p.stages;
   for (int i = threadIdx.x; i < p.n_classes * TAB_STRIDE; i += blockDim.x) stab[i] = __ldg(p.table + i);
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) {
+    for (int i = 0; i < TAPS_MAX_STAGES; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
     }
@@ -356,14 +359,15 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
   p.b_stage_bytes = round_up((uint32_t)max_ops * NC * 32u, 128u);
   const uint32_t stage = p.a_bytes + p.b_stage_bytes;
   int stages = (int)(200u * 1024u / stage);
-  if (stages > 4) stages = 4;
+  if (stages > TAPS_MAX_STAGES) stages = TAPS_MAX_STAGES;
+  if (const char* e = getenv("BOA_B200_TAPS_STAGES")) stages = std::max(2, std::min(stages, atoi(e)));
   if (stages < 2) {
     set_error("conv_taps: stage of %u bytes does not fit twice in shared memory", stage);
     conv_taps_plan_destroy(pl);
     return nullptr;
   }
   p.stages = stages;
-  pl->smem = (size_t)stages * stage + 256 + 8 * TAB_STRIDE * sizeof(int32_t);
+  pl->smem = (size_t)stages * stage + (2 * TAPS_MAX_STAGES + 8) * 8 + 8 * TAB_STRIDE * sizeof(int32_t);
   // the attribute is per kernel, not per plan: always opt in to the full 227 KB
   cudaError_t e = NC == 128 ? cudaFuncSetAttribute(conv_taps_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)
                             : cudaFuncSetAttribute(conv_taps_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);

@@ -1,5 +1,6 @@
 // Library-wide state: last-error string, launch counter, device queries.
 #include "common.cuh"
+#include <stdlib.h>
 #include <string.h>
 
 namespace boa {
@@ -12,6 +13,15 @@ void set_error(const char* fmt, ...) {
   va_start(ap, fmt);
   vsnprintf(g_err, sizeof(g_err), fmt, ap);
   va_end(ap);
+}
+
+bool thin_passes() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BOA_B200_THIN");
+    v = (e && atoi(e) == 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 int sm_count() {

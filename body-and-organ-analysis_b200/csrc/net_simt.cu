@@ -2,6 +2,7 @@
 // reference kernels (direct conv / transposed conv / head).  The SIMT convs exist as an on-device cross-check for
 // the tcgen05 kernels and as the implementation of ops that have not moved to tensor cores yet; they are selected
 // explicitly, never as a silent fallback.
+#include <algorithm>
 #include "net_kernels.cuh"
 
 namespace boa {
@@ -303,6 +304,65 @@ norm_lrelu_kernel(const uint4* __restrict__ raw, int groups, int D, int H, int W
   }
 }
 
+// Co-resident ("thin") variant.  The persistent tcgen05 conv CTAs hold ~48 K of the SM's 64 K registers and almost all
+// of its shared memory; a pass of the OTHER lane only overlaps them if one of its blocks fits into what is left
+// (<= 16 K registers: 256 threads x 64) AND never occupies more than that, so that a conv CTA can always start next to
+// it.  Hence: one persistent block per SM, 8 independent 16-byte loads in flight per thread (32 KB per SM) instead of
+// occupancy to cover the HBM latency.  Same arithmetic as norm_lrelu_kernel.
+constexpr int THIN_U = 8;
+__global__ void __launch_bounds__(256, 4)
+norm_lrelu_thin_kernel(const uint4* __restrict__ raw, int planes, int groups, int D, int H, int W,
+                       const float* __restrict__ scale, const float* __restrict__ shift, float slope,
+                       uint4* __restrict__ dst, int dst_groups_total, int dst_group_off, uint4* __restrict__ s2d) {
+  const int vox = D * H * W;  // voxels of one (batch item, channel group) plane: < 2^31
+  constexpr int CHUNK = 256 * THIN_U;
+  const int chunks = (vox + CHUNK - 1) / CHUNK;
+  const int items = planes * chunks;
+  __shared__ float ws[8][16];
+  const int lane = threadIdx.x & 31;
+  float* wsl = ws[threadIdx.x >> 5];
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int bg = item / chunks;
+    const int vbase = (item - bg * chunks) * CHUNK + (int)threadIdx.x;
+    const int nrem = vox - vbase;  // element u of this thread exists iff u * 256 < nrem
+    const uint4* __restrict__ src = raw + (size_t)bg * vox + vbase;
+    uint4 r[THIN_U];
+#pragma unroll
+    for (int u = 0; u < THIN_U; ++u)
+      if (u * 256 < nrem) r[u] = __ldcs(src + u * 256);
+    // the 8 scale / shift pairs of this plane live in a warp-private shared-memory slot (broadcast reads), not in 16
+    // registers: the register budget goes to the loads in flight
+    __syncwarp();
+    if (lane < 16) wsl[lane] = lane < 8 ? __ldg(scale + (size_t)bg * 8 + lane) : __ldg(shift + (size_t)bg * 8 + lane - 8);
+    __syncwarp();
+    const int b = bg / groups, g = bg - b * groups;
+    uint4* __restrict__ out = dst ? dst + ((size_t)b * dst_groups_total + dst_group_off + g) * vox + vbase : nullptr;
+    uint4* __restrict__ out2 = s2d ? s2d + ((size_t)b * 8 * groups + g) * (vox >> 3) : nullptr;
+    const int phase_stride = groups * (vox >> 3);
+#pragma unroll
+    for (int u = 0; u < THIN_U; ++u) {
+      if (u * 256 < nrem) {
+        float f[8];
+        unpack8(r[u], f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float z = __fadd_rn(__fmul_rn(f[e], wsl[e]), wsl[8 + e]);
+          f[e] = z > 0.f ? z : __fmul_rn(z, slope);
+        }
+        const uint4 o = pack8(f);
+        if (out) out[u * 256] = o;
+        if (out2) {
+          const int v = vbase + u * 256;
+          const int x = v % W, y = (v / W) % H, z = v / (W * H);
+          const int ph = ((z & 1) * 2 + (y & 1)) * 2 + (x & 1);
+          const int hv = ((z >> 1) * (H >> 1) + (y >> 1)) * (W >> 1) + (x >> 1);
+          out2[(size_t)ph * phase_stride + hv] = o;
+        }
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------ SIMT direct conv
 // One thread = one output voxel x 8 output channels.  Accumulates InstanceNorm statistics with fp64 atomics.
 struct Int3 { int z, y, x; };
@@ -512,7 +572,7 @@ int launch_extract_patches(const FwdCall* d_call, int B, int p0, int p1, int p2,
   if (mode == 2) {
     const size_t total = (size_t)B * p0 * p1 * p2;
     BOA_CARVEOUT_ONCE(extract_patches_nb9_kernel);
-    extract_patches_nb9_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_call, nullptr, B, p0, p1, p2,
+    extract_patches_nb9_kernel<<<grid_for(total, 256, thin_passes() ? 2 : 8), 256, 0, s>>>(d_call, nullptr, B, p0, p1, p2,
                                                                     reinterpret_cast<uint4*>(d_out));
   } else if (mode == 1) {
     const size_t total = (size_t)B * p0 * p1 * p2;
@@ -570,6 +630,16 @@ int launch_norm_lrelu(const __half* d_raw, int B, int groups, int D, int H, int 
                       const float* d_shift, float slope, const ActView& dst, __half* d_s2d, cudaStream_t s) {
   const size_t vox = (size_t)D * H * W;
   const int planes = B * groups;
+  if (thin_passes()) {
+    BOA_CARVEOUT_ONCE(norm_lrelu_thin_kernel);
+    const size_t items = (size_t)planes * ((vox + 256 * THIN_U - 1) / (256 * THIN_U));
+    const int grid = (int)std::min<size_t>(items, (size_t)sm_count());
+    norm_lrelu_thin_kernel<<<grid, 256, 0, s>>>(
+        reinterpret_cast<const uint4*>(d_raw), planes, groups, D, H, W, d_scale, d_shift, slope,
+        reinterpret_cast<uint4*>(dst.base), dst.groups_total, dst.group_off, reinterpret_cast<uint4*>(d_s2d));
+    BOA_CHECK_LAUNCH();
+    return BOA_OK;
+  }
   // ~8 resident blocks per SM in total, split over the (b, group) planes; 4 vectors per thread per iteration
   int bx = (int)((vox + 4 * 256 - 1) / (4 * 256));
   const int cap = (sm_count() * 8 + planes - 1) / planes;
@@ -615,10 +685,13 @@ int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias
   const size_t vox = src.voxels();
   const size_t smem = ((size_t)C * Cin + C + 2 * Cin) * sizeof(float);
   const uint4* in = reinterpret_cast<const uint4*>(src.base);
-  const int grid = grid_for(vox, 256, 8);
+  // thin mode: 128 threads x <= 128 registers per SM (see norm_lrelu_thin_kernel), one persistent block per SM
+  const bool thin = thin_passes();
+  const int threads = thin ? 128 : 256;
+  const int grid = thin ? (int)std::min<size_t>((vox + 127) / 128, (size_t)sm_count()) : grid_for(vox, 256, 8);
 #define BOA_HEAD(CIN_)                                                                                              \
   BOA_CARVEOUT_ONCE(head_kernel<CIN_>);                                                                               \
-  head_kernel<CIN_><<<grid, 256, smem, s>>>(in, src.groups_total, src.group_off, b, src.D, src.H, src.W, d_w, d_bias, \
+  head_kernel<CIN_><<<grid, threads, smem, s>>>(in, src.groups_total, src.group_off, b, src.D, src.H, src.W, d_w, d_bias, \
                                             C, d_logits_b, d_call, d_in_scale, d_in_shift, slope)
   switch (Cin) {
     case 8: BOA_HEAD(8); break;
