@@ -43,6 +43,7 @@ struct ConvMmaParams {
   const float* in_shift;
   int in_channels;
   float slope;
+  int tmap_merged;  // tensor map built with the (channel, x) dimensions merged (tmap.cuh)
   int ntaps;  // 9: (dy,dx) taps as address shifts; 1: the in-plane taps already sit on K (first layer), centre only
 };
 
@@ -106,7 +107,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
         if (elect_one()) {
           uint8_t* sa = smem + st * stage_bytes;
           mbar_arrive_expect_tx(&full[st], stage_bytes);
-          tma_load_5d(sa, &tmapA, &full[st], 0, tx * TILE_X - 1, ty * TILE_Y - 1, tz * p.zt - 1,
+          tma_load_c8(sa, &tmapA, &full[st], p.tmap_merged, tx * TILE_X - 1, ty * TILE_Y - 1, tz * p.zt - 1,
                       b * p.in_groups_total + p.in_group_off + 2 * kc);
           bulk_load(sa + a_bytes,
                     reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)(nt * p.kc_count + kc) * b_bytes, b_bytes,
@@ -296,6 +297,7 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   p.in_groups_total = src.groups_total; p.in_group_off = src.group_off;
   p.out = d_raw_out; p.stats = d_stats;
   p.ntaps = ntaps;
+  p.tmap_merged = c8_tmap_merged() ? 1 : 0;
   p.in_scale = d_in_scale; p.in_shift = d_in_shift; p.in_channels = cin_w; p.slope = slope;
   pl->fused = d_in_scale != nullptr;
   if (pl->fused && (cin_w % 16 != 0 || taps_on_k)) {

@@ -46,6 +46,7 @@ struct TapsParams {
   int in_groups_total, in_group_off;
   int out_groups_total, out_group_off, Cout;
   int stages;
+  int tmap_merged;  // tensor map built with the (channel, x) dimensions merged (tmap.cuh)
   uint32_t a_bytes, a_tx_bytes, b_stage_bytes, b_nt_bytes;  // a_bytes: smem placement (128 B multiple), a_tx: TMA box
 };
 
@@ -114,7 +115,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
           uint8_t* sa = smem + (size_t)st * stage_bytes;
           const uint32_t bbytes = (uint32_t)n_ops * NC * 32u;
           mbar_arrive_expect_tx(&full[st], p.a_tx_bytes + bbytes);
-          tma_load_5d(sa, &tmapA, &full[st], 0, tx * TT_X + p.org, ty * TT_Y + p.org, tz * p.zt + p.org,
+          tma_load_c8(sa, &tmapA, &full[st], p.tmap_merged, tx * TT_X + p.org, ty * TT_Y + p.org, tz * p.zt + p.org,
                       b * p.in_groups_total + p.in_group_off + 2 * kc);
           bulk_load(sa + p.a_bytes,
                     reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)nt * p.b_nt_bytes + (size_t)b_off * 16u,
@@ -367,6 +368,7 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
     return nullptr;
   }
   p.stages = stages;
+  p.tmap_merged = c8_tmap_merged() ? 1 : 0;
   pl->smem = (size_t)stages * stage + (2 * TAPS_MAX_STAGES + 8) * 8 + 8 * TAB_STRIDE * sizeof(int32_t);
   // the attribute is per kernel, not per plan: always opt in to the full 227 KB
   cudaError_t e = NC == 128 ? cudaFuncSetAttribute(conv_taps_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)

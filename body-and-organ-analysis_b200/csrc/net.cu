@@ -12,6 +12,7 @@
 // statistics come from the fp32 accumulators (fp64 sums); normalise + LeakyReLU are applied to the stored fp16 values
 // in fp32 and stored as fp16 (the reference's CUDA path runs the same ops under torch.autocast fp16,
 // predict_from_raw_data.py:648).
+#include <string.h>
 #include <map>
 #include <string>
 #include <vector>
@@ -108,6 +109,7 @@ struct boa_net {
   double ms_convs = 0, ms_total = 0;
   int64_t n_conv_launches = 0;
   int use_graph = 1;
+  int debug_only = 0;  // profiling aid (BOA_B200_DEBUG_ONLY=conv|thin at creation): launch only one class of kernels
 };
 
 namespace {
@@ -191,6 +193,15 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
   const bool time_it = net->timing;
   if (time_it) cudaEventRecord(next_event(net, &e0), s);
   int r = BOA_OK;
+  if (net->debug_only == 2) {  // thin passes only
+    if (st.is_tconv) return BOA_OK;
+    if ((r = launch_stats_finalize(st.d_stats, st.d_gamma, st.d_beta, B, st.cout, (double)st.Do * st.Ho * st.Wo, a.eps,
+                                   st.d_scale, st.d_shift, s)))
+      return r;
+    if (st.norm_fused_downstream && net->mode == 0) return BOA_OK;
+    return launch_norm_lrelu(st.raw, B, st.cout / 8, st.Do, st.Ho, st.Wo, st.d_scale, st.d_shift, a.leaky_slope, st.dst,
+                             st.s2d, s);
+  }
   if (st.is_tconv) {
     if (st.kind == STEP_TCONV_TAPS && net->mode == 0) r = conv_taps_launch(st.taps, s);
     else r = launch_tconv_simt(st.src, B, st.d_w, st.d_bias, st.cin, st.cout, st.stride, st.dst, s);
@@ -212,6 +223,7 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
     net->conv_spans.push_back({e0, e1});
   }
   if (r) return r;
+  if (net->debug_only == 1) return BOA_OK;  // convolutions only
   if ((r = launch_stats_finalize(st.d_stats, st.d_gamma, st.d_beta, B, st.cout, (double)st.Do * st.Ho * st.Wo, a.eps,
                                  st.d_scale, st.d_shift, s)))
     return r;
@@ -241,6 +253,7 @@ int run_heads(boa_net* net, Lane& L, int nb, float* d_logits, cudaStream_t s) {
   const boa_arch& a = net->arch;
   const bool fh = L.head_scale && net->mode == 0;
   const size_t pv = (size_t)a.patch[0] * a.patch[1] * a.patch[2];
+  if (net->debug_only == 1) return BOA_OK;
   for (int b = 0; b < nb; ++b)
     if (int r = launch_head(fh ? L.head_src_raw : L.head_src, b, net->d_head_w, net->d_head_b, a.features[0],
                             a.num_classes, d_logits ? d_logits + (size_t)b * a.num_classes * pv : nullptr, L.d_call,
@@ -305,6 +318,7 @@ extern "C" int boa_net_create(const boa_arch* arch, int device, int max_batch, b
   net->ws = new Workspace();
   const char* nl = getenv("BOA_B200_LANES");
   net->n_lanes = (nl && atoi(nl) == 1) ? 1 : MAX_LANES;
+  if (const char* d = getenv("BOA_B200_DEBUG_ONLY")) net->debug_only = !strcmp(d, "conv") ? 1 : (!strcmp(d, "thin") ? 2 : 0);
   *out = net;
   return BOA_OK;
 }

@@ -61,6 +61,20 @@ __device__ __forceinline__ void tma_load_5d(void* smem_dst, const void* tmap, ui
       ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(void* smem_dst, const void* tmap, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+// C8 activation box: (x0, y0, z0, g0) = first voxel / channel group of the box.  merged != 0: the tensor map has the
+// (channel, x) dimensions merged into one (see make_c8_tmap), so the x coordinate is in elements.
+__device__ __forceinline__ void tma_load_c8(void* smem_dst, const void* tmap, uint64_t* bar, int merged, int x0, int y0,
+                                            int z0, int g0) {
+  if (merged) tma_load_4d(smem_dst, tmap, bar, x0 * 8, y0, z0, g0);
+  else tma_load_5d(smem_dst, tmap, bar, 0, x0, y0, z0, g0);
+}
 // Plain (non-tensor) bulk copy global -> shared, completes on an mbarrier. bytes % 16 == 0, 16B-aligned.
 __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(

@@ -174,8 +174,41 @@ class VolumeResult:
     timings: dict = field(default_factory=dict)
 
 
+class HostStager:
+    """Device -> host staging of the label maps for callers that hold host buffers: each map is copied into a pinned
+    buffer on a side stream as soon as it is final, so the transfer overlaps the networks that follow (the reference
+    writes every map to disk between tasks, totalsegmentator/nnunet.py:553-559,723-726).  Buffers are reused across
+    volumes; `collect()` waits for the copies and hands out the host tensors (valid until the next volume)."""
+
+    def __init__(self, device):
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        self._buf: dict = {}
+        self._pending: dict = {}
+
+    def stage(self, name: str, t: torch.Tensor | None) -> None:
+        if t is None:
+            return
+        key = (name, tuple(t.shape), t.dtype)
+        if key not in self._buf:
+            self._buf[key] = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        self.stream.wait_event(ready)
+        with torch.cuda.stream(self.stream):
+            self._buf[key].copy_(t, non_blocking=True)
+        t.record_stream(self.stream)
+        self._pending[name] = self._buf[key]
+
+    def collect(self) -> dict:
+        self.stream.synchronize()
+        out, self._pending = self._pending, {}
+        return out
+
+
 def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total", "bca"), fast_bca: bool = False,
-                   cnr_adjustment: bool = False, dist_ctx: DistContext | None = None) -> VolumeResult:
+                   cnr_adjustment: bool = False, dist_ctx: DistContext | None = None,
+                   stager: HostStager | None = None) -> VolumeResult:
     """compute_all_models + run_pipeline numerics for one CT already on the device (int16 [z,y,x]).
 
     spacing_zyx: voxel spacing of the array axes.  `total` expects 1.5 mm (resampling is identity there,
@@ -200,10 +233,14 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
             raise NotImplementedError("`total` needs a 1.5 mm volume: 3-D cubic resampling is not on the GPU path yet")
         res.total = segment_total(ct, zoo, dist_ctx)
         mark("total_nets")
+        if stager is not None:
+            stager.stage("total", res.total)
         sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
         res.total_measurements, res.ct_pfav = compute_measurements_on_device(
             ct, {"total": res.total}, sx_sy_sz, cnr_adjustment, return_ct_pfav_mask=True)
         mark("total_measurements")
+        if stager is not None:
+            stager.stage("ct_pfav", res.ct_pfav)
     if "bca" in models or "body_parts" in models or "body_regions" in models:
         ct5 = resample_thickness(ct, spacing_zyx[0], 5.0)
         mark("resample")
@@ -211,11 +248,17 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         want_regions = "bca" in models or "body_regions" in models
         if want_parts:
             res.body_parts = upsample_labels_nearest(segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx), ct.shape[0])
+            if stager is not None:
+                stager.stage("body_parts", res.body_parts)
         if want_regions:
             res.body_regions = upsample_labels_nearest(segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx), ct.shape[0])
+        if stager is not None:
+            stager.stage("body_regions", res.body_regions)
         mark("bca_nets")
     if "bca" in models:
         res.tissues = bca.subclassify_tissues(ct, res.body_regions)
+        if stager is not None:
+            stager.stage("tissues", res.tissues)
         sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
         res.bca_measurements, res.vertebrae, _ = bca.build_bca_measurements(
             ct, res.tissues, res.body_parts, res.body_regions, res.total, sx_sy_sz)
@@ -228,14 +271,18 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
 
 def analyze_from_host(ct_host: torch.Tensor, spacing_zyx, zoo: ModelZoo, device=None, **kw) -> dict:
     """The call a user of the Python API makes for one CT held in (pinned) host memory: H2D of the int16 volume,
-    all networks and passes on the device, D2H of the uint8 label maps; returns host tensors + measurement dicts."""
+    all networks and passes on the device, D2H of the uint8 label maps (pinned staging buffers owned by the zoo,
+    copied on a side stream while later networks run); returns host tensors + measurement dicts.  The host tensors
+    are views of the staging buffers: copy them if they must outlive the next call on the same zoo."""
     dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    stager = getattr(zoo, "_stager", None)
+    if stager is None or stager.device != dev:
+        stager = zoo._stager = HostStager(dev)
     ct = ct_host.to(dev, non_blocking=True)
-    res = analyze_volume(ct, spacing_zyx, zoo, **kw)
+    res = analyze_volume(ct, spacing_zyx, zoo, stager=stager, **kw)
     out = {"total_measurements": res.total_measurements, "bca_measurements": res.bca_measurements,
            "vertebrae": res.vertebrae, "timings": res.timings}
+    host = stager.collect()
     for name in ("total", "body_parts", "body_regions", "tissues", "ct_pfav"):
-        t = getattr(res, name)
-        out[name] = t.to("cpu", non_blocking=True) if t is not None else None
-    torch.cuda.synchronize(dev)
+        out[name] = host.get(name)
     return out

@@ -101,3 +101,22 @@ def test_crop_to_nonzero(cuda, small_zoo):
     assert (lab[:4] == 0).all() and (lab[:, :3] == 0).all() and (lab[:, :, 37:] == 0).all()
     ref, _ = _oracle_labels(specs[291], ct[4:, 3:, :37], 0.5, [0])
     assert (lab[4:, 3:, :37] == ref).mean() > 0.99
+
+
+def test_host_api_matches_device_api(cuda, small_zoo):
+    """analyze_from_host (pinned staging buffers, copies on a side stream) returns exactly what analyze_volume
+    leaves on the device, twice in a row on the same zoo (buffer reuse)."""
+    from boa_b200.pipeline import analyze_from_host
+
+    specs, mz = small_zoo
+    for seed in (5, 6):
+        ct = zoo.synthetic_ct((40, 48, 40), seed=seed)
+        ct_host = torch.from_numpy(ct).pin_memory()
+        res = analyze_volume(ct_host.cuda(), (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=True)
+        out = analyze_from_host(ct_host, (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=True)
+        for name in ("total", "body_parts", "body_regions", "tissues", "ct_pfav"):
+            assert out[name].device.type == "cpu" and out[name].is_pinned()
+            assert np.array_equal(out[name].numpy(), getattr(res, name).cpu().numpy()), name
+        from test_oracle_golden import _close
+        _close(res.total_measurements, out["total_measurements"])
+        _close(res.bca_measurements, out["bca_measurements"])
