@@ -59,8 +59,9 @@ inline void prefer_max_smem_carveout(K kernel) {
     }                                        \
   } while (0)
 
-// Co-resident ("thin") launch shapes for the HBM-bound passes of a forward (default on; BOA_B200_THIN=0 restores the
-// occupancy-style launches): see norm_lrelu_thin_kernel in net_simt.cu.
+// Co-resident ("thin") launch shapes for the HBM-bound passes of a forward (opt-in with BOA_B200_THIN=1): see
+// norm_lrelu_thin_kernel in net_simt.cu.  Measured (profiles/r01_overlap.txt): the passes do co-run with the conv
+// CTAs, but both sides then share HBM / L2 and the sum barely moves, while the thin shapes are slower on their own.
 bool thin_passes();
 
 // Number of SMs of the current device (cached) - grids are sized in multiples of it.

@@ -369,7 +369,13 @@ void conv_mma_plan_destroy(ConvMmaPlan* p) {
 
 double conv_mma_plan_macs(const ConvMmaPlan* p) { return p->macs; }
 
-int conv_mma_launch(ConvMmaPlan* pl, cudaStream_t s) {
+int conv_mma_launch(ConvMmaPlan* pl, cudaStream_t s, int nb) {
+  if (nb > 0 && nb != pl->prm.B) {  // partial batch: only the tiles of the first nb items (item index is decoded mod B)
+    ConvMmaParams& p = pl->prm;
+    p.total_tiles = p.total_tiles / p.B * nb;
+    p.B = nb;
+    pl->grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  }
   if (pl->fused) {
     if (pl->nc == 64)
       conv3_fold_kernel<64, true><<<pl->grid, MMA_THREADS_FUSED, pl->smem, s>>>(pl->tmap, pl->prm);

@@ -390,7 +390,13 @@ void conv_taps_plan_destroy(ConvTapsPlan* p) {
   delete p;
 }
 
-int conv_taps_launch(ConvTapsPlan* pl, cudaStream_t s) {
+int conv_taps_launch(ConvTapsPlan* pl, cudaStream_t s, int nb) {
+  if (nb > 0 && nb != pl->prm.B) {  // partial batch: only the tiles of the first nb items (item index is decoded mod B)
+    TapsParams& p = pl->prm;
+    p.total_tiles = p.total_tiles / p.B * nb;
+    p.B = nb;
+    pl->grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
+  }
   if (pl->nc == 128)
     conv_taps_kernel<128><<<pl->grid, TAPS_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
   else

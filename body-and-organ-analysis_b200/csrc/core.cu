@@ -19,7 +19,7 @@ bool thin_passes() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("BOA_B200_THIN");
-    v = (e && atoi(e) == 0) ? 0 : 1;
+    v = (e && atoi(e) != 0) ? 1 : 0;
   }
   return v == 1;
 }

@@ -13,6 +13,7 @@
 // in fp32 and stored as fp16 (the reference's CUDA path runs the same ops under torch.autocast fp16,
 // predict_from_raw_data.py:648).
 #include <string.h>
+#include <algorithm>
 #include <map>
 #include <string>
 #include <vector>
@@ -55,7 +56,7 @@ struct ConvStep {  // conv -> (stats) -> norm + lrelu   |   transposed conv
 // streams, so the HBM-bound passes of one batch overlap the tensor-bound convolutions of the other and kernel
 // boundaries stop draining the machine; only the head (the ordered `logits[sl] += pred * g`) is serialised between
 // lanes with an event.  The streams belong to the workspace, so networks that share it stay ordered.
-constexpr int MAX_LANES = 2;
+constexpr int MAX_LANES = 4;
 struct Workspace {
   std::vector<std::pair<void*, size_t>> bufs[MAX_LANES];
   cudaStream_t stream[MAX_LANES] = {};
@@ -89,7 +90,7 @@ struct boa_net {
   std::vector<void*> allocs;  // per-network memory (weights)
   Workspace* ws = nullptr;    // shared scratch
   Lane lane[MAX_LANES];
-  int n_lanes = 2;
+  int n_lanes = 2;  // BOA_B200_LANES (1..MAX_LANES)
   std::map<std::string, float*> wcache;  // device copies of the fp32 parameters, shared by the lanes
   // head
   float *d_head_w = nullptr, *d_head_b = nullptr;
@@ -109,6 +110,7 @@ struct boa_net {
   double ms_convs = 0, ms_total = 0;
   int64_t n_conv_launches = 0;
   int use_graph = 1;
+  int cur_nb = 0;      // batch items the next launches process (plain launches: the real count; graphs: always B)
   int debug_only = 0;  // profiling aid (BOA_B200_DEBUG_ONLY=conv|thin at creation): launch only one class of kernels
 };
 
@@ -188,7 +190,7 @@ cudaEvent_t next_event(boa_net* net, size_t* idx) {
 
 int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
   const boa_arch& a = net->arch;
-  const int B = net->B;
+  const int B = net->cur_nb > 0 ? net->cur_nb : net->B;
   size_t e0 = 0, e1 = 0;
   const bool time_it = net->timing;
   if (time_it) cudaEventRecord(next_event(net, &e0), s);
@@ -203,7 +205,7 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
                              st.s2d, s);
   }
   if (st.is_tconv) {
-    if (st.kind == STEP_TCONV_TAPS && net->mode == 0) r = conv_taps_launch(st.taps, s);
+    if (st.kind == STEP_TCONV_TAPS && net->mode == 0) r = conv_taps_launch(st.taps, s, B);
     else r = launch_tconv_simt(st.src, B, st.d_w, st.d_bias, st.cin, st.cout, st.stride, st.dst, s);
     if (time_it) {
       cudaEventRecord(next_event(net, &e1), s);
@@ -213,8 +215,8 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
   }
   if (st.kind == STEP_CONV_FIRST)
     r = launch_conv_first(st.src.base, B, st.d_w, st.d_bias, st.cout, st.raw, st.Do, st.Ho, st.Wo, st.d_stats, s);
-  else if (net->mode == 0 && st.kind == STEP_CONV_FOLD) r = conv_mma_launch(st.fold, s);
-  else if (net->mode == 0 && st.kind == STEP_CONV_TAPS) r = conv_taps_launch(st.taps, s);
+  else if (net->mode == 0 && st.kind == STEP_CONV_FOLD) r = conv_mma_launch(st.fold, s, B);
+  else if (net->mode == 0 && st.kind == STEP_CONV_TAPS) r = conv_taps_launch(st.taps, s, B);
   else
     r = launch_conv_simt(st.src_plain, B, st.d_w, st.d_bias, st.cin, st.cout, st.ks, st.stride, st.raw, st.Do, st.Ho,
                          st.Wo, st.d_stats, s);
@@ -243,7 +245,7 @@ int run_body(boa_net* net, Lane& L, cudaStream_t s) {
 // input staging + network body of one batch
 int run_front(boa_net* net, Lane& L, cudaStream_t s) {
   const boa_arch& a = net->arch;
-  if (int r = launch_extract_patches(L.d_call, net->B, a.patch[0], a.patch[1], a.patch[2], L.d_patch, net->input_mode, s))
+  if (int r = launch_extract_patches(L.d_call, net->cur_nb > 0 ? net->cur_nb : net->B, a.patch[0], a.patch[1], a.patch[2], L.d_patch, net->input_mode, s))
     return r;
   return run_body(net, L, s);
 }
@@ -317,7 +319,7 @@ extern "C" int boa_net_create(const boa_arch* arch, int device, int max_batch, b
   net->B = max_batch;
   net->ws = new Workspace();
   const char* nl = getenv("BOA_B200_LANES");
-  net->n_lanes = (nl && atoi(nl) == 1) ? 1 : MAX_LANES;
+  net->n_lanes = nl ? std::max(1, std::min(MAX_LANES, atoi(nl))) : 2;
   if (const char* d = getenv("BOA_B200_DEBUG_ONLY")) net->debug_only = !strcmp(d, "conv") ? 1 : (!strcmp(d, "thin") ? 2 : 0);
   *out = net;
   return BOA_OK;
@@ -668,6 +670,7 @@ extern "C" int boa_net_forward_accumulate(boa_net* net, const float* d_vol, cons
     size_t f0 = 0, f1 = 0;
     if (timing) cudaEventRecord(next_event(net, &f0), s);
     const bool graph = net->use_graph && !timing;
+    net->cur_nb = graph ? net->B : nb;  // plain launches skip the padding items of a partial batch entirely
     if (graph) {
       if (!L.g_body) {
         if (int r = capture_graph(&L.g_body, &L.launches_body, [&](cudaStream_t cs) { return run_front(net, L, cs); }))
@@ -686,7 +689,7 @@ extern "C" int boa_net_forward_accumulate(boa_net* net, const float* d_vol, cons
     if (graph) {
       BOA_CUDA(cudaGraphLaunch(L.g_head, s));
       count_launch(L.launches_head);
-    } else if (int r = run_heads(net, L, net->B, nullptr, s)) {
+    } else if (int r = run_heads(net, L, nb, nullptr, s)) {
       return r;
     }
     if (lanes) {
@@ -718,6 +721,7 @@ extern "C" int boa_net_forward_logits(boa_net* net, const float* d_patches, int 
   for (int p0 = 0; p0 < n_patches; p0 += net->B) {
     const int nb = std::min(net->B, n_patches - p0);
     Lane& L = net->lane[0];
+    net->cur_nb = nb;
     if (nb < net->B) BOA_CUDA(cudaMemsetAsync(L.d_patch, 0, (size_t)net->B * 16 * pv * sizeof(__half), s));
     if (net->input_mode == 2) {
       if (int r = launch_pack_patches_nb9(d_patches + (size_t)p0 * pv, nb, a.patch[0], a.patch[1], a.patch[2],
@@ -794,6 +798,7 @@ extern "C" int boa_net_time_layers(boa_net* net, int cap, float* ms, void* strea
   net->fwd_spans.clear();
   net->ev_used = 0;
   net->timing = true;
+  net->cur_nb = net->B;
   int r = run_body(net, net->lane[0], s);
   net->timing = was;
   if (r) return r;

@@ -77,7 +77,8 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w /*[Cout][Cin_w][27] fp32*/, c
                                   double* d_stats, bool taps_on_k = false, const float* d_in_scale = nullptr,
                                   const float* d_in_shift = nullptr, float slope = 0.01f);
 void conv_mma_plan_destroy(ConvMmaPlan* p);
-int conv_mma_launch(ConvMmaPlan* p, cudaStream_t s);
+// nb: batch items to process (<= the B the plan was created with; the tensors keep their [B]-strided layout)
+int conv_mma_launch(ConvMmaPlan* p, cudaStream_t s, int nb = -1);
 
 // ---- tcgen05 implicit GEMM over an explicit tap list (conv_taps.cu): stride-2 convs on the space-to-depth copy,
 //      transposed convs (one tap, 8 output phases on N), plain 3x3x3.
@@ -89,6 +90,6 @@ enum TapsKind { TAPS_CONV3_S1 = 0, TAPS_CONV3_S2 = 1, TAPS_TCONV2 = 2 };
 ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float* h_bias, int cin_w, int Cout,
                                     const ActView& src, int B, const ActView& dst, double* d_stats);
 void conv_taps_plan_destroy(ConvTapsPlan* p);
-int conv_taps_launch(ConvTapsPlan* p, cudaStream_t s);
+int conv_taps_launch(ConvTapsPlan* p, cudaStream_t s, int nb = -1);
 
 }  // namespace boa

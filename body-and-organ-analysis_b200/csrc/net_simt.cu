@@ -2,6 +2,7 @@
 // reference kernels (direct conv / transposed conv / head).  The SIMT convs exist as an on-device cross-check for
 // the tcgen05 kernels and as the implementation of ops that have not moved to tensor cores yet; they are selected
 // explicitly, never as a silent fallback.
+#include <stdlib.h>
 #include <algorithm>
 #include "net_kernels.cuh"
 
@@ -557,6 +558,143 @@ head_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off,
   }
 }
 
+// ------------------------------------------------------------------------------------------ head on mma.sync
+// Same op as head_kernel for CIN = 32 and C <= 32 (every BOA network): the 32 x C product runs on the tensor cores
+// through mma.sync.m16n8k16 (fp16 operands - the activations ARE fp16 and the weights are fp16-representable - fp32
+// accumulation), which leaves the kernel with what it is bound by: the fp32 read-modify-write of the C logits planes.
+// (tcgen05 is not an option here: the accumulators of a 1x1x1 conv are consumed once, and a TMEM round trip per 128
+// voxels buys nothing for K = 32.)
+// A warp step covers 32 consecutive voxels (two m16 tiles).  The MMA's K index is a free permutation of the input
+// channels as long as both operands agree, so it is chosen such that thread (g = lane / 4, t = lane % 4) needs exactly
+// the 8 channels of channel group t of its rows - one 16-byte load per row straight from the C8 tensor:
+//   k-step s, k = 2t + j      <->  channel 8t + 4s + j        (j = 0, 1)
+//   k-step s, k = 2t + 8 + j  <->  channel 8t + 4s + 2 + j
+__device__ __forceinline__ void mma_m16n8k16(float (&d)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                             uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+template <int NT>  // n-tiles of 8 classes: C <= 8 * NT
+__global__ void __launch_bounds__(128, 4)
+head_mma_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off, int b, int D, int H, int W,
+                const float* __restrict__ w, const float* __restrict__ bias, int C, float* __restrict__ logits_b,
+                const FwdCall* __restrict__ call, const float* __restrict__ in_scale,
+                const float* __restrict__ in_shift, float slope) {
+  __shared__ uint2 sB[NT][2][32];  // B fragments: [n-tile][k-step][lane] = {b0 (k = 2t, 2t+1), b1 (k = 2t+8, 2t+9)}
+  __shared__ float sbias[8 * NT];
+  __shared__ float snorm[64];      // [32] scale, [32] shift of batch item b (fused normalisation of the input)
+  // per-warp transpose buffer [class][voxel]: the MMA leaves a thread with 2 classes x 4 voxels per n-tile, the
+  // accumulate wants thread = voxel so that every class plane is touched 128 contiguous bytes at a time.  Row stride
+  // 36: bank = 4 * class + voxel, conflict-free for the fragment writes (class = c0 + 2t, voxel = v0 + g -> 8t + g)
+  // and for the row reads (voxel = lane).
+  __shared__ float sT[4][8 * NT][36];
+  if (in_scale && threadIdx.x < 64)
+    snorm[threadIdx.x] = threadIdx.x < 32 ? in_scale[(size_t)b * 32 + threadIdx.x] : in_shift[(size_t)b * 32 + threadIdx.x - 32];
+  for (int i = threadIdx.x; i < NT * 64; i += blockDim.x) {
+    const int ln = i & 31, ks = (i >> 5) & 1, nt = i >> 6;
+    const int cls = nt * 8 + (ln >> 2), ch = 8 * (ln & 3) + 4 * ks;
+    __half2 lo = __floats2half2_rn(0.f, 0.f), hi = lo;
+    if (cls < C) {
+      lo = __floats2half2_rn(w[cls * 32 + ch], w[cls * 32 + ch + 1]);
+      hi = __floats2half2_rn(w[cls * 32 + ch + 2], w[cls * 32 + ch + 3]);
+    }
+    sB[nt][ks][ln] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+  for (int i = threadIdx.x; i < 8 * NT; i += blockDim.x) sbias[i] = i < C ? bias[i] : 0.f;
+  __syncthreads();
+  float* __restrict__ acc = nullptr;
+  const float* __restrict__ gauss = nullptr;
+  int o0 = 0, o1 = 0, o2 = 0, d1 = 0, d2 = 0;
+  size_t vol_voxels = 0;
+  if (!logits_b) {
+    if (b >= call->n_valid) return;
+    acc = call->acc; gauss = call->gaussian;
+    o0 = call->origins[b][0]; o1 = call->origins[b][1]; o2 = call->origins[b][2];
+    d1 = call->d1; d2 = call->d2;
+    vol_voxels = (size_t)call->d0 * d1 * d2;
+  }
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, g = lane >> 2, t = lane & 3;
+  const int vox = D * H * W;
+  const float* sc = snorm + 8 * t;  // scale / shift of this thread's 8 channels (broadcast reads)
+  const float* sh = snorm + 32 + 8 * t;
+  float (*tb)[36] = sT[warp];
+  const uint4* __restrict__ src = in + ((size_t)b * in_groups_total + in_group_off + t) * vox;
+  const size_t cstride = logits_b ? (size_t)vox : vol_voxels;
+  const int warps = gridDim.x * (blockDim.x >> 5);
+  for (int v0 = (blockIdx.x * (blockDim.x >> 5) + warp) * 32; v0 < vox; v0 += warps * 32) {
+    // ---- this thread as an accumulate lane: voxel v0 + lane, every class.  Issue its loads first.
+    const int v = v0 + lane;
+    const bool ok = v < vox;
+    float* dst = nullptr;
+    float gw = 0.f;
+    float old[8 * NT];
+    if (ok) {
+      if (logits_b) {
+        dst = logits_b + v;
+      } else {
+        const int k = v % W, j = (v / W) % H, ii = v / (W * H);
+        dst = acc + ((size_t)(o0 + ii) * d1 + (o1 + j)) * d2 + (o2 + k);
+        gw = __ldg(gauss + v);
+#pragma unroll
+        for (int c = 0; c < 8 * NT; ++c)
+          if (c < C) old[c] = __ldcg(dst + (size_t)c * cstride);
+      }
+    }
+    // ---- this thread as an MMA lane: rows v0 + g + 8 i, i = 0..3 (m-tile i / 2, upper half i & 1), channel group t
+    uint32_t a[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int vr = v0 + g + 8 * i;
+      uint4 raw = make_uint4(0u, 0u, 0u, 0u);
+      if (vr < vox) raw = __ldg(src + vr);
+      if (in_scale) {
+        // RAW output of the last conv: its InstanceNorm affine + LeakyReLU and the fp16 rounding of the standalone
+        // pass (same operations as norm_lrelu_kernel)
+        float f[8];
+        unpack8(raw, f);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const float z = __fadd_rn(__fmul_rn(f[e], sc[e]), sh[e]);
+          f[e] = z > 0.f ? z : __fmul_rn(z, slope);
+        }
+        raw = pack8(f);
+      }
+      a[i][0] = raw.x; a[i][1] = raw.y; a[i][2] = raw.z; a[i][3] = raw.w;
+    }
+    __syncwarp();  // the previous step's reads of the transpose buffer are done
+#pragma unroll
+    for (int m = 0; m < 2; ++m)
+#pragma unroll
+      for (int nt = 0; nt < NT; ++nt) {
+        float d[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          const uint2 bf = sB[nt][ks][lane];
+          mma_m16n8k16(d, a[2 * m][2 * ks], a[2 * m + 1][2 * ks], a[2 * m][2 * ks + 1], a[2 * m + 1][2 * ks + 1], bf.x,
+                       bf.y);
+        }
+        // d[0], d[1]: row 16 m + g, classes nt*8 + 2t, +1;  d[2], d[3]: row 16 m + g + 8
+        tb[nt * 8 + 2 * t][16 * m + g] = d[0];
+        tb[nt * 8 + 2 * t + 1][16 * m + g] = d[1];
+        tb[nt * 8 + 2 * t][16 * m + g + 8] = d[2];
+        tb[nt * 8 + 2 * t + 1][16 * m + g + 8] = d[3];
+      }
+    __syncwarp();
+    if (ok) {
+#pragma unroll
+      for (int c = 0; c < 8 * NT; ++c) {
+        if (c < C) {
+          const float sres = tb[c][lane] + sbias[c];
+          if (logits_b) dst[(size_t)c * cstride] = sres;
+          else __stcg(dst + (size_t)c * cstride, __fadd_rn(old[c], __fmul_rn(sres, gw)));
+        }
+      }
+    }
+  }
+}
+
 // ================================================================================================ launchers
 int launch_pack_patches_nb9(const float* d_patches, int n, int p0, int p1, int p2, __half* d_out, cudaStream_t s) {
   const size_t total = (size_t)n * p0 * p1 * p2;
@@ -589,6 +727,15 @@ int launch_pack_patches_plain(const float* d_patches, size_t total, __half* d_ou
   pack_patches_plain_kernel<<<grid_for(total, 256), 256, 0, s>>>(d_patches, total, d_out);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
+}
+
+static bool head_on_mma() {  // BOA_B200_HEAD_FMA=1 selects the FP32-FMA head (cross-check of the mma.sync head)
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("BOA_B200_HEAD_FMA");
+    v = (e && atoi(e) != 0) ? 0 : 1;
+  }
+  return v == 1;
 }
 
 bool conv_first_supported(int Cout) { return Cout == 32 || Cout == 16 || Cout == 8; }
@@ -683,6 +830,25 @@ int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias
     return BOA_ERR_UNSUPPORTED;
   }
   const size_t vox = src.voxels();
+  if (Cin == 32 && C <= 32 && head_on_mma()) {
+    const int nt = (C + 7) / 8;
+    // four blocks of 128 threads per SM (<= 128 registers), each thread with up to 8 * NT + 5 loads in flight
+    const int grid = (int)std::min<size_t>((vox + 127) / 128, (size_t)sm_count() * 4);
+    const uint4* in4 = reinterpret_cast<const uint4*>(src.base);
+#define BOA_HEAD_MMA(NT_)                                                                                            \
+  BOA_CARVEOUT_ONCE(head_mma_kernel<NT_>);                                                                             \
+  head_mma_kernel<NT_><<<grid, 128, 0, s>>>(in4, src.groups_total, src.group_off, b, src.D, src.H, src.W, d_w, d_bias, \
+                                            C, d_logits_b, d_call, d_in_scale, d_in_shift, slope)
+    switch (nt) {
+      case 1: BOA_HEAD_MMA(1); break;
+      case 2: BOA_HEAD_MMA(2); break;
+      case 3: BOA_HEAD_MMA(3); break;
+      default: BOA_HEAD_MMA(4); break;
+    }
+#undef BOA_HEAD_MMA
+    BOA_CHECK_LAUNCH();
+    return BOA_OK;
+  }
   const size_t smem = ((size_t)C * Cin + C + 2 * Cin) * sizeof(float);
   const uint4* in = reinterpret_cast<const uint4*>(src.base);
   // thin mode: 128 threads x <= 128 registers per SM (see norm_lrelu_thin_kernel), one persistent block per SM

@@ -274,7 +274,7 @@ def analyze_from_host(ct_host: torch.Tensor, spacing_zyx, zoo: ModelZoo, device=
     all networks and passes on the device, D2H of the uint8 label maps (pinned staging buffers owned by the zoo,
     copied on a side stream while later networks run); returns host tensors + measurement dicts.  The host tensors
     are views of the staging buffers: copy them if they must outlive the next call on the same zoo."""
-    dev = torch.device(device if device is not None else ("cuda", torch.cuda.current_device()))
+    dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
     stager = getattr(zoo, "_stager", None)
     if stager is None or stager.device != dev:
         stager = zoo._stager = HostStager(dev)
