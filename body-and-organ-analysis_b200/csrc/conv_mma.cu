@@ -16,6 +16,7 @@
 //   * Persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2-5
 //     epilogue (TMEM -> regs, +bias, InstanceNorm sum / sum^2, fp16 C8 store).  2-stage smem ring over K chunks of
 //     16 input channels; TMEM accumulators double-buffered when zt*NC <= 256.
+#include <stdlib.h>
 #include <vector>
 #include "net_kernels.cuh"
 #include "conv_epilogue.cuh"
@@ -43,6 +44,9 @@ struct ConvMmaParams {
   const float* in_shift;
   int in_channels;
   float slope;
+  int stages;      // shared-memory ring depth of the A operand (2..4)
+  int b_resident;  // 1: the weights of ALL K chunks stay in shared memory for the whole kernel (n_ntiles == 1), the
+                   //    ring carries only the activation tiles
   int tmap_merged;  // tensor map built with the (channel, x) dimensions merged (tmap.cuh)
   int ntaps;  // 9: (dy,dx) taps as address shifts; 1: the in-plane taps already sit on K (first layer), centre only
 };
@@ -56,6 +60,42 @@ __device__ __forceinline__ void decode_tile(int t, const ConvMmaParams& p, int& 
   nt = t / p.B;
 }
 
+// MMAs of one K chunk (16 input channels) of one tile: input z-plane i of the halo box feeds output slots i-2 .. i
+// with the weight blocks dz = 2, 1, 0 (one MMA, N = 3*NC, three consecutive TMEM slots); the planes at the box ends
+// feed fewer slots.  ZT > 0: the z-tile height is a compile-time constant and the plane loop is fully unrolled, so
+// every descriptor / column / instruction-descriptor offset is an immediate - the single issuing thread was spending
+// ~40 % of its time on the dependent uniform-datapath arithmetic of the runtime version (ncu source view,
+// profiles/r01_fold_issue.txt).  ZT == 0: runtime z-tile (small volumes).
+template <int NC, int ZT>
+__device__ __forceinline__ void issue_chunk(uint64_t a_base, uint64_t b_base, uint32_t dcol0, bool first_kc, bool taps9,
+                                            int zt_rt) {
+  constexpr uint32_t BG16 = 96u * NC / 16u;  // one (dy,dx) weight block, in 16-byte units
+  const int zt = ZT > 0 ? ZT : zt_rt;
+#pragma unroll
+  for (int i = 0; i < (ZT > 0 ? ZT + 2 : 18); ++i) {
+    if (ZT == 0 && i >= zt + 2) break;
+    const int lo = i - 2 > 0 ? i - 2 : 0, hi = i < zt - 1 ? i : zt - 1;
+    const int jlo = lo - (i - 2);         // first valid dz block (blocks are ordered dz = 2,1,0)
+    const int n = hi - lo + 1;
+    const uint64_t ad = a_base + (uint64_t)(i * SLAB);
+    const uint64_t bd = b_base + (uint64_t)(jlo * NC);
+    const uint32_t dcol = dcol0 + (uint32_t)(lo * NC);
+    const uint32_t idesc = umma_idesc_f16(128, (uint32_t)(n * NC));
+    if (first_kc && i <= zt - 1) {
+      // slot i (= hi) receives its first contribution now: overwrite it, accumulate into the slots below
+      if (n > 1) umma_f16(dcol, ad, bd, umma_idesc_f16(128, (uint32_t)((n - 1) * NC)), 1u);
+      umma_f16(dcol0 + (uint32_t)(hi * NC), ad, bd + (uint64_t)((n - 1) * NC), umma_idesc_f16(128, NC), 0u);
+    } else {
+      umma_f16(dcol, ad, bd, idesc, 1u);
+    }
+    if (taps9) {
+#pragma unroll
+      for (int g = 1; g < 9; ++g)
+        umma_f16(dcol, ad + (uint64_t)((g / 3) * XB + (g % 3)), bd + (uint64_t)(g * BG16), idesc, 1u);
+    }
+  }
+}
+
 template <int NC, bool FUSE>
 __global__ void __launch_bounds__(FUSE ? MMA_THREADS_FUSED : MMA_THREADS, 1)
 conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams p) {
@@ -64,25 +104,33 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
   const uint32_t a_bytes = 2u * zb * SLAB * 16u;
   constexpr uint32_t b_group = 96u * NC;  // [2 kchunks][3*NC rows][16 B]
   const uint32_t b_bytes = (uint32_t)p.ntaps * b_group;
-  const uint32_t stage_bytes = a_bytes + b_bytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + 2 * stage_bytes);
-  uint64_t* full = bars;        // [2] TMA -> MMA
-  uint64_t* empty = bars + 2;   // [2] MMA -> TMA
-  uint64_t* tfull = bars + 4;   // [2] MMA -> epilogue
-  uint64_t* tempty = bars + 6;  // [2] epilogue -> MMA
-  uint64_t* ready = bars + 8;   // [2] transform warps -> MMA (FUSE only)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 10);
+  // smem: [resident weights: kc_count * b_bytes (b_resident only)] [stages x (A tile [+ B chunk])] [barriers]
+  const uint32_t stage_bytes = a_bytes + (p.b_resident ? 0u : b_bytes);
+  const uint32_t bres_bytes = p.b_resident ? (uint32_t)p.kc_count * b_bytes : 0u;
+  uint8_t* const ring = smem + bres_bytes;
+  const int nstage = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * stage_bytes);
+  uint64_t* full = bars;         // [4] TMA -> MMA
+  uint64_t* empty = bars + 4;    // [4] MMA -> TMA
+  uint64_t* tfull = bars + 8;    // [2] MMA -> epilogue
+  uint64_t* tempty = bars + 10;  // [2] epilogue -> MMA
+  uint64_t* ready = bars + 12;   // [4] transform warps -> MMA (FUSE only)
+  uint64_t* bfull = bars + 16;   // [1] resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nbuf = (p.zt * NC <= 256) ? 2 : 1;
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
       mbar_init(&ready[i], 128);
     }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(bfull, 1);
     fence_barrier_init();
     tma_prefetch_desc(&tmapA);
   }
@@ -97,70 +145,68 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
 
   if (warp == 0) {
     // ===================================================================== TMA producer
-    uint32_t it = 0;
+    if (p.b_resident && elect_one()) {  // n_ntiles == 1: one weight set for every tile of this CTA
+      mbar_arrive_expect_tx(bfull, bres_bytes);
+      for (int kc = 0; kc < p.kc_count; ++kc)
+        bulk_load(smem + (size_t)kc * b_bytes, reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)kc * b_bytes,
+                  b_bytes, bfull);
+    }
+    __syncwarp();
+    int st = 0;
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int nt, b, tz, ty, tx;
       decode_tile(tile, p, nt, b, tz, ty, tx);
-      for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
-        const int st = it & 1;
-        mbar_wait(&empty[st], ((it >> 1) & 1) ^ 1);
+      for (int kc = 0; kc < p.kc_count; ++kc) {
+        mbar_wait(&empty[st], ph ^ 1);
         if (elect_one()) {
-          uint8_t* sa = smem + st * stage_bytes;
+          uint8_t* sa = ring + (size_t)st * stage_bytes;
           mbar_arrive_expect_tx(&full[st], stage_bytes);
           tma_load_c8(sa, &tmapA, &full[st], p.tmap_merged, tx * TILE_X - 1, ty * TILE_Y - 1, tz * p.zt - 1,
                       b * p.in_groups_total + p.in_group_off + 2 * kc);
-          bulk_load(sa + a_bytes,
-                    reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)(nt * p.kc_count + kc) * b_bytes, b_bytes,
-                    &full[st]);
+          if (!p.b_resident)
+            bulk_load(sa + a_bytes,
+                      reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)(nt * p.kc_count + kc) * b_bytes, b_bytes,
+                      &full[st]);
         }
         __syncwarp();
+        if (++st == nstage) { st = 0; ph ^= 1; }
       }
     }
   } else if (warp == 1) {
     // ===================================================================== MMA issuer (ONE thread runs the loop)
     if (elect_one()) {
-      uint32_t it = 0, tcount = 0;
+      uint32_t tcount = 0;
+      int st = 0;
+      uint32_t ph = 0;
+      if (p.b_resident) {
+        mbar_wait(bfull, 0);
+        tc_fence_after();
+      }
       const uint32_t a_lbo = (uint32_t)zb * SLAB * 16u;  // next channel group (K chunk of 8)
       // descriptors with a zero address field; tap / slab / row-block shifts are added to the low word (16-byte units;
       // shared memory is < 256 KB so the 14-bit address field never carries)
       const uint64_t a_desc0 = umma_desc(0, a_lbo, XB * 16u);
       const uint64_t b_desc0 = umma_desc(0, 3u * NC * 16u, 128u);
-      constexpr uint32_t BG16 = b_group / 16u;           // one (dy,dx) weight block, in 16-byte units
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
         const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0;
         const uint32_t tph = nbuf == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
         mbar_wait(&tempty[buf], tph ^ 1);
         tc_fence_after();
         const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
-        for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
-          const int st = it & 1;
-          mbar_wait(FUSE ? &ready[st] : &full[st], (it >> 1) & 1);
+        for (int kc = 0; kc < p.kc_count; ++kc) {
+          mbar_wait(FUSE ? &ready[st] : &full[st], ph);
           tc_fence_after();
-          const uint32_t a0 = smem_u32(smem + st * stage_bytes);
+          const uint32_t a0 = smem_u32(ring + (size_t)st * stage_bytes);
           const uint64_t a_base = a_desc0 + (uint64_t)(a0 >> 4);
-          const uint64_t b_base = b_desc0 + (uint64_t)((a0 + a_bytes) >> 4);
-          for (int i = 0; i < zb; ++i) {          // input z-plane (slab) i feeds output slots i-2 .. i
-            const int lo = max(0, i - 2), hi = min(p.zt - 1, i);
-            const int jlo = lo - (i - 2);         // first valid dz block (blocks are ordered dz = 2,1,0)
-            const int n = hi - lo + 1;
-            const uint64_t ad = a_base + (uint64_t)(i * SLAB + (p.ntaps == 1 ? XB + 1 : 0));
-            const uint64_t bd = b_base + (uint64_t)(jlo * NC);
-            const uint32_t dcol = dcol0 + (uint32_t)(lo * NC);
-            const uint32_t idesc = umma_idesc_f16(128, (uint32_t)(n * NC));
-            if (kc == 0 && i <= p.zt - 1) {
-              // slot i (= hi) receives its first contribution now: overwrite it, accumulate into the slots below
-              if (n > 1) umma_f16(dcol, ad, bd, umma_idesc_f16(128, (uint32_t)((n - 1) * NC)), 1u);
-              umma_f16(dcol0 + (uint32_t)(hi * NC), ad, bd + (uint64_t)((n - 1) * NC), umma_idesc_f16(128, NC), 0u);
-            } else {
-              umma_f16(dcol, ad, bd, idesc, 1u);
-            }
-            if (p.ntaps == 9) {
-#pragma unroll
-              for (int g = 1; g < 9; ++g)
-                umma_f16(dcol, ad + (uint64_t)((g / 3) * XB + (g % 3)), bd + (uint64_t)(g * BG16), idesc, 1u);
-            }
-          }
+          const uint64_t b_base =
+              b_desc0 + (uint64_t)((p.b_resident ? smem_u32(smem) + (uint32_t)kc * b_bytes : a0 + a_bytes) >> 4);
+          const uint64_t a_tap0 = a_base + (uint64_t)(p.ntaps == 1 ? XB + 1 : 0);
+          if (p.zt == 8) issue_chunk<NC, 8>(a_tap0, b_base, dcol0, kc == 0, p.ntaps == 9, 8);
+          else if (p.zt == 4) issue_chunk<NC, 4>(a_tap0, b_base, dcol0, kc == 0, p.ntaps == 9, 4);
+          else issue_chunk<NC, 0>(a_tap0, b_base, dcol0, kc == 0, p.ntaps == 9, p.zt);
           umma_commit(&empty[st]);   // smem stage reusable once these MMAs retire
+          if (++st == nstage) { st = 0; ph ^= 1; }
         }
         umma_commit(&tfull[buf]);     // accumulators of this tile complete
       }
@@ -172,13 +218,13 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
     // volume stays zero: padding applies to the ACTIVATED tensor).  Same fp32 operations as norm_lrelu_kernel.
     const int tid = threadIdx.x - 192;
     const int per_group = zb * SLAB;
-    uint32_t it = 0;
+    int st = 0;
+    uint32_t ph = 0;
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
       int nt, b, tz, ty, tx;
       decode_tile(tile, p, nt, b, tz, ty, tx);
       const int z0 = tz * p.zt - 1, y0 = ty * TILE_Y - 1, x0 = tx * TILE_X - 1;
-      for (int kc = 0; kc < p.kc_count; ++kc, ++it) {
-        const int st = it & 1;
+      for (int kc = 0; kc < p.kc_count; ++kc) {
         float a[2][8], sh[2][8];
 #pragma unroll
         for (int g = 0; g < 2; ++g) {
@@ -190,8 +236,8 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
           sh[g][0] = s0.x; sh[g][1] = s0.y; sh[g][2] = s0.z; sh[g][3] = s0.w;
           sh[g][4] = s1.x; sh[g][5] = s1.y; sh[g][6] = s1.z; sh[g][7] = s1.w;
         }
-        mbar_wait(&full[st], (it >> 1) & 1);
-        uint4* tile_a = reinterpret_cast<uint4*>(smem + st * stage_bytes);
+        mbar_wait(&full[st], ph);
+        uint4* tile_a = reinterpret_cast<uint4*>(ring + (size_t)st * stage_bytes);
         for (int pos = tid; pos < per_group; pos += 128) {
           const int z = pos / SLAB, r = pos - z * SLAB, y = r / XB, x = r - y * XB;
           const int gz = z0 + z, gy = y0 + y, gx = x0 + x;
@@ -214,6 +260,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
         }
         fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
         mbar_arrive(&ready[st]);
+        if (++st == nstage) { st = 0; ph ^= 1; }
       }
     }
   } else {
@@ -343,8 +390,26 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
     conv_mma_plan_destroy(pl);
     return nullptr;
   }
-  const size_t stage = 2 * (size_t)(zt + 2) * SLAB * 16 + (size_t)ntaps * 96 * (size_t)NC;
-  pl->smem = 2 * stage + 128;
+  // Weights resident when one weight set serves every tile (Cout == NC) and it fits next to >= 2 activation stages:
+  // the ring then carries 58 KB instead of 85 KB per K chunk (the convs are bound by what TMA can bring into an SM)
+  // and, for Cin = 32, a third stage fits.  BOA_B200_BRES=0 disables it.
+  const size_t a_stage = 2 * (size_t)(zt + 2) * SLAB * 16, b_chunk = (size_t)ntaps * 96 * (size_t)NC;
+  const size_t smem_cap = (size_t)MAX_DYN_SMEM - 256;
+  const char* bres_env = getenv("BOA_B200_BRES");
+  p.b_resident = (p.n_ntiles == 1 && !pl->fused && !(bres_env && atoi(bres_env) == 0) &&
+                  p.kc_count * b_chunk + 2 * a_stage <= smem_cap) ? 1 : 0;
+  const size_t stage = a_stage + (p.b_resident ? 0 : b_chunk);
+  const size_t fixed = p.b_resident ? p.kc_count * b_chunk : 0;
+  int stages = (int)((smem_cap - fixed) / stage);
+  stages = stages > 4 ? 4 : stages;
+  if (pl->fused) stages = 2;
+  if (stages < 2) {
+    set_error("conv_mma: two stages of %zu bytes do not fit in shared memory", stage);
+    conv_mma_plan_destroy(pl);
+    return nullptr;
+  }
+  p.stages = stages;
+  pl->smem = fixed + (size_t)stages * stage + 192;
   cudaError_t e = cudaSuccess;
   for (const void* fn : {(const void*)conv3_fold_kernel<64, false>, (const void*)conv3_fold_kernel<32, false>,
                          (const void*)conv3_fold_kernel<64, true>, (const void*)conv3_fold_kernel<32, true>}) {

@@ -174,6 +174,45 @@ class VolumeResult:
     timings: dict = field(default_factory=dict)
 
 
+class _Background:
+    """Run fn() on a helper thread with its own CUDA stream, ordered after everything enqueued so far on the caller's
+    stream; join() re-raises what fn raised, makes the caller's stream wait for the side stream and returns the host
+    seconds fn took.  `inputs` are tensors produced on the caller's stream that fn reads."""
+
+    def __init__(self, device, fn, inputs=()):
+        import threading
+        import time
+
+        self.device = torch.device(device)
+        self.stream = torch.cuda.Stream(self.device)
+        ready = torch.cuda.Event()
+        ready.record(torch.cuda.current_stream(self.device))
+        for t in inputs:
+            t.record_stream(self.stream)
+        self.error = None
+        self.seconds = 0.0
+
+        def run():
+            t0 = time.perf_counter()
+            try:
+                with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
+                    self.stream.wait_event(ready)
+                    fn()
+            except BaseException as e:  # noqa: BLE001 - re-raised by join()
+                self.error = e
+            self.seconds = time.perf_counter() - t0
+
+        self.thread = threading.Thread(target=run, name="boa-b200-measurements", daemon=True)
+        self.thread.start()
+
+    def join(self) -> float:
+        self.thread.join()
+        torch.cuda.current_stream(self.device).wait_stream(self.stream)
+        if self.error is not None:
+            raise self.error
+        return self.seconds
+
+
 class HostStager:
     """Device -> host staging of the label maps for callers that hold host buffers: each map is copied into a pinned
     buffer on a side stream as soon as it is final, so the transfer overlaps the networks that follow (the reference
@@ -219,6 +258,7 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
     models = set(models)
     if "bca" in models:
         models.add("total")  # compute/config.py:54-55
+    background = None
     ev = lambda: torch.cuda.Event(enable_timing=True)
     marks = [("start", ev())]
     marks[-1][1].record()
@@ -236,11 +276,23 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         if stager is not None:
             stager.stage("total", res.total)
         sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
-        res.total_measurements, res.ct_pfav = compute_measurements_on_device(
-            ct, {"total": res.total}, sx_sy_sz, cnr_adjustment, return_ct_pfav_mask=True)
-        mark("total_measurements")
-        if stager is not None:
-            stager.stage("ct_pfav", res.ct_pfav)
+
+        def total_measurements():
+            res.total_measurements, res.ct_pfav = compute_measurements_on_device(
+                ct, {"total": res.total}, sx_sy_sz, cnr_adjustment, return_ct_pfav_mask=True)
+
+        # `total-measurements.json` needs only the CT and the `total` label map, so it CAN run on a side stream driven
+        # by a helper thread while the body-composition networks follow (BOA_B200_ASYNC_MEAS=1).  Measured on B200: a
+        # loss - the helper's 60 ms of Python compete with the launch loop of the networks for the GIL (bca_nets
+        # +70 ms on 1 GPU, +350 ms next to the NCCL exchange on 2), so it is off by default.
+        run_async = bool(models & {"bca", "body_parts", "body_regions"}) and os.environ.get("BOA_B200_ASYNC_MEAS", "0") == "1"
+        if run_async:
+            background = _Background(ct.device, total_measurements, (ct, res.total))
+        else:
+            total_measurements()
+            mark("total_measurements")
+            if stager is not None:
+                stager.stage("ct_pfav", res.ct_pfav)
     if "bca" in models or "body_parts" in models or "body_regions" in models:
         ct5 = resample_thickness(ct, spacing_zyx[0], 5.0)
         mark("resample")
@@ -255,6 +307,11 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         if stager is not None:
             stager.stage("body_regions", res.body_regions)
         mark("bca_nets")
+    if background is not None:
+        res.timings["total_measurements_async_host"] = background.join()
+        mark("total_measurements_join")
+        if stager is not None:
+            stager.stage("ct_pfav", res.ct_pfav)
     if "bca" in models:
         res.tissues = bca.subclassify_tissues(ct, res.body_regions)
         if stager is not None:
