@@ -9,7 +9,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libboa_b200.so")
 
 BOA_MAX_STAGES = 8
-BOA_DT_I16, BOA_DT_F32 = 0, 1
+BOA_DT_I16, BOA_DT_F32, BOA_DT_F64 = 0, 1, 2
 
 
 class BoaArch(C.Structure):
@@ -64,6 +64,8 @@ _SIGS = {
                                               C.c_int, _P, _P]),
     "boa_resample_z_cubic": (C.c_int, [_P, C.c_int, C.c_int, C.c_size_t, C.c_int, _P, _P, _P]),
     "boa_resample_z_nearest_u8": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_int, _P, _P]),
+    "boa_resample_axis_cubic": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.c_int, _P, _P, C.c_int, _P]),
+    "boa_resample_nearest_u8": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P]),
     "boa_add_slab": (C.c_int, [_P, _P, C.c_size_t, _P]),
 }
 EXPORTS = sorted(_SIGS)

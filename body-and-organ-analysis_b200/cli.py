@@ -43,10 +43,8 @@ def run(argv=None) -> None:
     models = resolve_models(args.models, strict=True)
     fast_bca = args.fast_bca if args.fast_bca is not None else env_bool("FAST_BCA")
     fast_total = args.fast_total if args.fast_total is not None else env_bool("FAST_TOTAL")
-    if fast_total:
-        raise NotImplementedError("--fast-total (3 mm model 297) needs 3-D resampling, not on the GPU path yet")
     from .commands import analyze_ct
-    out, stats = analyze_ct(args.input_image, args.output_dir, models=models, fast_bca=fast_bca,
+    out, stats = analyze_ct(args.input_image, args.output_dir, models=models, fast_bca=fast_bca, fast_total=fast_total,
                             cnr_adjustment=bool(args.cnr_adjustment), device=device,
                             recompute=args.force_recompute, weights_root=args.weights or os.environ.get("TOTALSEG_WEIGHTS_PATH"))
     logging.getLogger(__name__).info("results in %s: %s", out, stats)

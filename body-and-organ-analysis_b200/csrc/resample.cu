@@ -89,6 +89,106 @@ nearest_z_kernel(const uint8_t* __restrict__ in, int z_in, size_t plane, int z_o
   }
 }
 
+
+// ------------------------------------------------------------------------------------------ 3-D resampling
+// change_spacing(img, [1.5]*3, order=3) (_external/totalsegmentator/nnunet.py:466-470 -> resampling.py:129-222):
+// scipy's order-3 zoom is a tensor product, so it is applied as three 1-D passes (prefilter + evaluation along one
+// axis each, fp64 intermediates, the same edge padding / mirror initialisation per axis as above); only the last pass
+// truncates to integers.  A volume is addressed as [outer][n][inner] around the axis being resampled; one thread owns
+// one line (outer, inner), neighbouring threads neighbouring `inner` => coalesced for the z and y passes (the x pass,
+// inner = 1, walks contiguous lines and runs last, on the smallest intermediate).
+template <typename T>
+__device__ __forceinline__ double load_as_double(const T* p, size_t i) { return (double)p[i]; }
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+spline_prefilter_axis_kernel(const T* __restrict__ in, size_t outer, int n_in, size_t inner, double* __restrict__ c) {
+  const size_t line = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (line >= outer * inner) return;
+  const size_t o = line / inner, i0 = line - o * inner;
+  const T* src = in + o * (size_t)n_in * inner + i0;
+  const int n = n_in + 2 * NPAD;
+  double* dst = c + o * (size_t)n * inner + i0;
+  const double z1 = sqrt(3.0) - 2.0;
+  const double gain = (1.0 - z1) * (1.0 - 1.0 / z1);
+  auto sample = [&](int i) -> double {
+    int k = i - NPAD;
+    k = k < 0 ? 0 : (k >= n_in ? n_in - 1 : k);
+    return load_as_double(src, (size_t)k * inner) * gain;
+  };
+  double c0 = sample(0);
+  {
+    double zi = z1;
+    const int horizon = n - 1 < 80 ? n - 1 : 80;
+    for (int i = 1; i < horizon; ++i) {
+      c0 += zi * sample(i);
+      zi *= z1;
+    }
+  }
+  double prev = c0;
+  dst[0] = prev;
+  for (int i = 1; i < n; ++i) {
+    prev = sample(i) + z1 * prev;
+    dst[(size_t)i * inner] = prev;
+  }
+  const double cn2 = dst[(size_t)(n - 2) * inner];
+  double next = (z1 / (z1 * z1 - 1.0)) * (z1 * cn2 + prev);
+  dst[(size_t)(n - 1) * inner] = next;
+  for (int i = n - 2; i >= 0; --i) {
+    next = z1 * (next - dst[(size_t)i * inner]);
+    dst[(size_t)i * inner] = next;
+  }
+}
+
+// out_mode 0: fp64 (intermediate pass);  1: int16, truncated toward zero;  2: int32, truncated toward zero
+__global__ void __launch_bounds__(256)
+spline_eval_axis_kernel(const double* __restrict__ c, size_t outer, int n_in, size_t inner, int n_out, void* __restrict__ out,
+                        int out_mode) {
+  const size_t total = outer * (size_t)n_out * inner;
+  const double zoom = n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 1.0;
+  const int n = n_in + 2 * NPAD;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const size_t i0 = i % inner;
+    const int k = (int)((i / inner) % (size_t)n_out);
+    const size_t o = i / (inner * (size_t)n_out);
+    const double cc = (double)k * zoom + (double)NPAD;
+    const double fl = floor(cc);
+    const double y = cc - fl, z = 1.0 - y;
+    const double w1 = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
+    const double w2 = (z * z * (z - 2.0) * 3.0 + 4.0) / 6.0;
+    const double w0 = z * z * z / 6.0;
+    const double w3 = 1.0 - w0 - w1 - w2;
+    const double* line = c + o * (size_t)n * inner + i0;
+    const size_t s = (size_t)((int)fl - 1);
+    const double v = w0 * line[s * inner] + w1 * line[(s + 1) * inner] + w2 * line[(s + 2) * inner] +
+                     w3 * line[(s + 3) * inner];
+    if (out_mode == 0) static_cast<double*>(out)[i] = v;
+    else if (out_mode == 1) static_cast<int16_t*>(out)[i] = (int16_t)(int)v;
+    else static_cast<int32_t*>(out)[i] = (int32_t)v;
+  }
+}
+
+// Order-0 zoom of a label map in 3-D (change_spacing(..., target_shape=original, order=0), nnunet.py:685-687): every
+// axis picks floor(o * (n_in - 1) / (n_out - 1) + 0.5), clamped.
+__global__ void __launch_bounds__(256)
+nearest_3d_kernel(const uint8_t* __restrict__ in, int zi, int yi, int xi, int zo, int yo, int xo,
+                  uint8_t* __restrict__ out) {
+  const size_t total = (size_t)zo * yo * xo;
+  const double fz = zo > 1 ? (double)(zi - 1) / (double)(zo - 1) : 1.0;
+  const double fy = yo > 1 ? (double)(yi - 1) / (double)(yo - 1) : 1.0;
+  const double fx = xo > 1 ? (double)(xi - 1) / (double)(xo - 1) : 1.0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int x = (int)(i % xo), y = (int)((i / xo) % yo), z = (int)(i / ((size_t)xo * yo));
+    int kz = (int)floor((double)z * fz + 0.5), ky = (int)floor((double)y * fy + 0.5), kx = (int)floor((double)x * fx + 0.5);
+    kz = kz < 0 ? 0 : (kz >= zi ? zi - 1 : kz);
+    ky = ky < 0 ? 0 : (ky >= yi ? yi - 1 : ky);
+    kx = kx < 0 ? 0 : (kx >= xi ? xi - 1 : kx);
+    out[i] = in[((size_t)kz * yi + ky) * xi + kx];
+  }
+}
+
 }  // namespace boa
 
 using namespace boa;
@@ -116,6 +216,42 @@ extern "C" int boa_resample_z_nearest_u8(const uint8_t* d_in, int z_in, size_t p
   BOA_REQUIRE(z_in >= 1 && z_out >= 1 && plane > 0, "boa_resample_z_nearest_u8: bad sizes");
   nearest_z_kernel<<<grid_for((size_t)z_out * plane, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
       d_in, z_in, plane, z_out, d_out);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+extern "C" int boa_resample_axis_cubic(const void* d_in, int in_dtype, size_t outer, int n_in, size_t inner, int n_out,
+                                       double* d_scratch, void* d_out, int out_mode, void* stream) {
+  BOA_REQUIRE(d_in && d_scratch && d_out, "boa_resample_axis_cubic: null pointer");
+  BOA_REQUIRE(n_in >= 2 && n_out >= 1 && outer > 0 && inner > 0, "boa_resample_axis_cubic: bad sizes (n_in=%d n_out=%d)",
+              n_in, n_out);
+  BOA_REQUIRE(in_dtype == BOA_DT_I16 || in_dtype == BOA_DT_F32 || in_dtype == BOA_DT_F64,
+              "boa_resample_axis_cubic: bad input dtype %d", in_dtype);
+  BOA_REQUIRE(out_mode >= 0 && out_mode <= 2, "boa_resample_axis_cubic: bad output mode %d", out_mode);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const size_t lines = outer * inner;
+  const unsigned blocks = (unsigned)((lines + 255) / 256);
+  if (in_dtype == BOA_DT_I16)
+    spline_prefilter_axis_kernel<short><<<blocks, 256, 0, s>>>(static_cast<const short*>(d_in), outer, n_in, inner, d_scratch);
+  else if (in_dtype == BOA_DT_F32)
+    spline_prefilter_axis_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(d_in), outer, n_in, inner, d_scratch);
+  else
+    spline_prefilter_axis_kernel<double><<<blocks, 256, 0, s>>>(static_cast<const double*>(d_in), outer, n_in, inner, d_scratch);
+  BOA_CHECK_LAUNCH();
+  spline_eval_axis_kernel<<<grid_for(outer * (size_t)n_out * inner, 256), 256, 0, s>>>(d_scratch, outer, n_in, inner, n_out,
+                                                                                    d_out, out_mode);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+extern "C" int boa_resample_nearest_u8(const uint8_t* d_in, const int32_t* in_shape, const int32_t* out_shape,
+                                       uint8_t* d_out, void* stream) {
+  BOA_REQUIRE(d_in && d_out && in_shape && out_shape, "boa_resample_nearest_u8: null pointer");
+  for (int k = 0; k < 3; ++k)
+    BOA_REQUIRE(in_shape[k] >= 1 && out_shape[k] >= 1, "boa_resample_nearest_u8: bad shape");
+  const size_t total = (size_t)out_shape[0] * out_shape[1] * out_shape[2];
+  nearest_3d_kernel<<<grid_for(total, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_in, in_shape[0], in_shape[1], in_shape[2], out_shape[0], out_shape[1], out_shape[2], d_out);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }

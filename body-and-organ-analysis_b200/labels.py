@@ -9,6 +9,7 @@ from functools import lru_cache
 _DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data", "class_maps.json")
 
 TOTAL_TASK_IDS = [291, 292, 293, 294, 295]           # totalsegmentator/python_api.py:182-189
+TOTAL_FAST_TASK_ID = 297                              # --fast-total: one 3 mm model, all 117 classes (python_api.py:169-175)
 BODY_REGIONS_TASK_ID, BODY_PARTS_TASK_ID = 542, 543  # body_composition_analysis/tasks.py:15-48
 
 # body_composition_analysis/body_regions/definition.py, body_parts/definition.py, tissue/definition.py

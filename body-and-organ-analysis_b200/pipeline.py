@@ -21,12 +21,13 @@ import torch
 
 from . import bca, passes
 from .dist import DistContext, exchange_slabs, gather_label_slabs, plan_shards
-from .labels import BODY_PARTS_TASK_ID, BODY_REGIONS_TASK_ID, TOTAL_TASK_IDS, part_luts
+from .labels import BODY_PARTS_TASK_ID, BODY_REGIONS_TASK_ID, TOTAL_FAST_TASK_ID, TOTAL_TASK_IDS, part_luts
 from .measurements import compute_measurements_on_device
 from .plans import find_model_folder, load_model_folder
 from .predictor import finalize_argmax, nnUNetPredictor, weight_sum
 
 TRAINERS = {**{t: "nnUNetTrainerNoMirroring" for t in TOTAL_TASK_IDS},
+            TOTAL_FAST_TASK_ID: "nnUNetTrainer_4000epochs_NoMirroring",
             BODY_REGIONS_TASK_ID: "nnUNetTrainerNoMirroring",
             BODY_PARTS_TASK_ID: "nnUNetTrainer_1500epochs_NoMirroring"}
 
@@ -154,6 +155,12 @@ def segment_total(ct: torch.Tensor, zoo: ModelZoo, dist_ctx: DistContext | None 
     return segment_task(ct, zoo, TOTAL_TASK_IDS, [0], 0.8, part_luts(), dist_ctx)
 
 
+def segment_total_fast(ct_3mm: torch.Tensor, zoo: ModelZoo, dist_ctx: DistContext | None = None) -> torch.Tensor:
+    """task `total` with --fast-total: the single 3 mm model 297, fold 0, step 0.5 (the 0.8 step applies only below
+    3 mm, totalsegmentator/nnunet.py:507-514); its labels are the global class ids already."""
+    return segment_task(ct_3mm, zoo, [TOTAL_FAST_TASK_ID], [0], 0.5, None, dist_ctx)
+
+
 def segment_bca_net(ct_5mm: torch.Tensor, zoo: ModelZoo, task: str, fast: bool,
                     dist_ctx: DistContext | None = None) -> torch.Tensor:
     tid = BODY_PARTS_TASK_ID if task == "body_parts" else BODY_REGIONS_TASK_ID
@@ -247,12 +254,12 @@ class HostStager:
 
 def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total", "bca"), fast_bca: bool = False,
                    cnr_adjustment: bool = False, dist_ctx: DistContext | None = None,
-                   stager: HostStager | None = None) -> VolumeResult:
+                   stager: HostStager | None = None, fast_total: bool = False) -> VolumeResult:
     """compute_all_models + run_pipeline numerics for one CT already on the device (int16 [z,y,x]).
 
     spacing_zyx: voxel spacing of the array axes.  `total` expects 1.5 mm (resampling is identity there,
     totalsegmentator/resampling.py:179-181); the BCA nets run at 5 mm slice thickness (resample_only_thickness)."""
-    from .resample import resample_thickness, upsample_labels_nearest
+    from .resample import resample_labels_nearest, resample_thickness, resample_volume_cubic, upsample_labels_nearest
 
     res = VolumeResult()
     models = set(models)
@@ -269,9 +276,15 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         marks.append((name, e))
 
     if "total" in models:
-        if not np.allclose(spacing_zyx, 1.5):
-            raise NotImplementedError("`total` needs a 1.5 mm volume: 3-D cubic resampling is not on the GPU path yet")
-        res.total = segment_total(ct, zoo, dist_ctx)
+        # `total` runs at 1.5 mm: other inputs are resampled (order 3) and the label map goes back to the input grid
+        # (order 0), totalsegmentator/nnunet.py:466-470,685-687
+        net_spacing = 3.0 if fast_total else 1.5  # python_api.py:169-189
+        ct_net = resample_volume_cubic(ct, spacing_zyx, net_spacing)
+        if ct_net is not ct:
+            mark("resample_total")
+        seg = segment_total_fast(ct_net, zoo, dist_ctx) if fast_total else segment_total(ct_net, zoo, dist_ctx)
+        res.total = resample_labels_nearest(seg, ct.shape)
+        del ct_net, seg
         mark("total_nets")
         if stager is not None:
             stager.stage("total", res.total)

@@ -23,6 +23,7 @@ DATASETS = {
     293: ("Dataset293_TotalSegmentator_part3_cardiac_1559subj", "nnUNetTrainerNoMirroring", 19),
     294: ("Dataset294_TotalSegmentator_part4_muscles_1559subj", "nnUNetTrainerNoMirroring", 24),
     295: ("Dataset295_TotalSegmentator_part5_ribs_1559subj", "nnUNetTrainerNoMirroring", 27),
+    297: ("Dataset297_TotalSegmentator_total_3mm_1559subj", "nnUNetTrainer_4000epochs_NoMirroring", 118),
     542: ("Dataset542_BodyRegions", "nnUNetTrainerNoMirroring", 12),
     543: ("Dataset543_BodyParts", "nnUNetTrainer_1500epochs_NoMirroring", 7),
 }
@@ -130,7 +131,7 @@ def write_zoo(root: str, patch=(128, 128, 128), base=32, max_features=320, n_sta
     for did, (name, trainer, ncls) in DATASETS.items():
         if datasets is not None and did not in datasets:
             continue
-        spacing = (1.5, 1.5, 1.5) if did < 500 else (5.0, 1.5, 1.5)
+        spacing = (3.0, 3.0, 3.0) if did == 297 else ((1.5, 1.5, 1.5) if did < 500 else (5.0, 1.5, 1.5))
         plans = default_plans(patch, base, max_features, n_stages, spacing, name)
         folds = (0,) if did < 500 else tuple(bca_folds)
         out[did] = write_model(root, did, plans, ncls, folds, seed)

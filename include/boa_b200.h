@@ -36,6 +36,7 @@ extern "C" {
 /* dtype tags for CT volumes */
 #define BOA_DT_I16 0
 #define BOA_DT_F32 1
+#define BOA_DT_F64 2
 
 const char* boa_last_error(void);
 /* ABI version of this header (bumped on any signature change). */
@@ -172,6 +173,18 @@ int boa_resample_z_cubic(const void* d_in, int in_dtype, int z_in, size_t plane,
                          int16_t* d_out, void* stream);
 /* Order-0 zoom of a label map along the outermost axis back to the input grid (nnunet.py:685-687). */
 int boa_resample_z_nearest_u8(const uint8_t* d_in, int z_in, size_t plane, int z_out, uint8_t* d_out, void* stream);
+
+/* 3-D resampling to / from the network spacing (change_spacing(img, [1.5]*3, order=3, dtype=int32) before and
+ * change_spacing(seg, target_shape=original, order=0) after the networks, _external/totalsegmentator/nnunet.py:466-470,
+ * 685-687 -> resampling.py:24-56,129-222; scipy.ndimage.zoom(mode="nearest")).  The cubic zoom is a tensor product:
+ * call boa_resample_axis_cubic once per axis on a volume viewed as [outer][n_in][inner].  in_dtype: BOA_DT_I16 /
+ * F32 / F64; out_mode 0: fp64 (feed the next pass), 1: int16, 2: int32 (both truncated toward zero like astype()).
+ * d_scratch: double [outer * (n_in + 24) * inner]. */
+int boa_resample_axis_cubic(const void* d_in, int in_dtype, size_t outer, int n_in, size_t inner, int n_out,
+                            double* d_scratch, void* d_out, int out_mode, void* stream);
+/* Order-0 zoom of a uint8 label map [z][y][x] from in_shape to out_shape (host int32[3] each). */
+int boa_resample_nearest_u8(const uint8_t* d_in, const int32_t* in_shape, const int32_t* out_shape, uint8_t* d_out,
+                            void* stream);
 
 /* Multi-GPU exchange, device side: d_dst[i] += d_src[i] (fp32, round-to-nearest, fixed order chosen by the caller). */
 int boa_add_slab(float* d_dst, const float* d_src, size_t n, void* stream);

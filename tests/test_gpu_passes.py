@@ -163,3 +163,45 @@ def test_resample_thickness_vs_scipy(cuda):
     lab = rng.integers(0, 7, size=ref.shape).astype(np.uint8)
     up = upsample_labels_nearest(_dev(lab), 47).cpu().numpy()
     assert np.array_equal(up, ndimage.zoom(lab, (47 / lab.shape[0], 1, 1), order=0, mode="nearest"))
+
+
+@pytest.mark.parametrize("shape,spacing", [((37, 44, 52), (2.0, 0.9765625, 0.9765625)),   # thick slices, fine in-plane
+                                           ((40, 33, 29), (1.0, 1.5, 0.8)),               # one axis already at 1.5 mm
+                                           ((21, 64, 48), (3.0, 0.7, 0.7))])
+def test_resample_3d_vs_scipy(cuda, shape, spacing):
+    """change_spacing(img, [1.5]*3, order=3) and back with order=0 against scipy.ndimage.zoom, the function the
+    reference calls (totalsegmentator/resampling.py:24-56)."""
+    from scipy import ndimage
+    from boa_b200.resample import resample_labels_nearest, resample_volume_cubic, zoomed_shape
+    rng = np.random.default_rng(11)
+    # smooth-ish field + noise so that neighbouring voxels are correlated like a CT
+    ct = (rng.integers(-1000, 2000, size=shape) * 0.3 + 400 * np.sin(np.arange(shape[2]) / 5.0)[None, None, :]).astype(np.int16)
+    zoom = [np.float64(np.float32(s)) / 1.5 for s in spacing]
+    # scipy evaluates the axes that are already at 1.5 mm at integer coordinates, where the spline reproduces the
+    # samples; the product skips those axes (like the thickness-only path)
+    ref = ndimage.zoom(ct.astype(np.float64), zoom, order=3, mode="nearest")
+    got = resample_volume_cubic(_dev(ct), spacing, 1.5).cpu().numpy()
+    assert got.shape == ref.shape == zoomed_shape(shape, spacing, 1.5)
+    assert got.dtype == np.int16
+    # fp64 splines on both sides: the values agree to ~1e-11 before truncation, so the integers can differ (by one)
+    # only where the spline value is numerically an integer - output points that coincide with input samples, which
+    # the (1.0, 1.5, 0.8) case has on purpose (zoom scales 1.5 and 2.0); there scipy's own rounding noise decides
+    diff = np.abs(got.astype(np.int64) - ref.astype(np.int32))
+    assert diff.max() <= 1, diff.max()
+    inner = np.abs(ref - np.rint(ref)) > 1e-6
+    assert inner.mean() > 0.4
+    assert np.array_equal(got[inner], ref.astype(np.int32)[inner])
+    lab = rng.integers(0, 118, size=ref.shape).astype(np.uint8)
+    back = resample_labels_nearest(_dev(lab), shape).cpu().numpy()
+    ref_back = ndimage.zoom(lab, np.array(shape) / np.array(lab.shape), order=0, mode="nearest")
+    assert back.shape == tuple(shape) and np.array_equal(back, ref_back)
+
+
+def test_resample_identity_and_errors(cuda):
+    from boa_b200.resample import resample_labels_nearest, resample_volume_cubic
+    ct = _dev(np.zeros((8, 9, 10), dtype=np.int16))
+    assert resample_volume_cubic(ct, (1.5, 1.5, 1.5), 1.5) is ct
+    lab = _dev(np.zeros((8, 9, 10), dtype=np.uint8))
+    assert resample_labels_nearest(lab, (8, 9, 10)) is lab
+    with pytest.raises(TypeError):
+        resample_volume_cubic(ct.to(torch.float64), (1.0, 1.0, 1.0), 1.5)

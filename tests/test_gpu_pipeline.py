@@ -120,3 +120,28 @@ def test_host_api_matches_device_api(cuda, small_zoo):
         from test_oracle_golden import _close
         _close(res.total_measurements, out["total_measurements"])
         _close(res.bca_measurements, out["bca_measurements"])
+
+
+def test_total_on_a_volume_that_is_not_at_1_5_mm(cuda, small_zoo):
+    """Non-1.5 mm input: order-3 resampling to 1.5 mm, networks, order-0 resampling of the label map back to the input
+    grid (totalsegmentator/nnunet.py:466-470,685-687) - checked against scipy.ndimage.zoom + the oracle networks."""
+    from scipy import ndimage
+    specs, mz = small_zoo
+    ct = zoo.synthetic_ct((36, 80, 72), seed=9)
+    spacing = (2.5, 0.9, 0.9)
+    res = analyze_volume(torch.from_numpy(ct).cuda(), spacing, mz, models=("total",))
+    total = res.total.cpu().numpy()
+    assert total.shape == ct.shape and total.dtype == np.uint8
+    zoomf = [np.float64(np.float32(s)) / 1.5 for s in spacing]
+    ct15 = ndimage.zoom(ct.astype(np.float64), zoomf, order=3, mode="nearest").astype(np.int32).astype(np.int16)
+    segs = [_oracle_labels(specs[tid], ct15, 0.8, [0])[0] for tid in (291, 292, 293, 294, 295)]
+    ref15 = merge_parts(segs, part_luts(), ct15.shape)
+    ref = ndimage.zoom(ref15, np.array(ct.shape) / np.array(ref15.shape), order=0, mode="nearest")
+    agree = (total == ref).mean()
+    print(f"total on a {spacing} mm volume: agreement {agree:.5f}")
+    assert agree > 0.99
+    # the measurements are taken on the ORIGINAL grid with the ORIGINAL spacing
+    ref_meas = compute_measurements(ct, total, (spacing[2], spacing[1], spacing[0]), cnr_adjustment=False)
+    ref_meas.pop("_ct_pfav_mask")
+    from test_oracle_golden import _close
+    _close(ref_meas, res.total_measurements)

@@ -1,0 +1,3 @@
+#!/bin/bash
+set -u
+echo "== pytest -m gpu"; timeout 900 python -m pytest tests -m gpu -x -q 2>&1 | tail -15
