@@ -281,7 +281,7 @@ def run_ours(a):
     traffic = None
     try:  # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture
         with open(os.path.join(ROOT, "profiles", "r01_fold_traffic.json")) as f:
-            traffic = json.load(f)
+            traffic = float(json.load(f)["bytes_per_launch"])
     except Exception:
         pass
     roofline = {"bound": "tensor", "kernel": kinds[0], "achieved": dom["tflops"], "peak": peak, "unit": "TFLOP/s",

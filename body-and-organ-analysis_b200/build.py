@@ -9,7 +9,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libboa_b200.so")
-SOURCES = ["core.cu", "passes.cu", "net_simt.cu", "conv_mma.cu", "conv_taps.cu", "net.cu", "comm.cu", "resample.cu"]
+SOURCES = ["core.cu", "passes.cu", "net_simt.cu", "conv_mma.cu", "conv_taps.cu", "net.cu", "comm.cu", "resample.cu", "cc.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
          "-Xptxas", "-v"]

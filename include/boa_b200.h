@@ -186,6 +186,23 @@ int boa_resample_axis_cubic(const void* d_in, int in_dtype, size_t outer, int n_
 int boa_resample_nearest_u8(const uint8_t* d_in, const int32_t* in_shape, const int32_t* out_shape, uint8_t* d_out,
                             void* stream);
 
+/* Connected-component post-processing of the body-composition label maps (between the networks and the tissue rules,
+ * _external/body_composition_analysis/infer/infer.py:81-89):
+ *   postprocess_region_segmentation (body_regions/postprocess.py:8-40): skimage.measure.label (26-connected) +
+ *     regionprops, every component of a label set but the largest -> 255                                   = op 0
+ *   postprocess_part_segmentation (body_parts/postprocess.py:7-60): slice-wise cv2 external-contour fill = op 2 on the
+ *     complement with mode 1; remove_small_objects(max_size, connectivity=3) on objects / holes           = op 1
+ * The set is {v : h_label_set[d_seg[v]] != 0} (256 host bytes), complemented when invert != 0.  mode 0: 26-connected in
+ * 3-D, 1: 4-connected inside every z-slice.  op 0: voxels of the set outside its largest component (first in raster
+ * order on ties) := fill_value; op 1: voxels in components of size <= threshold := fill_value; op 2: voxels in components
+ * that do not touch the border of their slice := fill_value.  Sizes are sum of d_slice_weight[z] (int32 [D], null = 1).
+ * d_labels, d_sizes, d_border: int32 [V] scratch (d_border: op 2 only); d_best: 16 bytes scratch.  V < 2^31. */
+int boa_cc_filter(uint8_t* d_seg, const int32_t* shape, const uint8_t* h_label_set, int invert, int mode, int op,
+                  int threshold, int fill_value, const int32_t* d_slice_weight, int32_t* d_labels, int32_t* d_sizes,
+                  int32_t* d_border, void* d_best, void* stream);
+/* d_out[v] = label where d_mask[v] != 0 (body_parts/postprocess.py:50). */
+int boa_paint_label(const uint8_t* d_mask, size_t n, int label, uint8_t* d_out, void* stream);
+
 /* Multi-GPU exchange, device side: d_dst[i] += d_src[i] (fp32, round-to-nearest, fixed order chosen by the caller). */
 int boa_add_slab(float* d_dst, const float* d_src, size_t n, void* stream);
 

@@ -118,3 +118,47 @@ def test_product_host_statistics_match_reference():
     assert {k: list(v) for k, v in vert.items()} == goldb["vertebrae"]
     ex = pbca.AggregatableBodyPart(goldb["body_part"])
     assert pbca.secondary_findings(t, ex, float(np.prod(sp) / 1000.0)) == goldb["other_findings"]
+
+
+def test_postprocess_oracle_matches_reference_vectors():
+    """oracle/postprocess.py against vectors produced by the reference's own postprocess_region_segmentation /
+    remove_small_labeled_objects (tests/golden/make_golden_postprocess.py)."""
+    from oracle import postprocess as opp
+    z = np.load(os.path.join(G, "postprocess.npz"))
+    i = 0
+    while f"regions_in_{i}" in z:
+        assert np.array_equal(opp.postprocess_region_segmentation(z[f"regions_in_{i}"]), z[f"regions_out_{i}"]), i
+        i += 1
+    assert i == 5
+    i = 0
+    while f"parts_in_{i}" in z:
+        got = opp.remove_small_labeled_objects(z[f"parts_in_{i}"], int(z[f"parts_thr_{i}"]))
+        assert np.array_equal(got, z[f"parts_out_{i}"]), i
+        i += 1
+    assert i == 4
+
+
+def test_postprocess_on_the_5mm_grid_with_slice_weights_equals_the_full_grid():
+    """The claim behind boa_b200.postprocess: replicating slices (order-0 zoom along z) maps components one to one, so
+    post-processing the 5 mm map with per-slice weights and replicating afterwards equals the reference's order
+    (replicate, then post-process)."""
+    from scipy import ndimage
+    from oracle import postprocess as opp
+    z = np.load(os.path.join(G, "postprocess.npz"))
+    for key, fn, kw in (("regions_in_0", opp.postprocess_region_segmentation, {}),
+                        ("regions_in_2", opp.postprocess_region_segmentation, {}),
+                        ("parts_in_0", opp.remove_small_labeled_objects, {"threshold": 130}),
+                        ("parts_in_2", opp.remove_small_labeled_objects, {"threshold": 33})):
+        low = z[key]
+        z_out = int(round(low.shape[0] * 3.3))
+        zoom = (z_out / low.shape[0], 1, 1)
+        full = ndimage.zoom(low, zoom, order=0, mode="nearest")
+        scale = (low.shape[0] - 1) / (z_out - 1)  # scipy's order-0 coordinate: floor(o * scale + 0.5)
+        src = np.clip(np.floor(np.arange(z_out, dtype=np.float64) * scale + 0.5).astype(int), 0, low.shape[0] - 1)
+        assert np.array_equal(full, low[src])
+        w = np.bincount(src, minlength=low.shape[0])
+        from boa_b200.postprocess import slice_weights
+        assert np.array_equal(slice_weights(low.shape[0], z_out, "cpu").numpy(), w)
+        ref = fn(full, **kw)
+        got = fn(low, weights=w, **kw)[src]
+        assert np.array_equal(got, ref), key
