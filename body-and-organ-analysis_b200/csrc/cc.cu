@@ -47,14 +47,38 @@ struct CcLabelSet {
   uint8_t in[256];
 };
 
+// Initial forest: every voxel of the set points at the first voxel of its x-run inside the 32-voxel segment its warp
+// covers (ballot + bit scan), so the links along x - the bulk of all links in a solid region - never go through the
+// union-find; runs that continue across a segment boundary are joined by one union in the merge pass.
 __global__ void __launch_bounds__(256)
-cc_init_kernel(const uint8_t* __restrict__ seg, size_t n, CcLabelSet set, int invert, int* __restrict__ L) {
+cc_init_kernel(const uint8_t* __restrict__ seg, size_t n, int W, CcLabelSet set, int invert, int* __restrict__ L) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
-    L[v] = ((set.in[seg[v]] != 0) != (invert != 0)) ? (int)v : -1;
+  const size_t n_round = (n + 31) / 32 * 32;
+  const unsigned lane = threadIdx.x & 31u;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n_round; v += stride) {
+    const bool in = v < n && ((set.in[seg[v]] != 0) != (invert != 0));
+    const bool row_start = v < n && (v % (size_t)W) == 0;
+    const unsigned bits = __ballot_sync(0xffffffffu, in);
+    const unsigned breaks = __ballot_sync(0xffffffffu, row_start);
+    if (v >= n) continue;
+    if (!in) { L[v] = -1; continue; }
+    const unsigned below = (1u << lane) - 1u;
+    const unsigned zeros = ~bits & below;                      // lanes below me that are outside the set
+    const unsigned stops = breaks & (below | (1u << lane));    // row starts at or below me
+    const int after_zero = zeros ? 32 - __clz(zeros) : 0;      // first lane after the highest such gap
+    const int at_break = stops ? 31 - __clz(stops) : 0;
+    const int start = after_zero > at_break ? after_zero : at_break;
+    L[v] = (int)(v - (lane - (unsigned)start));
+  }
 }
 
-// Every voxel of the set joins the neighbours that precede it in raster order (half of the neighbourhood).
+// Every voxel of the set joins the neighbours that precede it in raster order (half of the neighbourhood), except
+// where the link is implied by the links of its left neighbour v-1 (same run):
+//   row centre c in the set:      v ~ c   is implied when v-1 and c-1 are in the set  (v-1 ~ c-1, runs along x)
+//   centre outside, c-1 in set:   v ~ c-1 is implied when v-1 is in the set           (c-1 is the centre of v-1)
+//   centre outside, c+1 in set:   always joined
+// (centre in the set: its own run links make the diagonals redundant).  Joins therefore happen where runs start to
+// overlap - on the surface of a region, not in its volume.
 __global__ void __launch_bounds__(256)
 cc_merge_kernel(int* L, int D, int H, int W, int mode /*0: 26-conn 3-D, 1: 4-conn per slice*/) {
   const size_t n = (size_t)D * H * W;
@@ -63,33 +87,25 @@ cc_merge_kernel(int* L, int D, int H, int W, int mode /*0: 26-conn 3-D, 1: 4-con
     if (L[i] < 0) continue;
     const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((size_t)W * H));
     const int v = (int)i;
-    if (mode == 1) {
-      if (x > 0 && L[i - 1] >= 0) cc_union(L, v, v - 1);
-      if (y > 0 && L[i - W] >= 0) cc_union(L, v, v - W);
-      continue;
-    }
-    // same slice: (y, x-1), (y-1, x-1 .. x+1); previous slice: all nine
-    if (x > 0 && L[i - 1] >= 0) cc_union(L, v, v - 1);
-    if (y > 0) {
-      const size_t r = i - W;
-      if (L[r] >= 0) cc_union(L, v, (int)r);
-      else {  // the centre joins both diagonals; only needed when it is not in the set
-        if (x > 0 && L[r - 1] >= 0) cc_union(L, v, (int)r - 1);
+    const bool left_in = x > 0 && L[i - 1] >= 0;
+    // a run that crosses the boundary of its warp's 32-voxel segment
+    if (left_in && (i & 31) == 0) cc_union(L, v, v - 1);
+    auto row = [&](size_t r, bool diagonals) {
+      const bool centre = L[r] >= 0;
+      const bool left = x > 0 && L[r - 1] >= 0;
+      if (centre) {
+        if (!(left_in && left)) cc_union(L, v, (int)r);
+      } else if (diagonals) {
+        if (left && !left_in) cc_union(L, v, (int)r - 1);
         if (x + 1 < W && L[r + 1] >= 0) cc_union(L, v, (int)r + 1);
       }
-    }
-    if (z > 0) {
+    };
+    if (y > 0) row(i - W, mode == 0);
+    if (mode == 0 && z > 0) {
       const size_t pz = i - (size_t)W * H;
-      for (int dy = -1; dy <= 1; ++dy) {
-        const int yy = y + dy;
-        if (yy < 0 || yy >= H) continue;
-        const size_t r = pz + (ptrdiff_t)dy * W;
-        if (L[r] >= 0) { cc_union(L, v, (int)r); }  // the row centre links its own x-neighbours within that row
-        else {
-          if (x > 0 && L[r - 1] >= 0) cc_union(L, v, (int)r - 1);
-          if (x + 1 < W && L[r + 1] >= 0) cc_union(L, v, (int)r + 1);
-        }
-      }
+      if (y > 0) row(pz - W, true);
+      row(pz, true);
+      if (y + 1 < H) row(pz + W, true);
     }
   }
 }
@@ -100,38 +116,35 @@ __global__ void __launch_bounds__(256) cc_compress_kernel(int* L, size_t n) {
     if (L[v] >= 0) L[v] = cc_find(L, (int)v);
 }
 
-// sizes[root] += weight[z] for every voxel of the set (warp-aggregated: one atomic per distinct root per warp);
-// border != nullptr: border[root] = 1 when a voxel of the component lies on the edge of its slice.
+// sizes[root] += weight[z] for every voxel of the set.  A solid region is ONE root for tens of millions of voxels, so
+// the adds are combined before they reach memory: a thread keeps a running sum while consecutive voxels of its
+// grid-stride walk share the root, and what is left at the end is combined across the warp (one atomic per distinct
+// root per warp).  border != nullptr: border[root] = 1 when a voxel of the component lies on the edge of its slice.
 __global__ void __launch_bounds__(256)
 cc_sizes_kernel(const int* __restrict__ L, int D, int H, int W, const int* __restrict__ weight, int* __restrict__ sizes,
                 int* __restrict__ border) {
   const size_t n = (size_t)D * H * W;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  const size_t n_round = (n + 31) / 32 * 32;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_round; i += stride) {
-    int root = -1, w = 0, edge = 0;
-    if (i < n) {
-      root = L[i];
-      if (root >= 0) {
-        const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((size_t)W * H));
-        w = weight ? weight[z] : 1;
-        edge = (x == 0 || y == 0 || x == W - 1 || y == H - 1) ? 1 : 0;
-      }
+  int cur = -1, sum = 0;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int root = L[i];
+    if (root < 0) continue;
+    const int x = (int)(i % W), y = (int)((i / W) % H), z = (int)(i / ((size_t)W * H));
+    if (border && (x == 0 || y == 0 || x == W - 1 || y == H - 1)) border[root] = 1;
+    const int w = weight ? weight[z] : 1;
+    if (root != cur) {
+      if (cur >= 0) atomicAdd(&sizes[cur], sum);
+      cur = root;
+      sum = 0;
     }
-    const unsigned peers = __match_any_sync(0xffffffffu, root);
-    if (root >= 0) {
-      // sum w / or edge over the lanes that share this root
-      int sum = 0, any_edge = 0;
-      for (unsigned m = peers; m; m &= m - 1) {
-        const int src = __ffs(m) - 1;
-        sum += __shfl_sync(peers, w, src);
-        any_edge |= __shfl_sync(peers, edge, src);
-      }
-      if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) {
-        atomicAdd(&sizes[root], sum);
-        if (border && any_edge) border[root] = 1;
-      }
-    }
+    sum += w;
+  }
+  // every thread arrives here: combine the leftovers of the warp per root
+  const unsigned peers = __match_any_sync(0xffffffffu, cur);
+  if (cur >= 0) {
+    int total = 0;
+    for (unsigned m = peers; m; m &= m - 1) total += __shfl_sync(peers, sum, __ffs(m) - 1);
+    if ((int)(threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&sizes[cur], total);
   }
 }
 
@@ -197,7 +210,7 @@ extern "C" int boa_cc_filter(uint8_t* d_seg, const int32_t* shape, const uint8_t
   BOA_REQUIRE(n < ((size_t)1 << 31), "boa_cc_filter: more than 2^31 voxels");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int grid = grid_for(n, 256);
-  cc_init_kernel<<<grid, 256, 0, s>>>(d_seg, n, set, invert, d_labels);
+  cc_init_kernel<<<grid, 256, 0, s>>>(d_seg, n, W, set, invert, d_labels);
   BOA_CHECK_LAUNCH();
   cc_merge_kernel<<<grid, 256, 0, s>>>(d_labels, D, H, W, mode);
   BOA_CHECK_LAUNCH();

@@ -254,7 +254,8 @@ class HostStager:
 
 def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total", "bca"), fast_bca: bool = False,
                    cnr_adjustment: bool = False, dist_ctx: DistContext | None = None,
-                   stager: HostStager | None = None, fast_total: bool = False) -> VolumeResult:
+                   stager: HostStager | None = None, fast_total: bool = False,
+                   postprocess: bool = True) -> VolumeResult:
     """compute_all_models + run_pipeline numerics for one CT already on the device (int16 [z,y,x]).
 
     spacing_zyx: voxel spacing of the array axes.  `total` expects 1.5 mm (resampling is identity there,
@@ -311,12 +312,27 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         mark("resample")
         want_parts = "bca" in models or "body_parts" in models
         want_regions = "bca" in models or "body_regions" in models
+        # connected-component post-processing of both maps (infer/infer.py:81-89).  The reference applies it after the
+        # maps are back on the input grid; replicated slices map components one to one, so it runs here on the 5 mm
+        # grid with every slice weighted by the number of output slices it becomes (postprocess.py)
+        from .postprocess import postprocess_part_segmentation, postprocess_region_segmentation, slice_weights
+        weights = slice_weights(ct5.shape[0], ct.shape[0], ct.device)
         if want_parts:
-            res.body_parts = upsample_labels_nearest(segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx), ct.shape[0])
+            parts5 = segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx)
+            mark("body_parts_net")
+            if postprocess:
+                parts5 = postprocess_part_segmentation(parts5, weights)
+                mark("body_parts_postprocess")
+            res.body_parts = upsample_labels_nearest(parts5, ct.shape[0])
             if stager is not None:
                 stager.stage("body_parts", res.body_parts)
         if want_regions:
-            res.body_regions = upsample_labels_nearest(segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx), ct.shape[0])
+            regions5 = segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx)
+            mark("body_regions_net")
+            if postprocess:
+                regions5 = postprocess_region_segmentation(regions5, weights)
+                mark("body_regions_postprocess")
+            res.body_regions = upsample_labels_nearest(regions5, ct.shape[0])
         if stager is not None:
             stager.stage("body_regions", res.body_regions)
         mark("bca_nets")

@@ -53,6 +53,16 @@ def test_total_and_bca_against_oracle(cuda, small_zoo):
     _close(ref_meas, res.total_measurements)
     regions, parts = res.body_regions.cpu().numpy(), res.body_parts.cpu().numpy()
     assert regions.shape == ct.shape and parts.shape == ct.shape
+    # connected-component post-processing: the pipeline runs it on the 5 mm grid with slice weights; the reference's
+    # order is replicate to the input grid first, then post-process (infer/infer.py:67-89) - same result
+    from boa_b200.pipeline import segment_bca_net
+    from boa_b200.resample import resample_thickness, upsample_labels_nearest
+    from oracle import postprocess as opp
+    ct5 = resample_thickness(torch.from_numpy(ct).cuda(), 1.5, 5.0)
+    for task, got, fn in (("body_regions", regions, opp.postprocess_region_segmentation),
+                          ("body_parts", parts, opp.remove_small_labeled_objects)):
+        raw = upsample_labels_nearest(segment_bca_net(ct5, mz, task, fast=False), ct.shape[0]).cpu().numpy()
+        assert np.array_equal(got, fn(raw)), task
     tissues = res.tissues.cpu().numpy()
     assert np.array_equal(tissues, op.subclassify_tissues(ct, regions))
     js, vert = bca_json(ct, tissues, parts, regions, total, (1.5, 1.5, 1.5))
