@@ -20,13 +20,19 @@
 
 namespace boa {
 
+// Root of v with path halving: every visited node is re-pointed at its grandparent.  Pointers only ever move to an
+// ancestor (trees merge by hanging the larger root under the smaller), so the plain stores are safe next to the
+// concurrent atomicMin of cc_union - at worst a node keeps a slightly older ancestor.
 // (no const / __restrict__ on L: the tree is updated concurrently, its loads must not take the read-only path)
 __device__ __forceinline__ int cc_find(int* L, int v) {
   int r = v;
   while (true) {
     const int p = L[r];
     if (p == r) return r;
-    r = p;
+    const int gp = L[p];
+    if (gp == p) return p;
+    L[r] = gp;
+    r = gp;
   }
 }
 
@@ -110,10 +116,21 @@ cc_merge_kernel(int* L, int D, int H, int W, int mode /*0: 26-conn 3-D, 1: 4-con
   }
 }
 
+// Final pass: every node points straight at its root.  The walk is read-only (no halving here: a late halving store of
+// another thread could replace a node's final root pointer by an intermediate ancestor); the only store to L[v] is its
+// owner's.
 __global__ void __launch_bounds__(256) cc_compress_kernel(int* L, size_t n) {
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride)
-    if (L[v] >= 0) L[v] = cc_find(L, (int)v);
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < n; v += stride) {
+    int r = L[v];
+    if (r < 0) continue;
+    while (true) {
+      const int p = L[r];
+      if (p == r) break;
+      r = p;
+    }
+    L[v] = r;
+  }
 }
 
 // sizes[root] += weight[z] for every voxel of the set.  A solid region is ONE root for tens of millions of voxels, so

@@ -67,10 +67,22 @@ def metrics_from_hist(hist: np.ndarray, hu_min: int, autochthon_mean, autochthon
     return m
 
 
-def _window(hist_row: np.ndarray, lo: int, hi: int) -> np.ndarray:
+def _window(hist_row: np.ndarray, lo: int, hi: int, hu_min: int = HU_MIN) -> np.ndarray:
+    """hist_row restricted to lo <= HU <= hi (hist_row[i] counts HU == hu_min + i)."""
     out = np.zeros_like(hist_row)
-    out[lo - HU_MIN:hi - HU_MIN + 1] = hist_row[lo - HU_MIN:hi - HU_MIN + 1]
+    a, b = max(lo - hu_min, 0), min(hi - hu_min + 1, hist_row.shape[0])
+    if b > a:
+        out[a:b] = hist_row[a:b]
     return out
+
+
+def _occupied_range(hist_dev: torch.Tensor) -> tuple[int, int]:
+    """[lo, hi) of the histogram columns any label uses: a CT occupies ~4 000 of the 65 536 int16 bins, and every
+    per-label statistic below walks its whole row."""
+    idx = torch.nonzero((hist_dev != 0).any(dim=0)).flatten()
+    if idx.numel() == 0:
+        return 0, 1
+    return int(idx[0]), int(idx[-1]) + 1
 
 
 def _masked_hist(ct: torch.Tensor, mask: torch.Tensor) -> np.ndarray:
@@ -101,7 +113,9 @@ def compute_measurements_on_device(ct: torch.Tensor, segmentations: dict[str, to
         label_map = measurement_label_map(model_name)
         n_labels = max(label_map.values()) + 1
         hist_dev, _ = passes.label_hu_hist(ct, labels, n_labels, HU_MIN, N_BINS)
-        hist = hist_dev.cpu().numpy().view(np.uint32)
+        col_lo, col_hi = _occupied_range(hist_dev)
+        hist = hist_dev[:, col_lo:col_hi].contiguous().cpu().numpy().view(np.uint32)
+        hu0 = HU_MIN + col_lo  # hist[label][i] = #voxels of the label with HU == hu0 + i
         if model_name == "total":
             ids = [label_map["autochthon_right"], label_map["autochthon_left"]]
             h = _eroded_region_hist(ct, labels, ids, minus_fat=True)
@@ -110,16 +124,16 @@ def compute_measurements_on_device(ct: torch.Tensor, segmentations: dict[str, to
                 aut_mean, aut_std = ref["mean_hu"], ref["std_hu"]
         res = {}
         for region, label in label_map.items():
-            res[region] = metrics_from_hist(hist[label], HU_MIN, aut_mean, aut_std, spacing)
+            res[region] = metrics_from_hist(hist[label], hu0, aut_mean, aut_std, spacing)
         if "autochthon_left" in label_map and "autochthon_right" in label_map:
             union = hist[label_map["autochthon_left"]].astype(np.int64) + hist[label_map["autochthon_right"]]
-            res["autochthon"] = metrics_from_hist(union, HU_MIN, aut_mean, aut_std, spacing)
+            res["autochthon"] = metrics_from_hist(union, hu0, aut_mean, aut_std, spacing)
         if model_name == "total":
             def lung(names):
-                u = np.zeros(N_BINS, dtype=np.int64)
+                u = np.zeros(hist.shape[1], dtype=np.int64)
                 for nme in names:
-                    u += _window(hist[label_map[nme]], *ADIPOSE_TISSUE)
-                return metrics_from_hist(u, HU_MIN, aut_mean, aut_std, spacing)
+                    u += _window(hist[label_map[nme]], *ADIPOSE_TISSUE, hu_min=hu0)
+                return metrics_from_hist(u, hu0, aut_mean, aut_std, spacing)
             for nme in LUNG_MASKS:
                 res["ct_pfav_" + nme] = lung([nme])
             for side in ("left", "right"):

@@ -77,3 +77,19 @@ def test_errors(cuda):
     with pytest.raises(ValueError):
         pp.postprocess_region_segmentation(torch.zeros((4, 4, 4), dtype=torch.uint8, device="cuda"),
                                            weights=torch.ones(3, dtype=torch.int32, device="cuda"))
+
+
+def test_repeated_runs_are_identical_on_a_solid_volume(cuda):
+    """A solid region (one root for millions of voxels) with speckle around it: the concurrent union-find must give the
+    same, correct answer every time (regression test for a late path-halving store overwriting a final root)."""
+    from scipy import ndimage
+    rng = np.random.default_rng(3)
+    shape = (40, 256, 256)
+    solid = ndimage.gaussian_filter(rng.standard_normal(shape), 6.0) > -0.01
+    speckle = rng.random(shape) < 0.08
+    seg = np.where(solid | speckle, 3, 0).astype(np.uint8)
+    seg[rng.random(shape) < 0.02] = 7
+    ref = opp.postprocess_region_segmentation(seg)
+    dev = _dev(seg)
+    for _ in range(5):
+        assert np.array_equal(pp.postprocess_region_segmentation(dev).cpu().numpy(), ref)
