@@ -66,6 +66,7 @@ _SIGS = {
     "boa_resample_z_nearest_u8": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_int, _P, _P]),
     "boa_resample_axis_cubic": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.c_int, _P, _P, C.c_int, _P]),
     "boa_resample_nearest_u8": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P]),
+    "boa_median3x3_slices": (C.c_int, [_P, C.POINTER(C.c_int32), _P, _P]),
     "boa_cc_filter": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int,
                                 C.c_int, _P, _P, _P, _P, _P, _P]),
     "boa_paint_label": (C.c_int, [_P, C.c_size_t, C.c_int, _P, _P]),

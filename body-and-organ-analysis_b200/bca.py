@@ -33,8 +33,10 @@ class AggregatableBodyPart(enum.IntFlag):
 
 
 def subclassify_tissues(ct: torch.Tensor, body_regions: torch.Tensor, median_filtering: bool = False) -> torch.Tensor:
+    """subclassify_tissues (tissue/subclassification.py:10-63); median_filtering: the HU rules see the CT after an
+    in-plane 3x3 median (:20-36; the arrays here are [z, y, x] with z the slice axis), the report keeps the original."""
     if median_filtering:
-        raise NotImplementedError("--bca-median-filtering is not implemented on the GPU path (SURVEY.md 8f rank 4)")
+        ct = passes.median3x3_slices(ct)
     return passes.tissue_subclassify(ct, body_regions)
 
 

@@ -28,6 +28,8 @@ def get_parser() -> argparse.ArgumentParser:
     p.add_argument("--fast-bca", default=None, action="store_true")
     p.add_argument("--fast-total", default=None, action="store_true")
     p.add_argument("--bca-no-pdf", default=None, action="store_true", help="accepted; the PDF report is never produced")
+    p.add_argument("--bca-median-filtering", default=False, action="store_true",
+                   help="in-plane 3x3 median of the CT before the tissue HU thresholds")
     p.add_argument("--cnr-adjustment", default=None, action="store_true")
     p.add_argument("--skip-contrast-information", default=None, action="store_true")
     p.add_argument("--force-recompute", default=False, action="store_true")
@@ -45,6 +47,7 @@ def run(argv=None) -> None:
     fast_total = args.fast_total if args.fast_total is not None else env_bool("FAST_TOTAL")
     from .commands import analyze_ct
     out, stats = analyze_ct(args.input_image, args.output_dir, models=models, fast_bca=fast_bca, fast_total=fast_total,
+                            bca_median_filtering=bool(args.bca_median_filtering),
                             cnr_adjustment=bool(args.cnr_adjustment), device=device,
                             recompute=args.force_recompute, weights_root=args.weights or os.environ.get("TOTALSEG_WEIGHTS_PATH"))
     logging.getLogger(__name__).info("results in %s: %s", out, stats)

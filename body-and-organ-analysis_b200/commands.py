@@ -29,7 +29,8 @@ def range_warning(ct: np.ndarray) -> None:
 
 
 def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_folder: Path | None = None,
-               models=("total", "bca"), fast_bca: bool = False, fast_total: bool = False, cnr_adjustment: bool = True,
+               models=("total", "bca"), fast_bca: bool = False, fast_total: bool = False,
+               bca_median_filtering: bool = False, cnr_adjustment: bool = True,
                device: str = "gpu",
                recompute: bool = True, weights_root: str | None = None, zoo: ModelZoo | None = None, **_ignored):
     """NIfTI in -> segmentations + measurement JSONs out.  Returns (output folder, stats dict) like the reference."""
@@ -54,7 +55,8 @@ def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_f
     t0 = time.time()
     ct = torch.from_numpy(ct_np).pin_memory().to(dev, non_blocking=True)
     res = analyze_volume(ct, (zooms[2], zooms[1], zooms[0]), zoo, models=tuple(models), fast_bca=fast_bca,
-                         fast_total=fast_total, cnr_adjustment=cnr_adjustment)
+                         fast_total=fast_total, cnr_adjustment=cnr_adjustment,
+                         median_filtering=bca_median_filtering)
     stats["inference_time"] = time.time() - t0
 
     def write(name, tensor, labels=None):

@@ -486,6 +486,52 @@ extern "C" int boa_tissue_subclassify(const void* d_ct, int ct_dtype, const uint
   return BOA_OK;
 }
 
+// ------------------------------------------------------------------------------------------ in-plane median
+// scipy.ndimage.median_filter(image, size=[1, 3, 3]) of subclassify_tissues(median_filtering=True)
+// (_external/body_composition_analysis/tissue/subclassification.py:20-36): 3x3 median inside every slice, boundary
+// mode "reflect" (index -1 -> 0, n -> n-1).  Exact for integer HU: a 19-exchange median-of-9 network on int16.
+namespace boa {
+__device__ __forceinline__ void med_cswap(int& a, int& b) {
+  const int lo = a < b ? a : b, hi = a < b ? b : a;
+  a = lo; b = hi;
+}
+__global__ void __launch_bounds__(256)
+median3x3_kernel(const int16_t* __restrict__ in, int D, int H, int W, int16_t* __restrict__ out) {
+  const size_t n = (size_t)D * H * W;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+    const int x = (int)(i % W), y = (int)((i / W) % H);
+    const int16_t* sl = in + (i - (size_t)y * W - x);
+    const int xs[3] = {x > 0 ? x - 1 : 0, x, x + 1 < W ? x + 1 : W - 1};
+    const int ys[3] = {y > 0 ? y - 1 : 0, y, y + 1 < H ? y + 1 : H - 1};
+    int p[9];
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) p[a * 3 + b] = sl[(size_t)ys[a] * W + xs[b]];
+    // Paeth's median-of-9 network
+    med_cswap(p[1], p[2]); med_cswap(p[4], p[5]); med_cswap(p[7], p[8]);
+    med_cswap(p[0], p[1]); med_cswap(p[3], p[4]); med_cswap(p[6], p[7]);
+    med_cswap(p[1], p[2]); med_cswap(p[4], p[5]); med_cswap(p[7], p[8]);
+    med_cswap(p[0], p[3]); med_cswap(p[5], p[8]); med_cswap(p[4], p[7]);
+    med_cswap(p[3], p[6]); med_cswap(p[1], p[4]); med_cswap(p[2], p[5]);
+    med_cswap(p[4], p[7]); med_cswap(p[4], p[2]); med_cswap(p[6], p[4]);
+    med_cswap(p[4], p[2]);
+    out[i] = (int16_t)p[4];
+  }
+}
+}  // namespace boa
+
+extern "C" int boa_median3x3_slices(const int16_t* d_in, const int32_t* shape, int16_t* d_out, void* stream) {
+  BOA_REQUIRE(d_in && d_out && shape && d_in != d_out, "boa_median3x3_slices: bad pointers (in place is not supported)");
+  BOA_REQUIRE(shape[0] > 0 && shape[1] > 0 && shape[2] > 0, "boa_median3x3_slices: bad shape");
+  const size_t n = (size_t)shape[0] * shape[1] * shape[2];
+  boa::median3x3_kernel<<<boa::grid_for(n, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(d_in, shape[0], shape[1],
+                                                                                           shape[2], d_out);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
 extern "C" int boa_slice_label_stats(const uint8_t* d_labels, const uint8_t* d_mask, int mask_value, const void* d_ct,
                                      int ct_dtype, int Z, size_t slice_voxels, int n_labels, uint64_t* d_counts,
                                      int64_t* d_hu_sums, void* stream) {

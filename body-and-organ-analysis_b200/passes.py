@@ -85,6 +85,17 @@ def label_set_mask(labels: torch.Tensor, label_ids, ct: torch.Tensor | None = No
     return out
 
 
+def median3x3_slices(ct: torch.Tensor) -> torch.Tensor:
+    """scipy.ndimage.median_filter(ct, size=[1, 3, 3]) (mode "reflect") of an int16 [z, y, x] volume."""
+    _chk(ct)
+    if ct.dtype != torch.int16 or ct.dim() != 3:
+        raise TypeError("median3x3_slices needs an int16 [z, y, x] volume")
+    out = torch.empty_like(ct)
+    with torch.cuda.device(ct.device):
+        _lib.check(_lib.lib().boa_median3x3_slices(_lib.ptr(ct), _lib.i32x3(ct.shape), _lib.ptr(out), _lib.stream_ptr()))
+    return out
+
+
 def erode_box(mask: torch.Tensor, before: int = 3, after: int = 2) -> torch.Tensor:
     """erode_region (compute/measurements.py:61-71): 6^3 footprint padded at the end => offsets -3..+2."""
     _chk(mask)

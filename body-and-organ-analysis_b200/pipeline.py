@@ -255,7 +255,7 @@ class HostStager:
 def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total", "bca"), fast_bca: bool = False,
                    cnr_adjustment: bool = False, dist_ctx: DistContext | None = None,
                    stager: HostStager | None = None, fast_total: bool = False,
-                   postprocess: bool = True) -> VolumeResult:
+                   postprocess: bool = True, median_filtering: bool = False) -> VolumeResult:
     """compute_all_models + run_pipeline numerics for one CT already on the device (int16 [z,y,x]).
 
     spacing_zyx: voxel spacing of the array axes.  `total` expects 1.5 mm (resampling is identity there,
@@ -342,7 +342,7 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         if stager is not None:
             stager.stage("ct_pfav", res.ct_pfav)
     if "bca" in models:
-        res.tissues = bca.subclassify_tissues(ct, res.body_regions)
+        res.tissues = bca.subclassify_tissues(ct, res.body_regions, median_filtering)
         if stager is not None:
             stager.stage("tissues", res.tissues)
         sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])

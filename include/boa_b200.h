@@ -186,6 +186,11 @@ int boa_resample_axis_cubic(const void* d_in, int in_dtype, size_t outer, int n_
 int boa_resample_nearest_u8(const uint8_t* d_in, const int32_t* in_shape, const int32_t* out_shape, uint8_t* d_out,
                             void* stream);
 
+/* In-plane 3x3 median of every z-slice, boundary mode "reflect": scipy.ndimage.median_filter(image, size=[1,3,3]) of
+ * subclassify_tissues(median_filtering=True) (_external/body_composition_analysis/tissue/subclassification.py:20-36,
+ * CLI --bca-median-filtering).  int16 [z][y][x] -> int16, not in place. */
+int boa_median3x3_slices(const int16_t* d_in, const int32_t* shape, int16_t* d_out, void* stream);
+
 /* Connected-component post-processing of the body-composition label maps (between the networks and the tissue rules,
  * _external/body_composition_analysis/infer/infer.py:81-89):
  *   postprocess_region_segmentation (body_regions/postprocess.py:8-40): skimage.measure.label (26-connected) +

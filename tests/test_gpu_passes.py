@@ -205,3 +205,17 @@ def test_resample_identity_and_errors(cuda):
     assert resample_labels_nearest(lab, (8, 9, 10)) is lab
     with pytest.raises(TypeError):
         resample_volume_cubic(ct.to(torch.float64), (1.0, 1.0, 1.0), 1.5)
+
+
+@pytest.mark.parametrize("shape", [(5, 33, 47), (3, 1, 9), (2, 16, 1), (4, 64, 64)])
+def test_median3x3_slices_vs_scipy(cuda, shape):
+    """--bca-median-filtering: scipy.ndimage.median_filter(image, size=[1, 3, 3]) (subclassification.py:33-36)."""
+    from scipy import ndimage
+    rng = np.random.default_rng(21)
+    ct = rng.integers(-1100, 3100, size=shape).astype(np.int16)
+    got = passes.median3x3_slices(_dev(ct)).cpu().numpy()
+    assert np.array_equal(got, ndimage.median_filter(ct, size=[1, 3, 3]))
+    regions = rng.integers(0, 12, size=shape).astype(np.uint8)
+    from boa_b200 import bca
+    tis = bca.subclassify_tissues(_dev(ct), _dev(regions), median_filtering=True).cpu().numpy()
+    assert np.array_equal(tis, op.subclassify_tissues(ndimage.median_filter(ct, size=[1, 3, 3]), regions))
