@@ -26,7 +26,8 @@
 namespace boa {
 
 constexpr int MMA_THREADS = 192;        // producer warp, MMA warp, 4 epilogue warps
-constexpr int MMA_THREADS_FUSED = 320;  // + 4 operand-transform warps (normalise + LeakyReLU of the INPUT)
+constexpr int LDN_LOADER_WARPS = 8;     // fused-normalisation variant: loader warps instead of the TMA producer
+constexpr int LDN_THREADS = 32 * (1 + 4 + LDN_LOADER_WARPS);  // MMA warp, 4 epilogue warps, loaders = 416
 constexpr int TILE_X = 8, TILE_Y = 16;
 constexpr int XB = TILE_X + 2, YB = TILE_Y + 2, SLAB = XB * YB;  // 180 halo positions per z-plane
 
@@ -38,8 +39,9 @@ struct ConvMmaParams {
   int B, kc_count, Cout, D, H, W, zt;
   int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
   int in_groups_total, in_group_off;
-  // fused input transform: the source tensor holds the producer's RAW conv output; y = lrelu(x * scale + shift) is
-  // applied to the A tile in shared memory between TMA arrival and MMA issue (per (batch item, input channel))
+  // fused input normalisation (conv3_fold_ldnorm_kernel): in_raw holds the producer's RAW conv output; loader warps
+  // apply y = lrelu(x * scale + shift) per (batch item, input channel) on the way from global to shared memory
+  const __half* in_raw;   // base of the raw C8 tensor (same view as the tensor map of the unfused kernel)
   const float* in_scale;  // [B][in_channels] or nullptr
   const float* in_shift;
   int in_channels;
@@ -96,8 +98,8 @@ __device__ __forceinline__ void issue_chunk(uint64_t a_base, uint64_t b_base, ui
   }
 }
 
-template <int NC, bool FUSE>
-__global__ void __launch_bounds__(FUSE ? MMA_THREADS_FUSED : MMA_THREADS, 1)
+template <int NC>
+__global__ void __launch_bounds__(MMA_THREADS, 1)
 conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const int zb = p.zt + 2;
@@ -114,7 +116,6 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
   uint64_t* empty = bars + 4;    // [4] MMA -> TMA
   uint64_t* tfull = bars + 8;    // [2] MMA -> epilogue
   uint64_t* tempty = bars + 10;  // [2] epilogue -> MMA
-  uint64_t* ready = bars + 12;   // [4] transform warps -> MMA (FUSE only)
   uint64_t* bfull = bars + 16;   // [1] resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,7 +125,6 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
     for (int i = 0; i < 4; ++i) {
       mbar_init(&full[i], 1);
       mbar_init(&empty[i], 1);
-      mbar_init(&ready[i], 128);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -195,7 +195,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
         tc_fence_after();
         const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
         for (int kc = 0; kc < p.kc_count; ++kc) {
-          mbar_wait(FUSE ? &ready[st] : &full[st], ph);
+          mbar_wait(&full[st], ph);
           tc_fence_after();
           const uint32_t a0 = smem_u32(ring + (size_t)st * stage_bytes);
           const uint64_t a_base = a_desc0 + (uint64_t)(a0 >> 4);
@@ -212,57 +212,6 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
       }
     }
     __syncwarp();
-  } else if (FUSE && warp >= 6) {
-    // ===================================================================== operand transform (warps 6..9)
-    // InstanceNorm affine + LeakyReLU of the producer layer, applied in place to the A tile (the zero halo outside the
-    // volume stays zero: padding applies to the ACTIVATED tensor).  Same fp32 operations as norm_lrelu_kernel.
-    const int tid = threadIdx.x - 192;
-    const int per_group = zb * SLAB;
-    int st = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int nt, b, tz, ty, tx;
-      decode_tile(tile, p, nt, b, tz, ty, tx);
-      const int z0 = tz * p.zt - 1, y0 = ty * TILE_Y - 1, x0 = tx * TILE_X - 1;
-      for (int kc = 0; kc < p.kc_count; ++kc) {
-        float a[2][8], sh[2][8];
-#pragma unroll
-        for (int g = 0; g < 2; ++g) {
-          const float4* ps = reinterpret_cast<const float4*>(p.in_scale + (size_t)b * p.in_channels + kc * 16 + g * 8);
-          const float4* pf = reinterpret_cast<const float4*>(p.in_shift + (size_t)b * p.in_channels + kc * 16 + g * 8);
-          const float4 a0 = __ldg(ps), a1 = __ldg(ps + 1), s0 = __ldg(pf), s1 = __ldg(pf + 1);
-          a[g][0] = a0.x; a[g][1] = a0.y; a[g][2] = a0.z; a[g][3] = a0.w;
-          a[g][4] = a1.x; a[g][5] = a1.y; a[g][6] = a1.z; a[g][7] = a1.w;
-          sh[g][0] = s0.x; sh[g][1] = s0.y; sh[g][2] = s0.z; sh[g][3] = s0.w;
-          sh[g][4] = s1.x; sh[g][5] = s1.y; sh[g][6] = s1.z; sh[g][7] = s1.w;
-        }
-        mbar_wait(&full[st], ph);
-        uint4* tile_a = reinterpret_cast<uint4*>(ring + (size_t)st * stage_bytes);
-        for (int pos = tid; pos < per_group; pos += 128) {
-          const int z = pos / SLAB, r = pos - z * SLAB, y = r / XB, x = r - y * XB;
-          const int gz = z0 + z, gy = y0 + y, gx = x0 + x;
-          if (gz < 0 || gz >= p.D || gy < 0 || gy >= p.H || gx < 0 || gx >= p.W) continue;
-#pragma unroll
-          for (int g = 0; g < 2; ++g) {
-            uint4 raw = tile_a[g * per_group + pos];
-            __half2* h = reinterpret_cast<__half2*>(&raw);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              float2 f = __half22float2(h[e]);
-              f.x = __fadd_rn(__fmul_rn(f.x, a[g][2 * e]), sh[g][2 * e]);
-              f.y = __fadd_rn(__fmul_rn(f.y, a[g][2 * e + 1]), sh[g][2 * e + 1]);
-              f.x = f.x > 0.f ? f.x : __fmul_rn(f.x, p.slope);
-              f.y = f.y > 0.f ? f.y : __fmul_rn(f.y, p.slope);
-              h[e] = __floats2half2_rn(f.x, f.y);
-            }
-            tile_a[g * per_group + pos] = raw;
-          }
-        }
-        fence_proxy_async();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        mbar_arrive(&ready[st]);
-        if (++st == nstage) { st = 0; ph ^= 1; }
-      }
-    }
   } else {
     // ===================================================================== epilogue (warps 2..5)
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
@@ -301,6 +250,208 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
   if (warp == 1) tmem_dealloc(tbase, 512);
 }
 
+// ================================================================================================ fused normalisation
+// conv3_fold_kernel<32> for a layer whose input is the RAW output of the previous conv of the same stage: the
+// InstanceNorm affine + LeakyReLU of that producer is applied while the operand is staged, so the producer's
+// standalone normalise pass (read + write of the whole tensor) disappears.  An earlier variant transformed the tile
+// in place in shared memory after TMA had written it (profiles/r01_fused_norm.txt): a wash, because the extra LDS +
+// STS land on the shared-memory port the N = 96 MMAs already saturate.  Here the TMA producer is REPLACED: eight
+// loader warps read the raw tensor with plain 16-byte loads (8 in flight per thread), transform in registers and
+// store the tile once - the same shared-memory traffic as the TMA write it replaces.  Out-of-volume halo positions
+// are stored as zeros (the conv pads the ACTIVATED tensor).  Same fp32 operations as norm_lrelu_kernel, so the
+// result is bit-identical to the unfused schedule (tests/test_gpu_network.py).  Weights of all K chunks stay resident
+// (Cout = 32: 27 KB per chunk); 13 warps share the register file (ptxas caps 416 threads at 128 registers - the
+// allocation granularity is four warps), hence the 16-column epilogue strips.
+// Measured (B200, 32->32 at 128^3, batch 8): 1.18 ms against 0.81 ms unfused + 0.35 ms for the pass it removes - the
+// loaders (two rounds of 8 loads per stage, ~2 us of exposed latency each) do not keep up with the 3.5 us the MMAs
+// of a stage take; holding a thread's whole share of a stage in registers (15 loads) spills at 128 registers and ran
+// at 2.5 ms.  So this is an opt-in (BOA_B200_LDNORM=1) until the loader is rebuilt on cp.async / 12 warps.
+// ws: warp-private shared-memory slot [8 scale][8 shift] (broadcast float4 reads: the registers go to loads in flight)
+__device__ __forceinline__ uint4 ldn_transform(const uint4& raw, const float* ws, float slope) {
+  uint4 o;
+  const __half2* h = reinterpret_cast<const __half2*>(&raw);
+  __half2* r = reinterpret_cast<__half2*>(&o);
+  const float4 a0 = *reinterpret_cast<const float4*>(ws), a1 = *reinterpret_cast<const float4*>(ws + 4);
+  const float4 s0 = *reinterpret_cast<const float4*>(ws + 8), s1 = *reinterpret_cast<const float4*>(ws + 12);
+  const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+  const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    float2 f = __half22float2(h[e]);
+    f.x = __fadd_rn(__fmul_rn(f.x, a[2 * e]), sh[2 * e]);
+    f.y = __fadd_rn(__fmul_rn(f.y, a[2 * e + 1]), sh[2 * e + 1]);
+    f.x = f.x > 0.f ? f.x : __fmul_rn(f.x, slope);
+    f.y = f.y > 0.f ? f.y : __fmul_rn(f.y, slope);
+    r[e] = __floats2half2_rn(f.x, f.y);
+  }
+  return o;
+}
+
+__global__ void __launch_bounds__(LDN_THREADS, 1)
+conv3_fold_ldnorm_kernel(const ConvMmaParams p) {
+  constexpr int NC = 32;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  const int zb = p.zt + 2;
+  const uint32_t a_bytes = 2u * zb * SLAB * 16u;
+  constexpr uint32_t b_bytes = 9u * 96u * NC;
+  const uint32_t bres_bytes = (uint32_t)p.kc_count * b_bytes;
+  uint8_t* const ring = smem + bres_bytes;
+  const int nstage = p.stages;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * a_bytes);
+  uint64_t* full = bars;         // [4] loaders (256 arrivals) -> MMA
+  uint64_t* empty = bars + 4;    // [4] MMA -> loaders
+  uint64_t* tfull = bars + 8;    // [2] MMA -> epilogue
+  uint64_t* tempty = bars + 10;  // [2] epilogue -> MMA
+  uint64_t* bfull = bars + 12;   // [1] resident weights landed
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 4; ++i) {
+      mbar_init(&full[i], 32 * LDN_LOADER_WARPS);
+      mbar_init(&empty[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull[i], 1);
+      mbar_init(&tempty[i], 4);
+    }
+    mbar_init(bfull, 1);
+    fence_barrier_init();
+  }
+  if (warp == 0) {
+    tmem_alloc(tmem_slot, 512);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tbase = *tmem_slot;
+
+  if (warp == 0) {
+    // ===================================================================== weights + MMA issuer (one elected thread)
+    if (elect_one()) {
+      mbar_arrive_expect_tx(bfull, bres_bytes);
+      for (int kc = 0; kc < p.kc_count; ++kc)
+        bulk_load(smem + (size_t)kc * b_bytes, reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)kc * b_bytes,
+                  b_bytes, bfull);
+      mbar_wait(bfull, 0);
+      tc_fence_after();
+      uint32_t tcount = 0;
+      int st = 0;
+      uint32_t ph = 0;
+      const uint32_t a_lbo = (uint32_t)zb * SLAB * 16u;
+      const uint64_t a_desc0 = umma_desc(0, a_lbo, XB * 16u);
+      const uint64_t b_desc0 = umma_desc(0, 3u * NC * 16u, 128u);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+        const uint32_t buf = tcount & 1;
+        mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
+        tc_fence_after();
+        const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
+        for (int kc = 0; kc < p.kc_count; ++kc) {
+          mbar_wait(&full[st], ph);
+          tc_fence_after();
+          const uint64_t a_base = a_desc0 + (uint64_t)(smem_u32(ring + (size_t)st * a_bytes) >> 4);
+          const uint64_t b_base = b_desc0 + (uint64_t)((smem_u32(smem) + (uint32_t)kc * b_bytes) >> 4);
+          if (p.zt == 8) issue_chunk<NC, 8>(a_base, b_base, dcol0, kc == 0, true, 8);
+          else if (p.zt == 4) issue_chunk<NC, 4>(a_base, b_base, dcol0, kc == 0, true, 4);
+          else issue_chunk<NC, 0>(a_base, b_base, dcol0, kc == 0, true, p.zt);
+          umma_commit(&empty[st]);
+          if (++st == nstage) { st = 0; ph ^= 1; }
+        }
+        umma_commit(&tfull[buf]);
+      }
+    }
+    __syncwarp();
+  } else if (warp <= 4) {
+    // ===================================================================== epilogue (warps 1..4)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    uint32_t tcount = 0;
+    const int out_groups = p.Cout / 8;
+    RunningStats16 run;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+      int nt, b, tz, ty, tx;
+      decode_tile(tile, p, nt, b, tz, ty, tx);
+      const uint32_t buf = tcount & 1;
+      mbar_wait(&tfull[buf], (tcount >> 1) & 1);
+      tc_fence_after();
+      const int x = tx * TILE_X + (row & 7), y = ty * TILE_Y + (row >> 3);
+      const bool rowvalid = (x < p.W) && (y < p.H);
+      const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(p.zt * NC);
+      const size_t zstride = (size_t)p.H * p.W, gstride = (size_t)p.D * zstride;
+#pragma unroll
+      for (int chunk = 0; chunk < NC / 16; ++chunk) {
+        const int cbase = chunk * 16;
+        uint4* dst = reinterpret_cast<uint4*>(p.out) +
+                     ((((size_t)b * out_groups + (cbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
+        conv_epilogue_strip16(tlane + chunk * 16, NC, p.zt, p.bias + cbase, rowvalid, tz * p.zt, p.D, dst, zstride,
+                              gstride, lane, b * p.Cout, chunk & 1, run, p.stats);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[buf]);
+    }
+    stats_flush16(run, p.stats, lane);
+  } else {
+    // ===================================================================== loaders (warps 5..12)
+    const int lt = threadIdx.x - 160;  // 0..255
+    const int g = lt >> 7;             // channel group (of the two of a K chunk) this thread stages
+    const int t = lt & 127;
+    const int per_group = zb * SLAB;
+    // (dynamic shared memory: a static array would make the 227 KB opt-in of the attribute invalid)
+    float* wsl = reinterpret_cast<float*>(bars + 16) + (warp - 5) * 16;
+    constexpr int U = 8;               // loads in flight per thread (two rounds per stage)
+    int st = 0;
+    uint32_t ph = 0;
+    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+      int nt, b, tz, ty, tx;
+      decode_tile(tile, p, nt, b, tz, ty, tx);
+      const int z0 = tz * p.zt - 1, y0 = ty * TILE_Y - 1, x0 = tx * TILE_X - 1;
+      for (int kc = 0; kc < p.kc_count; ++kc) {
+        // scale / shift of this warp's 8 channels into its shared-memory slot (previous readers are past it: they
+        // arrived on full[] after their last transform, and a warp runs its stages in order)
+        __syncwarp();
+        if (lane < 16)
+          wsl[lane] = lane < 8 ? __ldg(p.in_scale + (size_t)b * p.in_channels + kc * 16 + g * 8 + lane)
+                               : __ldg(p.in_shift + (size_t)b * p.in_channels + kc * 16 + g * 8 + lane - 8);
+        __syncwarp();
+        const uint4* plane0 = reinterpret_cast<const uint4*>(p.in_raw) +
+                              (size_t)(b * p.in_groups_total + p.in_group_off + 2 * kc + g) * p.D * p.H * p.W;
+        mbar_wait(&empty[st], ph ^ 1);
+        uint4* dst = reinterpret_cast<uint4*>(ring + (size_t)st * a_bytes) + g * per_group;
+        for (int base = t; base < per_group; base += 128 * U) {
+          uint4 r[U];
+          uint32_t okmask = 0;
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int pos = base + u * 128;
+            if (pos < per_group) {
+              const int z = pos / SLAB, rr = pos - z * SLAB, y = rr / XB, x = rr - y * XB;
+              const int gz = z0 + z, gy = y0 + y, gx = x0 + x;
+              if (gz >= 0 && gz < p.D && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+                okmask |= 1u << u;
+                r[u] = __ldg(plane0 + ((size_t)gz * p.H + gy) * p.W + gx);
+              }
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < U; ++u) {
+            const int pos = base + u * 128;
+            if (pos < per_group)
+              dst[pos] = (okmask >> u) & 1u ? ldn_transform(r[u], wsl, p.slope) : make_uint4(0u, 0u, 0u, 0u);
+          }
+        }
+        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+        mbar_arrive(&full[st]);
+        if (++st == nstage) { st = 0; ph ^= 1; }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc(tbase, 512);
+}
+
 // ================================================================================================ host side
 struct ConvMmaPlan {
   CUtensorMap tmap;
@@ -308,7 +459,7 @@ struct ConvMmaPlan {
   __half* d_bpacked = nullptr;
   float* d_bias = nullptr;
   int nc = 32;
-  bool fused = false;
+  bool fused = false;  // conv3_fold_ldnorm_kernel: the input is the producer's raw output, normalised while staged
   size_t smem = 0;
   int grid = 0;
   double macs = 0;
@@ -346,9 +497,10 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   p.ntaps = ntaps;
   p.tmap_merged = c8_tmap_merged() ? 1 : 0;
   p.in_scale = d_in_scale; p.in_shift = d_in_shift; p.in_channels = cin_w; p.slope = slope;
+  p.in_raw = src.base;
   pl->fused = d_in_scale != nullptr;
-  if (pl->fused && (cin_w % 16 != 0 || taps_on_k)) {
-    set_error("conv_mma: fused input transform needs Cin %% 16 == 0");
+  if (pl->fused && (cin_w % 16 != 0 || taps_on_k || NC != 32 || p.n_ntiles != 1)) {
+    set_error("conv_mma: fused input normalisation needs Cin %% 16 == 0 and Cout == 32");
     conv_mma_plan_destroy(pl);
     return nullptr;
   }
@@ -394,25 +546,29 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   // the ring then carries 58 KB instead of 85 KB per K chunk (the convs are bound by what TMA can bring into an SM)
   // and, for Cin = 32, a third stage fits.  BOA_B200_BRES=0 disables it.
   const size_t a_stage = 2 * (size_t)(zt + 2) * SLAB * 16, b_chunk = (size_t)ntaps * 96 * (size_t)NC;
-  const size_t smem_cap = (size_t)MAX_DYN_SMEM - 256;
+  const size_t smem_cap = (size_t)MAX_DYN_SMEM - 1024;  // barriers + the loaders' scale / shift slots
   const char* bres_env = getenv("BOA_B200_BRES");
-  p.b_resident = (p.n_ntiles == 1 && !pl->fused && !(bres_env && atoi(bres_env) == 0) &&
+  p.b_resident = (p.n_ntiles == 1 && (pl->fused || !(bres_env && atoi(bres_env) == 0)) &&
                   p.kc_count * b_chunk + 2 * a_stage <= smem_cap) ? 1 : 0;
+  if (pl->fused && !p.b_resident) {
+    set_error("conv_mma: fused input normalisation needs the weights of all %d K chunks resident", p.kc_count);
+    conv_mma_plan_destroy(pl);
+    return nullptr;
+  }
   const size_t stage = a_stage + (p.b_resident ? 0 : b_chunk);
   const size_t fixed = p.b_resident ? p.kc_count * b_chunk : 0;
   int stages = (int)((smem_cap - fixed) / stage);
   stages = stages > 4 ? 4 : stages;
-  if (pl->fused) stages = 2;
   if (stages < 2) {
     set_error("conv_mma: two stages of %zu bytes do not fit in shared memory", stage);
     conv_mma_plan_destroy(pl);
     return nullptr;
   }
   p.stages = stages;
-  pl->smem = fixed + (size_t)stages * stage + 192;
+  pl->smem = fixed + (size_t)stages * stage + 768;
   cudaError_t e = cudaSuccess;
-  for (const void* fn : {(const void*)conv3_fold_kernel<64, false>, (const void*)conv3_fold_kernel<32, false>,
-                         (const void*)conv3_fold_kernel<64, true>, (const void*)conv3_fold_kernel<32, true>}) {
+  for (const void* fn : {(const void*)conv3_fold_kernel<64>, (const void*)conv3_fold_kernel<32>,
+                         (const void*)conv3_fold_ldnorm_kernel}) {
     cudaError_t e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
     if (e2 != cudaSuccess) e = e2;
   }
@@ -441,17 +597,12 @@ int conv_mma_launch(ConvMmaPlan* pl, cudaStream_t s, int nb) {
     p.B = nb;
     pl->grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
   }
-  if (pl->fused) {
-    if (pl->nc == 64)
-      conv3_fold_kernel<64, true><<<pl->grid, MMA_THREADS_FUSED, pl->smem, s>>>(pl->tmap, pl->prm);
-    else
-      conv3_fold_kernel<32, true><<<pl->grid, MMA_THREADS_FUSED, pl->smem, s>>>(pl->tmap, pl->prm);
-  } else {
-    if (pl->nc == 64)
-      conv3_fold_kernel<64, false><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
-    else
-      conv3_fold_kernel<32, false><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
-  }
+  if (pl->fused)
+    conv3_fold_ldnorm_kernel<<<pl->grid, LDN_THREADS, pl->smem, s>>>(pl->prm);
+  else if (pl->nc == 64)
+    conv3_fold_kernel<64><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
+  else
+    conv3_fold_kernel<32><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }

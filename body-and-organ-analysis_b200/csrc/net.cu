@@ -481,19 +481,20 @@ static int build_lane(boa_net* net, int li) {
       if (!st.fold) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_FOLD;
     } else if (is3(ks, 3) && is3(stride, 1) && cout % 32 == 0 && cin_padded <= src.groups * 8) {
-      // the producer is the previous conv of this stage: read its RAW output and normalise it while staging the
-      // operand (no standalone InstanceNorm / LeakyReLU pass for that tensor)
-      // Measured (profiles/r01_fused_norm.txt): the in-place transform costs the consumer exactly what the standalone
-      // pass saves, because the N = 96 / 192 MMAs already saturate the shared-memory port - so it is opt-in.
-      const bool fuse = producer && !producer->is_tconv && cin % 16 == 0 && producer->cout == cin &&
-                        getenv("BOA_B200_FUSE_NORM") != nullptr;
+      // The producer is the previous conv of this stage and nothing else reads its output: this conv CAN read the RAW
+      // tensor and normalise it while staging the operand (conv3_fold_ldnorm_kernel: loader warps on the global ->
+      // shared path), so that the producer's standalone InstanceNorm / LeakyReLU pass disappears.  Built for Cout = 32
+      // with all weights resident (Cin <= 64) - the two full-resolution conv1 layers.  Bit-identical, but measured
+      // slower than conv + pass (see the kernel): opt-in with BOA_B200_LDNORM=1.
+      const bool fuse = producer && !producer->is_tconv && cin % 16 == 0 && producer->cout == cin && cout == 32 &&
+                        cin <= 64 && getenv("BOA_B200_LDNORM") != nullptr;
       if (fuse) {
         st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, producer->raw_view, B, st.raw,
                                        st.d_stats, false, producer->d_scale, producer->d_shift, a.leaky_slope);
         if (st.fold) producer->norm_fused_downstream = true;
-      } else {
-        st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats);
       }
+      if (!st.fold)
+        st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats);
       if (!st.fold) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_FOLD;
     } else if (is3(ks, 3) && is3(stride, 2) && src_s2d.base && cin % 16 == 0 && cout % 64 == 0) {

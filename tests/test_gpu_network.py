@@ -75,3 +75,25 @@ def test_totalseg_geometry_one_patch(cuda):
     # the real TotalSegmentator geometry at a 64^3 patch (6 stages, 32..320 features): every layer shape class
     arch = _arch((64, 64, 64), 32, 320, 6, 25)
     _compare(arch, 3, 1, 1, TOL)
+
+
+def test_fused_input_normalisation_is_bit_identical(cuda, monkeypatch):
+    """conv3_fold_ldnorm_kernel (the conv1 layers with 32 outputs read the RAW output of conv0 and normalise it on the
+    global -> shared path) against the unfused schedule (standalone normalise pass): same fp32 operations, so the
+    logits must be identical bit for bit - also for a partial batch and a volume that is not a multiple of the tile."""
+    for patch, n_patches, max_batch in (((32, 32, 32), 3, 2), ((24, 40, 16), 2, 4)):
+        arch = _arch(patch, 32, 128, 3, 5)
+        sd = zoo.random_state_dict(arch, 17)
+        x = torch.from_numpy(np.random.default_rng(1).standard_normal((n_patches, 1, *patch)).astype(np.float32)).cuda()
+        outs = []
+        for no_fuse in (False, True):
+            if no_fuse:
+                monkeypatch.delenv("BOA_B200_LDNORM", raising=False)
+            else:
+                monkeypatch.setenv("BOA_B200_LDNORM", "1")
+            net = Network(arch, sd, 0, max_batch)
+            net.set_graph(False)
+            outs.append(net.forward_logits(x).cpu().numpy())
+            net.close()
+        assert np.isfinite(outs[0]).all()
+        assert np.array_equal(outs[0], outs[1]), np.abs(outs[0] - outs[1]).max()
