@@ -48,6 +48,9 @@ def test_cli_parser_flags():
     a = get_parser().parse_args(["--input-image", "x.nii.gz", "--models", "total+bca", "-d", "gpu", "--fast-bca",
                                  "--bca-no-pdf", "-o", "out"])
     assert str(a.input_image) == "x.nii.gz" and a.models == "total+bca" and a.fast_bca and a.bca_no_pdf
+    assert not a.bca_median_filtering and a.fast_total is None
+    b = get_parser().parse_args(["-i", "x.nii.gz", "-m", "total", "--fast-total", "--bca-median-filtering"])
+    assert b.fast_total and b.bca_median_filtering  # body_organ_analysis/cli.py:96-110,155-163
     with pytest.raises(SystemExit):
         get_parser().parse_args(["--models", "foo"])
     with pytest.raises(SystemExit):

@@ -114,3 +114,37 @@ def test_macs_per_patch_matches_baseline_table():
 def test_resampled_depth_and_weight_keys():
     from boa_b200.resample import resampled_depth
     assert resampled_depth(512, 1.5, 5.0) == 154 and resampled_depth(300, 1.5, 5.0) == 90
+
+
+def test_resampling_shapes_and_slice_weights_follow_scipy():
+    """zoomed_shape == scipy.ndimage.zoom's output shape for the float32 header spacings change_spacing uses
+    (totalsegmentator/resampling.py:171-176); slice_weights == multiplicities of scipy's order-0 source indices."""
+    from scipy import ndimage
+    from boa_b200.postprocess import slice_weights
+    from boa_b200.resample import resampled_depth, zoomed_shape
+    for shape, spacing, target in [((37, 44, 52), (2.0, 0.9765625, 0.9765625), 1.5), ((40, 33, 29), (1.0, 1.5, 0.8), 1.5),
+                                   ((61, 30, 30), (0.7, 0.7, 0.7), 3.0), ((9, 9, 9), (1.5, 1.5, 1.5), 1.5)]:
+        zoom = [np.float64(np.float32(s)) / target for s in spacing]
+        ref = ndimage.zoom(np.zeros(shape, np.uint8), zoom, order=0).shape
+        assert zoomed_shape(shape, spacing, target) == ref
+    for z_in, z_out in [(154, 512), (36, 120), (31, 103), (7, 7), (2, 9)]:
+        lab = np.arange(z_in, dtype=np.int32).reshape(z_in, 1, 1)
+        up = ndimage.zoom(lab, (z_out / z_in, 1, 1), order=0, mode="nearest")[:, 0, 0]
+        assert up.shape[0] == z_out
+        w = slice_weights(z_in, z_out, "cpu").numpy()
+        assert np.array_equal(w, np.bincount(up, minlength=z_in)) and w.sum() == z_out
+    assert resampled_depth(512, 1.5, 5.0) == 154
+
+
+def test_new_compute_entries_refuse_cpu_tensors():
+    """No CPU fallback for the passes added with resampling / post-processing / median filtering either."""
+    from boa_b200 import passes, postprocess, resample
+    ct = torch.zeros((4, 5, 6), dtype=torch.int16)
+    with pytest.raises(ValueError):
+        resample.resample_volume_cubic(ct, (1.0, 1.0, 1.0), 1.5)
+    with pytest.raises(ValueError):
+        resample.resample_labels_nearest(ct.to(torch.uint8), (8, 10, 12))
+    with pytest.raises(ValueError):
+        postprocess.postprocess_region_segmentation(ct.to(torch.uint8))
+    with pytest.raises(ValueError):
+        passes.median3x3_slices(ct)
