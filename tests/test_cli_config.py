@@ -50,7 +50,7 @@ def test_cli_parser_flags():
     assert str(a.input_image) == "x.nii.gz" and a.models == "total+bca" and a.fast_bca and a.bca_no_pdf
     assert not a.bca_median_filtering and a.fast_total is None
     b = get_parser().parse_args(["-i", "x.nii.gz", "-m", "total", "--fast-total", "--bca-median-filtering"])
-    assert b.fast_total and b.bca_median_filtering  # body_organ_analysis/cli.py:96-110,155-163
+    assert b.fast_total and b.bca_median_filtering  # body_organ_analysis/cli.py:155-163,175-187
     with pytest.raises(SystemExit):
         get_parser().parse_args(["--models", "foo"])
     with pytest.raises(SystemExit):
