@@ -291,6 +291,11 @@ def run_ours(a):
                 "per_launch": {"avg_ms": dom["ms"] / dom["launches"], "avg_flop": dom["flop"] / dom["launches"],
                                "patches_per_launch": a.batch},
                 "conv_time_share_of_forward": None, "kernels": per_kind}
+    # share of the step the dominant kernel accounts for (event-timed launches x batches per volume / step time), to
+    # be compared with its share in the ncu launch list of the same command (profiles/rNN_launches_summary.txt)
+    n_fwd = count_forwards(a)
+    batches = (n_fwd["total"] + n_fwd["bca"]) / float(a.batch) / max(world, 1)
+    roofline["share_of_step"] = dom["ms"] * batches / ms_step
 
     if rank == 0:
         cpu = None
