@@ -316,23 +316,31 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         # maps are back on the input grid; replicated slices map components one to one, so it runs here on the 5 mm
         # grid with every slice weighted by the number of output slices it becomes (postprocess.py)
         from .postprocess import postprocess_part_segmentation, postprocess_region_segmentation, slice_weights
-        weights = slice_weights(ct5.shape[0], ct.shape[0], ct.device)
-        if want_parts:
-            parts5 = segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx)
-            mark("body_parts_net")
+        # slices are REPLICATED on the way back (input thinner than 5 mm, the usual case): weighted labelling on the 5 mm
+        # grid is exact.  Input thicker than 5 mm: slices are dropped on the way back, which can split or join
+        # components, so the post-processing runs on the input grid like the reference's.
+        on_5mm = postprocess and ct5.shape[0] <= ct.shape[0]
+        weights = slice_weights(ct5.shape[0], ct.shape[0], ct.device) if on_5mm else None
+
+        def finish(net_out, fn, name):
+            mark(f"{name}_net")
+            if on_5mm:
+                net_out = fn(net_out, weights)
+            out = upsample_labels_nearest(net_out, ct.shape[0])
+            if postprocess and not on_5mm:
+                out = fn(out, None)
             if postprocess:
-                parts5 = postprocess_part_segmentation(parts5, weights)
-                mark("body_parts_postprocess")
-            res.body_parts = upsample_labels_nearest(parts5, ct.shape[0])
+                mark(f"{name}_postprocess")
+            return out
+
+        if want_parts:
+            res.body_parts = finish(segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx),
+                                    postprocess_part_segmentation, "body_parts")
             if stager is not None:
                 stager.stage("body_parts", res.body_parts)
         if want_regions:
-            regions5 = segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx)
-            mark("body_regions_net")
-            if postprocess:
-                regions5 = postprocess_region_segmentation(regions5, weights)
-                mark("body_regions_postprocess")
-            res.body_regions = upsample_labels_nearest(regions5, ct.shape[0])
+            res.body_regions = finish(segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx),
+                                      postprocess_region_segmentation, "body_regions")
         if stager is not None:
             stager.stage("body_regions", res.body_regions)
         mark("bca_nets")
