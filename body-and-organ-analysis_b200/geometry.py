@@ -69,3 +69,35 @@ def shard_patches(n_patches: int, world_size: int, rank: int) -> tuple[int, int]
     base, rem = divmod(n_patches, world_size)
     begin = rank * base + min(rank, rem)
     return begin, begin + base + (1 if rank < rem else 0)
+
+
+TRIPLE_SPLIT_VOXELS = 512 * 512 * 900  # totalsegmentator/nnunet.py:483
+TRIPLE_SPLIT_MARGIN = 20               # :495
+
+
+def needs_triple_split(shape, multimodel: bool, force_split: bool = False) -> bool:
+    """nnUNet_predict_image splits a volume into three overlapping z-parts when it is very large and several models
+    run on it (`total`), or when the caller forces it (the body-composition networks on more than 400 slices at 5 mm,
+    compute/inference.py:109-128): totalsegmentator/nnunet.py:483-492.  shape = array shape [z, y, x]."""
+    z = int(shape[0])
+    return bool(force_split or (int(np.prod([int(v) for v in shape], dtype=np.int64)) > TRIPLE_SPLIT_VOXELS and z > 200
+                                and multimodel))
+
+
+def triple_split_ranges(z: int, margin: int = TRIPLE_SPLIT_MARGIN):
+    """The three parts of nnunet.py:493-505 and how :582-586 stitches their predictions, along the slice axis:
+    [(part_lo, part_hi, keep_lo, keep_hi, dst_lo, dst_hi)] - predict volume[part_lo:part_hi], write its slices
+    [keep_lo:keep_hi] to out[dst_lo:dst_hi]."""
+    third = z // 3
+    parts = [(0, third + margin), (third + 1 - margin, 2 * third + margin), (2 * third + 1 - margin, z)]
+    keeps = [(0, third), (margin - 1, margin - 1 + third), (margin - 1, None)]
+    dsts = [(0, third), (third, 2 * third), (2 * third, z)]
+    out = []
+    for (plo, phi), (klo, khi), (dlo, dhi) in zip(parts, keeps, dsts):
+        if plo < 0 or phi > z or phi - plo <= 0:
+            raise ValueError(f"a volume of {z} slices is too short for the triple split (margin {margin})")
+        khi = (phi - plo) if khi is None else khi
+        if khi - klo != dhi - dlo:
+            raise ValueError(f"a volume of {z} slices is too short for the triple split (margin {margin})")
+        out.append((plo, phi, klo, khi, dlo, dhi))
+    return out

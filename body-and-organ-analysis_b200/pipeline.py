@@ -126,8 +126,21 @@ def _preprocess(ct: torch.Tensor, spec) -> tuple[torch.Tensor, list]:
 
 
 def segment_task(ct: torch.Tensor, zoo: ModelZoo, task_ids, folds, step_size: float, luts=None,
-                 dist_ctx: DistContext | None = None) -> torch.Tensor:
-    """One nnUNet_predict_image call on a volume that is already at the task's spacing: uint8 label map [z,y,x]."""
+                 dist_ctx: DistContext | None = None, force_split: bool = False) -> torch.Tensor:
+    """One nnUNet_predict_image call on a volume that is already at the task's spacing: uint8 label map [z,y,x].
+    Very large volumes (or force_split) are predicted as three overlapping z-parts and stitched, exactly where the
+    reference does it (totalsegmentator/nnunet.py:483-505,582-586) - each part is preprocessed on its own."""
+    from .geometry import needs_triple_split, triple_split_ranges
+    if needs_triple_split(ct.shape, len(task_ids) > 1, force_split):
+        out = torch.zeros(ct.shape, dtype=torch.uint8, device=ct.device)
+        for plo, phi, klo, khi, dlo, dhi in triple_split_ranges(int(ct.shape[0])):
+            part = _segment_task_whole(ct[plo:phi].contiguous(), zoo, task_ids, folds, step_size, luts, dist_ctx)
+            out[dlo:dhi] = part[klo:khi]
+        return out
+    return _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx)
+
+
+def _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx) -> torch.Tensor:
     out = torch.zeros(ct.shape, dtype=torch.uint8, device=ct.device)
     multi = len(task_ids) > 1
     for i, tid in enumerate(task_ids):
@@ -161,11 +174,15 @@ def segment_total_fast(ct_3mm: torch.Tensor, zoo: ModelZoo, dist_ctx: DistContex
     return segment_task(ct_3mm, zoo, [TOTAL_FAST_TASK_ID], [0], 0.5, None, dist_ctx)
 
 
+FORCE_SPLIT_THRESHOLD = 400  # slices at 5 mm (commands.py:155-170 -> compute/inference.py:109-128)
+
+
 def segment_bca_net(ct_5mm: torch.Tensor, zoo: ModelZoo, task: str, fast: bool,
                     dist_ctx: DistContext | None = None) -> torch.Tensor:
     tid = BODY_PARTS_TASK_ID if task == "body_parts" else BODY_REGIONS_TASK_ID
     folds = [0] if fast else [0, 1, 2, 3, 4]  # body_composition_analysis/tasks.py:15-48
-    return segment_task(ct_5mm, zoo, [tid], folds, 0.5, None, dist_ctx)
+    return segment_task(ct_5mm, zoo, [tid], folds, 0.5, None, dist_ctx,
+                        force_split=int(ct_5mm.shape[0]) > FORCE_SPLIT_THRESHOLD)
 
 
 @dataclass

@@ -148,3 +148,31 @@ def test_new_compute_entries_refuse_cpu_tensors():
         postprocess.postprocess_region_segmentation(ct.to(torch.uint8))
     with pytest.raises(ValueError):
         passes.median3x3_slices(ct)
+
+
+def test_triple_split_ranges_stitch_like_the_reference():
+    """Very large volumes are predicted in three overlapping z-parts (totalsegmentator/nnunet.py:483-505) and stitched
+    (:582-586).  With `prediction == input` the reference's index arithmetic (transcribed below on the slice axis) and
+    triple_split_ranges must rebuild the volume from the same source slices."""
+    from boa_b200.geometry import needs_triple_split, triple_split_ranges
+    for z in (201, 300, 512, 800, 1201):
+        vol = np.arange(z)
+        third, margin = z // 3, 20
+        p1, p2, p3 = vol[:third + margin], vol[third + 1 - margin:third * 2 + margin], vol[third * 2 + 1 - margin:]
+        ref = np.zeros(z, dtype=vol.dtype)
+        ref[:third] = p1[:-margin]
+        ref[third:third * 2] = p2[margin - 1:-margin]
+        ref[third * 2:] = p3[margin - 1:]
+        got = np.zeros(z, dtype=vol.dtype)
+        parts = triple_split_ranges(z)
+        for (plo, phi, klo, khi, dlo, dhi), p in zip(parts, (p1, p2, p3)):
+            assert np.array_equal(vol[plo:phi], p)
+            got[dlo:dhi] = vol[plo:phi][klo:khi]
+        assert np.array_equal(got, ref) and np.array_equal(got, vol)
+    with pytest.raises(ValueError):
+        triple_split_ranges(30)
+    assert not needs_triple_split((512, 512, 512), True)            # config 3: 1.3e8 voxels < 512*512*900
+    assert needs_triple_split((800, 1024, 1024), True)              # config 5
+    assert not needs_triple_split((800, 1024, 1024), False)         # single-model tasks only split when forced
+    assert not needs_triple_split((150, 2048, 2048), True)          # z <= 200
+    assert needs_triple_split((154, 512, 512), False, force_split=True)
