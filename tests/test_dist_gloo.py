@@ -1,4 +1,4 @@
-"""CPU, world_size 2 and 3 over gloo: the patch sharding plan and the slab exchange reproduce the single-process
+"""CPU, world_size 2, 3, 4 and 8 over gloo: the patch sharding plan and the slab exchange reproduce the single-process
 Gaussian-weighted accumulation (the arithmetic of the exchange; on GPUs the same code runs over NCCL)."""
 import os
 import socket
@@ -48,7 +48,9 @@ def _worker(rank, world, port, shape, patch, step, C, out_dir):
 
 @pytest.mark.parametrize("world,shape,patch,step", [(2, (40, 24, 20), (16, 16, 16), 0.5),
                                                     (3, (37, 16, 33), (16, 16, 16), 0.8),
-                                                    (4, (16, 16, 40), (16, 16, 16), 0.5)])
+                                                    (4, (16, 16, 40), (16, 16, 16), 0.5),
+                                                    (8, (70, 20, 36), (16, 16, 16), 0.5),   # 64 patches on 8 ranks
+                                                    (8, (16, 16, 24), (16, 16, 16), 0.5)])  # 2 patches: 6 idle ranks
 def test_slab_exchange_matches_single_process(tmp_path, world, shape, patch, step):
     from boa_b200.geometry import compute_gaussian, shard_patches, sliding_window_origins
     C = 3
