@@ -47,6 +47,8 @@ _SIGS = {
     "boa_net_macs_per_patch": (C.c_int64, [_P]),
     "boa_net_enable_timing": (C.c_int, [_P, C.c_int]),
     "boa_net_read_timing": (C.c_int, [_P, C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_int64), C.c_int]),
+    "boa_net_read_timing_kinds": (C.c_int, [_P, C.c_int, C.POINTER(C.c_double), C.POINTER(C.c_double),
+                                            C.POINTER(C.c_int64), C.c_int]),
     "boa_net_describe": (C.c_int, [_P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_double), C.c_char_p, C.c_int]),
     "boa_net_time_layers": (C.c_int, [_P, C.c_int, C.POINTER(C.c_float), _P]),
     "boa_net_destroy": (None, [_P]),

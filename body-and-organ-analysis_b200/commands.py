@@ -28,6 +28,23 @@ def range_warning(ct: np.ndarray) -> None:
         logger.warning("The CT has HU values outside of the usual range [-1024, 3071]: [%s, %s]", lo, hi)
 
 
+def to_int16_hu(data: np.ndarray) -> np.ndarray:
+    """The device pipeline keeps the CT as int16 HU (integer HU make every statistic exact).  Float data are truncated
+    like the reference's `.astype(np.int32)` after resampling (totalsegmentator/resampling.py:54); values outside the
+    int16 range would wrap silently, so they are clipped with a warning instead."""
+    if data.dtype == np.int16:
+        return np.ascontiguousarray(data)
+    if data.dtype.kind == "f":
+        if not np.isfinite(data).all():
+            raise ValueError("the CT contains NaN / inf values")
+        data = np.trunc(data)
+    lo, hi = float(data.min()), float(data.max())
+    if lo < -32768 or hi > 32767:
+        logger.warning("HU values outside the int16 range [%s, %s] are clipped to [-32768, 32767]", lo, hi)
+        data = np.clip(data, -32768, 32767)
+    return np.ascontiguousarray(data.astype(np.int16))
+
+
 def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_folder: Path | None = None,
                models=("total", "bca"), fast_bca: bool = False, fast_total: bool = False,
                bca_median_filtering: bool = False, cnr_adjustment: bool = True,
@@ -48,15 +65,32 @@ def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_f
     out_dir.mkdir(parents=True, exist_ok=True)
     img = nifti.load(input_folder)
     data, zooms, order = nifti.to_canonical(img.data, img.affine)
-    ct_np = np.ascontiguousarray(np.trunc(data).astype(np.int16)) if data.dtype.kind == "f" else data.astype(np.int16)
-    range_warning(ct_np)
+    range_warning(data)  # on the data as loaded, before the conversion below (compute/inference.py:21-30,46)
+    ct_np = to_int16_hu(data)
     stats = {"num_voxels": int(ct_np.size), "num_slices": int(ct_np.shape[0])}
     zoo = zoo or ModelZoo(weights_root, device=dev)
     t0 = time.time()
     ct = torch.from_numpy(ct_np).pin_memory().to(dev, non_blocking=True)
+    # recompute=False: label maps that already exist in the output folder are loaded instead of computed, and an
+    # existing total-measurements.json is kept (compute/inference.py:82-84,95-105; infer/infer.py:59-61)
+    precomputed, keep_total_json = {}, False
+    if not recompute:
+        for name in ("total", "body_parts", "body_regions"):
+            f = out_dir / f"{name}.nii.gz"
+            if f.is_file():
+                logger.info("Loading already computed %s...", name)
+                prev = nifti.load(f)
+                arr, _, _ = nifti.to_canonical(prev.data, prev.affine)
+                if arr.shape != ct_np.shape:
+                    raise ValueError(f"{f} has shape {arr.shape}, the CT {ct_np.shape}: use --force-recompute")
+                precomputed[name] = torch.from_numpy(np.ascontiguousarray(arr.astype(np.uint8)))
+        keep_total_json = (out_dir / "total-measurements.json").is_file() and (out_dir / "ct_pfav.nii.gz").is_file()
+        if keep_total_json:
+            logger.info("The total measurements were already computed, skipping...")
     res = analyze_volume(ct, (zooms[2], zooms[1], zooms[0]), zoo, models=tuple(models), fast_bca=fast_bca,
                          fast_total=fast_total, cnr_adjustment=cnr_adjustment,
-                         median_filtering=bca_median_filtering)
+                         median_filtering=bca_median_filtering, precomputed=precomputed,
+                         total_measurements=not keep_total_json)
     stats["inference_time"] = time.time() - t0
 
     def write(name, tensor, labels=None):
@@ -64,13 +98,15 @@ def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_f
         nifti.save(out_dir / f"{name}.nii.gz", arr, img.affine, labels)
 
     if res.total is not None:
-        write("total", res.total, class_map("total"))
-        write("ct_pfav", res.ct_pfav)
-        with (out_dir / "total-measurements.json").open("w") as f:
-            json.dump(res.total_measurements, f, indent=2)
-    if res.body_parts is not None:
+        if "total" not in precomputed:
+            write("total", res.total, class_map("total"))
+        if res.total_measurements is not None:
+            write("ct_pfav", res.ct_pfav)
+            with (out_dir / "total-measurements.json").open("w") as f:
+                json.dump(res.total_measurements, f, indent=2)
+    if res.body_parts is not None and "body_parts" not in precomputed:
         write("body_parts", res.body_parts, class_map("body_parts"))
-    if res.body_regions is not None:
+    if res.body_regions is not None and "body_regions" not in precomputed:
         write("body_regions", res.body_regions, class_map("body_regions"))
     if res.tissues is not None:
         write("tissues", res.tissues)

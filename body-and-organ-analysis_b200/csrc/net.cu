@@ -106,6 +106,7 @@ struct boa_net {
   std::vector<cudaEvent_t> ev;
   size_t ev_used = 0;
   std::vector<std::pair<size_t, size_t>> conv_spans;  // event index pairs around conv kernels
+  std::vector<std::pair<int, double>> conv_span_info;  // (StepKind, algorithmic FLOP of that launch) per span
   std::vector<std::pair<size_t, size_t>> fwd_spans;
   double ms_convs = 0, ms_total = 0;
   int64_t n_conv_launches = 0;
@@ -210,6 +211,7 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
     if (time_it) {
       cudaEventRecord(next_event(net, &e1), s);
       net->conv_spans.push_back({e0, e1});
+      net->conv_span_info.push_back({(int)st.kind, 2.0 * st.macs * B});
     }
     return r;
   }
@@ -223,6 +225,8 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
   if (time_it) {
     cudaEventRecord(next_event(net, &e1), s);
     net->conv_spans.push_back({e0, e1});
+    net->conv_span_info.push_back({(net->mode == 0 || st.kind == STEP_CONV_FIRST) ? (int)st.kind : (int)STEP_CONV_SIMT,
+                                   2.0 * st.macs * B});
   }
   if (r) return r;
   if (net->debug_only == 1) return BOA_OK;  // convolutions only
@@ -256,11 +260,21 @@ int run_heads(boa_net* net, Lane& L, int nb, float* d_logits, cudaStream_t s) {
   const bool fh = L.head_scale && net->mode == 0;
   const size_t pv = (size_t)a.patch[0] * a.patch[1] * a.patch[2];
   if (net->debug_only == 1) return BOA_OK;
-  for (int b = 0; b < nb; ++b)
+  const bool time_it = net->timing && !d_logits;
+  for (int b = 0; b < nb; ++b) {
+    size_t e0 = 0, e1 = 0;
+    if (time_it) cudaEventRecord(next_event(net, &e0), s);
     if (int r = launch_head(fh ? L.head_src_raw : L.head_src, b, net->d_head_w, net->d_head_b, a.features[0],
                             a.num_classes, d_logits ? d_logits + (size_t)b * a.num_classes * pv : nullptr, L.d_call,
                             fh ? L.head_scale : nullptr, fh ? L.head_shift : nullptr, a.leaky_slope, s))
       return r;
+    if (time_it) {  // kind 6: the second field carries the launch's algorithmic BYTES (activations read, fp32
+                    // read-modify-write of the C logit planes, Gaussian map)
+      cudaEventRecord(next_event(net, &e1), s);
+      net->conv_spans.push_back({e0, e1});
+      net->conv_span_info.push_back({6, (double)pv * (2.0 * a.features[0] + 8.0 * a.num_classes + 4.0)});
+    }
+  }
   return BOA_OK;
 }
 
@@ -754,10 +768,14 @@ extern "C" int boa_net_read_timing(boa_net* net, double* ms_convs, double* ms_to
   BOA_CUDA(cudaSetDevice(net->device));
   BOA_CUDA(cudaDeviceSynchronize());
   double mc = 0, mt = 0;
-  for (auto& sp : net->conv_spans) {
+  int64_t n_convs = 0;
+  for (size_t i = 0; i < net->conv_spans.size(); ++i) {
+    if (i < net->conv_span_info.size() && net->conv_span_info[i].first >= 6) continue;  // head launches
+    const auto& sp = net->conv_spans[i];
     float ms = 0;
     cudaEventElapsedTime(&ms, net->ev[sp.first], net->ev[sp.second]);
     mc += ms;
+    ++n_convs;
   }
   for (auto& sp : net->fwd_spans) {
     float ms = 0;
@@ -766,9 +784,38 @@ extern "C" int boa_net_read_timing(boa_net* net, double* ms_convs, double* ms_to
   }
   if (ms_convs) *ms_convs = mc;
   if (ms_total) *ms_total = mt;
-  if (n_conv_launches) *n_conv_launches = (int64_t)net->conv_spans.size();
+  if (n_conv_launches) *n_conv_launches = n_convs;
   if (reset) {
     net->conv_spans.clear();
+    net->conv_span_info.clear();
+    net->fwd_spans.clear();
+    net->ev_used = 0;
+  }
+  return BOA_OK;
+}
+
+// Per kernel kind (StepKind order: fold, stride-2 taps, conv SIMT, transposed taps, transposed SIMT, first-layer SIMT):
+// milliseconds, algorithmic FLOP and launches of the conv kernels recorded since the last reset while timing was
+// enabled - i.e. measured INSIDE real forward_accumulate calls (single-lane schedule, so the event brackets are
+// exclusive), under the clocks of a long step.
+extern "C" int boa_net_read_timing_kinds(boa_net* net, int n_kinds, double* ms, double* flop, int64_t* launches,
+                                         int reset) {
+  BOA_REQUIRE(net && ms && flop && launches && n_kinds > 0, "boa_net_read_timing_kinds: bad argument");
+  BOA_CUDA(cudaSetDevice(net->device));
+  BOA_CUDA(cudaDeviceSynchronize());
+  for (int k = 0; k < n_kinds; ++k) { ms[k] = 0; flop[k] = 0; launches[k] = 0; }
+  for (size_t i = 0; i < net->conv_spans.size() && i < net->conv_span_info.size(); ++i) {
+    const int k = net->conv_span_info[i].first;
+    if (k < 0 || k >= n_kinds) continue;
+    float t = 0;
+    cudaEventElapsedTime(&t, net->ev[net->conv_spans[i].first], net->ev[net->conv_spans[i].second]);
+    ms[k] += t;
+    flop[k] += net->conv_span_info[i].second;
+    ++launches[k];
+  }
+  if (reset) {
+    net->conv_spans.clear();
+    net->conv_span_info.clear();
     net->fwd_spans.clear();
     net->ev_used = 0;
   }
@@ -796,6 +843,7 @@ extern "C" int boa_net_time_layers(boa_net* net, int cap, float* ms, void* strea
   const bool was = net->timing;
   BOA_CUDA(cudaDeviceSynchronize());
   net->conv_spans.clear();
+  net->conv_span_info.clear();
   net->fwd_spans.clear();
   net->ev_used = 0;
   net->timing = true;
@@ -807,6 +855,7 @@ extern "C" int boa_net_time_layers(boa_net* net, int cap, float* ms, void* strea
   for (size_t i = 0; i < net->conv_spans.size() && (int)i < cap; ++i)
     cudaEventElapsedTime(&ms[i], net->ev[net->conv_spans[i].first], net->ev[net->conv_spans[i].second]);
   net->conv_spans.clear();
+  net->conv_span_info.clear();
   net->ev_used = 0;
   return BOA_OK;
 }

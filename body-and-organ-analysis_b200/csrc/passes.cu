@@ -137,15 +137,87 @@ __device__ __forceinline__ void argmax_group(const float* __restrict__ acc, cons
   }
 }
 
+// Fast path.  Dividing every channel by the weight sum costs ~20 instructions per (voxel, channel) and made the pass
+// instruction bound at half of the HBM rate.  Division by one positive w is monotone, so the argmax of x / w is the
+// argmax of x unless two channels are so close that their quotients may round to the same float (then numpy's "first
+// maximum wins" looks at the quotients).  The loop therefore tracks max / second max / max |x| / NaN of the raw sums
+// with the channel loads issued UNR at a time, and only a voxel group that is suspicious - near tie, tiny maximum
+// (quotients may underflow to a tie), non-finite input, w == 0 or an overflowing quotient - is redone by the exact
+// per-channel division of argmax_group<> (bit-identical result in every case, tests/test_gpu_passes.py).
+template <int UNR>
 __global__ void __launch_bounds__(256)
 finalize_argmax_kernel(const float* __restrict__ acc, const float* __restrict__ wacc, int C, size_t V, Lut256 lut,
                        int overwrite_nz, uint8_t* __restrict__ label, int* __restrict__ nonfinite) {
   int bad = 0;
   const size_t nvec = V / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
-  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride)
-    argmax_group<4>(acc, wacc, C, V, i * 4, lut, overwrite_nz, label, bad);
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nvec; i += stride) {
+    const size_t v0 = i * 4;
+    const float4 w4 = __ldcs(reinterpret_cast<const float4*>(wacc + v0));
+    const float w[4] = {w4.x, w4.y, w4.z, w4.w};
+    float m1[4], m2[4], mabs[4];
+    int arg[4];
+    bool odd = false;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { m1[k] = -INFINITY; m2[k] = -INFINITY; mabs[k] = 0.f; arg[k] = 0; }
+    for (int c0 = 0; c0 < C; c0 += UNR) {
+      float4 x4[UNR];
+#pragma unroll
+      for (int u = 0; u < UNR; ++u)
+        if (c0 + u < C) x4[u] = __ldcs(reinterpret_cast<const float4*>(acc + (size_t)(c0 + u) * V + v0));
+#pragma unroll
+      for (int u = 0; u < UNR; ++u) {
+        if (c0 + u < C) {
+          const float x[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            odd |= !(fabsf(x[k]) <= 3.0e38f);  // NaN / inf (and the few finite values above: handled exactly below)
+            mabs[k] = fmaxf(mabs[k], fabsf(x[k]));
+            m2[k] = fmaxf(m2[k], fminf(m1[k], x[k]));
+            if (x[k] > m1[k]) arg[k] = c0 + u;
+            m1[k] = fmaxf(m1[k], x[k]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const float qa = mabs[k] / w[k];
+      odd |= !(qa <= 3.0e38f);                                           // w == 0, NaN weight, overflowing quotient
+      odd |= !(w[k] > 0.f);
+      odd |= (C > 1) && !(m1[k] - m2[k] > 4.8e-7f * fabsf(m1[k]));       // near tie (2^-21 relative)
+      odd |= fabsf(m1[k]) < 1e-30f;                                      // quotients may underflow into a tie
+    }
+    if (odd) {
+      argmax_group<4>(acc, wacc, C, V, v0, lut, overwrite_nz, label, bad);
+      continue;
+    }
+    uint8_t out[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) out[k] = lut.v[arg[k]];
+    if (overwrite_nz) {
+      const uchar4 old = *reinterpret_cast<const uchar4*>(label + v0);
+      const uint8_t o[4] = {old.x, old.y, old.z, old.w};
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (out[k] == 0) out[k] = o[k];
+    }
+    *reinterpret_cast<uchar4*>(label + v0) = make_uchar4(out[0], out[1], out[2], out[3]);
+  }
   for (size_t v = nvec * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride)
+    argmax_group<1>(acc, wacc, C, V, v, lut, overwrite_nz, label, bad);
+  bad = __reduce_add_sync(0xffffffffu, bad);
+  if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nonfinite, bad);
+}
+
+// Scalar variant for channel planes that are not 16-byte aligned (V % 4 != 0: odd-sized volumes, or slabs of a sharded
+// volume): same exact arithmetic, one voxel per thread (coalesced 4-byte accesses).
+__global__ void __launch_bounds__(256)
+finalize_argmax_scalar_kernel(const float* __restrict__ acc, const float* __restrict__ wacc, int C, size_t V, Lut256 lut,
+                              int overwrite_nz, uint8_t* __restrict__ label, int* __restrict__ nonfinite) {
+  int bad = 0;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride)
     argmax_group<1>(acc, wacc, C, V, v, lut, overwrite_nz, label, bad);
   bad = __reduce_add_sync(0xffffffffu, bad);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nonfinite, bad);
@@ -454,18 +526,20 @@ extern "C" int boa_finalize_argmax(const float* d_logits_acc, const float* d_wei
                                    int32_t* d_nonfinite, void* stream) {
   BOA_REQUIRE(d_logits_acc && d_weight_acc && h_lut && d_label_inout && d_nonfinite, "boa_finalize_argmax: null");
   BOA_REQUIRE(C > 0 && C <= 256, "boa_finalize_argmax: C=%d out of range", C);
-  BOA_REQUIRE(aligned16(d_logits_acc) && aligned16(d_weight_acc) && (reinterpret_cast<uintptr_t>(d_label_inout) & 3) == 0,
-              "boa_finalize_argmax: misaligned pointer");
   if (V == 0) return BOA_OK;
   Lut256 lut;
   for (int c = 0; c < 256; ++c) lut.v[c] = c < C ? h_lut[c] : 0;
-  // float4 channel loads need V % 4 == 0 for every channel plane to stay 16-byte aligned
-  if (V % 4 != 0) {
-    set_error("boa_finalize_argmax: V (%zu) must be a multiple of 4", V);
-    return BOA_ERR_ARG;
-  }
-  finalize_argmax_kernel<<<grid_for(V / 4, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
-      d_logits_acc, d_weight_acc, C, V, lut, overwrite_nonzero_only, d_label_inout, d_nonfinite);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  // float4 channel loads need every channel plane 16-byte aligned (V % 4 == 0) and the label map 4-byte aligned;
+  // anything else (odd-sized volumes, slabs of a sharded volume) takes the scalar kernel
+  const bool vec = V % 4 == 0 && aligned16(d_logits_acc) && aligned16(d_weight_acc) &&
+                   (reinterpret_cast<uintptr_t>(d_label_inout) & 3) == 0;
+  if (vec)
+    finalize_argmax_kernel<8><<<grid_for(V / 4, 256, 8), 256, 0, s>>>(d_logits_acc, d_weight_acc, C, V, lut,
+                                                                      overwrite_nonzero_only, d_label_inout, d_nonfinite);
+  else
+    finalize_argmax_scalar_kernel<<<grid_for(V, 256, 8), 256, 0, s>>>(d_logits_acc, d_weight_acc, C, V, lut,
+                                                                      overwrite_nonzero_only, d_label_inout, d_nonfinite);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }

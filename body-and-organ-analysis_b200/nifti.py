@@ -62,10 +62,15 @@ def load(path) -> NiftiImage:
     dt = np.dtype(_DTYPES[datatype]).newbyteorder(e)
     n = nx * ny * nz  # only the first volume of a 4-D file (nnunet.py:405-407)
     data = np.frombuffer(raw, dtype=dt, count=n, offset=vox_offset).reshape(nz, ny, nx)
-    if slope not in (0.0, 1.0) or inter != 0.0:
-        if not np.isnan(slope) and slope != 0.0:
-            data = data.astype(np.float64) * slope + inter
     data = np.ascontiguousarray(data.astype(dt.newbyteorder("="), copy=False))
+    # scl_slope / scl_inter as nibabel applies them (nifti1.py get_slope_inter + get_fdata): a zero or non-finite slope
+    # means "no scaling"; a valid slope with a non-finite intercept is an error; scaled data are float64 (a uint16 file
+    # with inter = -1024 must not wrap, a fractional slope must not be truncated back to the stored dtype)
+    if np.isfinite(slope) and slope != 0.0:
+        if not np.isfinite(inter):
+            raise ValueError(f"{path}: valid scl_slope ({slope}) but invalid scl_inter ({inter})")
+        if (slope, inter) != (1.0, 0.0):
+            data = data.astype(np.float64) * np.float64(slope) + np.float64(inter)
     if sform_code > 0:
         aff = np.eye(4)
         aff[0] = struct.unpack(e + "4f", raw[280:296])

@@ -18,6 +18,7 @@ from dataclasses import dataclass, field
 
 import numpy as np
 import torch
+from torch.cuda import nvtx  # NVTX ranges around the stages (visible in nsys / ncu --nvtx)
 
 from . import bca, passes
 from .dist import DistContext, exchange_slabs, gather_label_slabs, plan_shards
@@ -101,7 +102,7 @@ def predict_labels_sharded(pred: nnUNetPredictor, data: torch.Tensor, lut=None, 
             pred.accumulate(vol[plan.zlo:plan.zhi], local, acc)
         slab = exchange_slabs(acc, plan, dist_ctx)
         del acc
-        w = weight_sum(vol.shape, pred.patch_size, origins, pred.gaussian())
+        w = weight_sum(vol.shape, pred.patch_size, origins, pred.gaussian(), pred.gaussian_kind)
         lo, hi = plan.slabs[dist_ctx.rank]
         lab_slab = finalize_argmax(slab, w[lo:hi], lut) if hi > lo else torch.zeros(
             (0, *vol.shape[1:]), dtype=torch.uint8, device=pred.device)
@@ -115,10 +116,35 @@ def predict_labels_sharded(pred: nnUNetPredictor, data: torch.Tensor, lut=None, 
         return label_inout
 
 
-def _preprocess(ct: torch.Tensor, spec) -> tuple[torch.Tensor, list]:
+def check_plan_geometry(spec, cropped_shape, spacing_zyx) -> None:
+    """DefaultPreprocessor.run_case_npy also applies plans.transpose_forward and resamples the cropped, normalised
+    volume to the configuration's spacing (default_preprocessor.py:57-90), and export_prediction resamples the logits
+    back before the argmax (export_prediction.py:25-34).  Both are identities on this path when the caller hands in a
+    volume whose grid is the plan's (`total`: TotalSegmentator resamples to 1.5 mm first).  Anything else would
+    silently run the network at the wrong scale, so it raises instead."""
+    if list(spec.transpose_forward) != [0, 1, 2] or list(spec.transpose_backward) != [0, 1, 2]:
+        raise NotImplementedError(
+            f"plans.json asks for transpose_forward={list(spec.transpose_forward)} / transpose_backward="
+            f"{list(spec.transpose_backward)}: only the identity is implemented (every BOA model is trained with it)")
+    if spacing_zyx is None:
+        return
+    target = list(spec.spacing)
+    if len(target) < 3:  # 2d configurations keep the slice spacing (default_preprocessor.py:72-75)
+        target = [spacing_zyx[0]] + target
+    # compute_new_shape (default_resampling.py:25-31); the reference resamples iff the shape changes (:139)
+    new_shape = [int(round(float(i) / float(j) * int(k))) for i, j, k in zip(spacing_zyx, target, cropped_shape)]
+    if new_shape != [int(v) for v in cropped_shape]:
+        raise NotImplementedError(
+            f"input grid {tuple(int(v) for v in cropped_shape)} @ {tuple(float(v) for v in spacing_zyx)} mm is not the "
+            f"plan's grid ({tuple(new_shape)} @ {tuple(target)} mm): nnU-Net's internal resampling to the "
+            "configuration spacing (and of the logits back) is not implemented")
+
+
+def _preprocess(ct: torch.Tensor, spec, spacing_zyx=None) -> tuple[torch.Tensor, list]:
     """crop_to_nonzero -> CTNormalization (fp32).  Returns the [1, z, y, x] network input and the crop box."""
     box = nonzero_bbox(ct)
     crop = ct[box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]].contiguous()
+    check_plan_geometry(spec, crop.shape, spacing_zyx)
     p = spec.intensity
     norm = passes.ct_normalize(crop, float(p["percentile_00_5"]), float(p["percentile_99_5"]), float(p["mean"]),
                                float(p["std"]))
@@ -126,7 +152,7 @@ def _preprocess(ct: torch.Tensor, spec) -> tuple[torch.Tensor, list]:
 
 
 def segment_task(ct: torch.Tensor, zoo: ModelZoo, task_ids, folds, step_size: float, luts=None,
-                 dist_ctx: DistContext | None = None, force_split: bool = False) -> torch.Tensor:
+                 dist_ctx: DistContext | None = None, force_split: bool = False, spacing_zyx=None) -> torch.Tensor:
     """One nnUNet_predict_image call on a volume that is already at the task's spacing: uint8 label map [z,y,x].
     Very large volumes (or force_split) are predicted as three overlapping z-parts and stitched, exactly where the
     reference does it (totalsegmentator/nnunet.py:483-505,582-586) - each part is preprocessed on its own."""
@@ -134,18 +160,20 @@ def segment_task(ct: torch.Tensor, zoo: ModelZoo, task_ids, folds, step_size: fl
     if needs_triple_split(ct.shape, len(task_ids) > 1, force_split):
         out = torch.zeros(ct.shape, dtype=torch.uint8, device=ct.device)
         for plo, phi, klo, khi, dlo, dhi in triple_split_ranges(int(ct.shape[0])):
-            part = _segment_task_whole(ct[plo:phi].contiguous(), zoo, task_ids, folds, step_size, luts, dist_ctx)
+            part = _segment_task_whole(ct[plo:phi].contiguous(), zoo, task_ids, folds, step_size, luts, dist_ctx,
+                                       spacing_zyx)
             out[dlo:dhi] = part[klo:khi]
         return out
-    return _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx)
+    return _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spacing_zyx)
 
 
-def _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx) -> torch.Tensor:
+def _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spacing_zyx=None) -> torch.Tensor:
     out = torch.zeros(ct.shape, dtype=torch.uint8, device=ct.device)
     multi = len(task_ids) > 1
     for i, tid in enumerate(task_ids):
         pred = zoo.get(tid, folds, step_size)
-        data, box = _preprocess(ct, pred.spec)
+        nvtx.range_push(f"boa/network/{tid}")
+        data, box = _preprocess(ct, pred.spec, spacing_zyx)
         sl = tuple(slice(b, e) for b, e in box)
         full = all(b == 0 and e == s for (b, e), s in zip(box, ct.shape))
         lut = luts[i] if luts is not None else None
@@ -159,30 +187,32 @@ def _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx) -> 
                 view[nz] = lab[nz]
             else:
                 out[sl] = lab
+        nvtx.range_pop()
     return out
 
 
-def segment_total(ct: torch.Tensor, zoo: ModelZoo, dist_ctx: DistContext | None = None) -> torch.Tensor:
+def segment_total(ct: torch.Tensor, zoo: ModelZoo, dist_ctx: DistContext | None = None, spacing_zyx=None) -> torch.Tensor:
     """task `total`, 1.5 mm: 5 part models, fold 0, step 0.8, merged through the part -> global LUTs
     (totalsegmentator/python_api.py:182-189, nnunet.py:507-559)."""
-    return segment_task(ct, zoo, TOTAL_TASK_IDS, [0], 0.8, part_luts(), dist_ctx)
+    return segment_task(ct, zoo, TOTAL_TASK_IDS, [0], 0.8, part_luts(), dist_ctx, spacing_zyx=spacing_zyx)
 
 
-def segment_total_fast(ct_3mm: torch.Tensor, zoo: ModelZoo, dist_ctx: DistContext | None = None) -> torch.Tensor:
+def segment_total_fast(ct_3mm: torch.Tensor, zoo: ModelZoo, dist_ctx: DistContext | None = None,
+                       spacing_zyx=None) -> torch.Tensor:
     """task `total` with --fast-total: the single 3 mm model 297, fold 0, step 0.5 (the 0.8 step applies only below
     3 mm, totalsegmentator/nnunet.py:507-514); its labels are the global class ids already."""
-    return segment_task(ct_3mm, zoo, [TOTAL_FAST_TASK_ID], [0], 0.5, None, dist_ctx)
+    return segment_task(ct_3mm, zoo, [TOTAL_FAST_TASK_ID], [0], 0.5, None, dist_ctx, spacing_zyx=spacing_zyx)
 
 
 FORCE_SPLIT_THRESHOLD = 400  # slices at 5 mm (commands.py:155-170 -> compute/inference.py:109-128)
 
 
 def segment_bca_net(ct_5mm: torch.Tensor, zoo: ModelZoo, task: str, fast: bool,
-                    dist_ctx: DistContext | None = None) -> torch.Tensor:
+                    dist_ctx: DistContext | None = None, spacing_zyx=None) -> torch.Tensor:
     tid = BODY_PARTS_TASK_ID if task == "body_parts" else BODY_REGIONS_TASK_ID
     folds = [0] if fast else [0, 1, 2, 3, 4]  # body_composition_analysis/tasks.py:15-48
     return segment_task(ct_5mm, zoo, [tid], folds, 0.5, None, dist_ctx,
-                        force_split=int(ct_5mm.shape[0]) > FORCE_SPLIT_THRESHOLD)
+                        force_split=int(ct_5mm.shape[0]) > FORCE_SPLIT_THRESHOLD, spacing_zyx=spacing_zyx)
 
 
 @dataclass
@@ -272,11 +302,16 @@ class HostStager:
 def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total", "bca"), fast_bca: bool = False,
                    cnr_adjustment: bool = False, dist_ctx: DistContext | None = None,
                    stager: HostStager | None = None, fast_total: bool = False,
-                   postprocess: bool = True, median_filtering: bool = False) -> VolumeResult:
+                   postprocess: bool = True, median_filtering: bool = False, precomputed: dict | None = None,
+                   total_measurements: bool = True) -> VolumeResult:
     """compute_all_models + run_pipeline numerics for one CT already on the device (int16 [z,y,x]).
 
     spacing_zyx: voxel spacing of the array axes.  `total` expects 1.5 mm (resampling is identity there,
-    totalsegmentator/resampling.py:179-181); the BCA nets run at 5 mm slice thickness (resample_only_thickness)."""
+    totalsegmentator/resampling.py:179-181); the BCA nets run at 5 mm slice thickness (resample_only_thickness).
+    precomputed: label maps on the input grid (uint8 [z,y,x], keys total / body_parts / body_regions) that are reused
+    instead of running their networks, total_measurements=False keeps an existing total-measurements.json - the
+    reference's `recompute=False` (compute/inference.py:82-84,95-105; infer/infer.py:59-61)."""
+    precomputed = precomputed or {}
     from .resample import resample_labels_nearest, resample_thickness, resample_volume_cubic, upsample_labels_nearest
 
     res = VolumeResult()
@@ -297,20 +332,28 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         # `total` runs at 1.5 mm: other inputs are resampled (order 3) and the label map goes back to the input grid
         # (order 0), totalsegmentator/nnunet.py:466-470,685-687
         net_spacing = 3.0 if fast_total else 1.5  # python_api.py:169-189
-        ct_net = resample_volume_cubic(ct, spacing_zyx, net_spacing)
-        if ct_net is not ct:
-            mark("resample_total")
-        seg = segment_total_fast(ct_net, zoo, dist_ctx) if fast_total else segment_total(ct_net, zoo, dist_ctx)
-        res.total = resample_labels_nearest(seg, ct.shape)
-        del ct_net, seg
+        if "total" in precomputed:
+            res.total = precomputed["total"].to(ct.device, torch.uint8).contiguous()
+        else:
+            ct_net = resample_volume_cubic(ct, spacing_zyx, net_spacing)
+            if ct_net is not ct:
+                mark("resample_total")
+            sp_net = (net_spacing,) * 3
+            seg = (segment_total_fast(ct_net, zoo, dist_ctx, sp_net) if fast_total
+                   else segment_total(ct_net, zoo, dist_ctx, sp_net))
+            res.total = resample_labels_nearest(seg, ct.shape)
+            del ct_net, seg
         mark("total_nets")
         if stager is not None:
             stager.stage("total", res.total)
         sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
 
-        def total_measurements():
-            res.total_measurements, res.ct_pfav = compute_measurements_on_device(
-                ct, {"total": res.total}, sx_sy_sz, cnr_adjustment, return_ct_pfav_mask=True)
+        def measure_total():
+            if not total_measurements:
+                return
+            with nvtx.range("boa/total_measurements"):
+                res.total_measurements, res.ct_pfav = compute_measurements_on_device(
+                    ct, {"total": res.total}, sx_sy_sz, cnr_adjustment, return_ct_pfav_mask=True)
 
         # `total-measurements.json` needs only the CT and the `total` label map, so it CAN run on a side stream driven
         # by a helper thread while the body-composition networks follow (BOA_B200_ASYNC_MEAS=1).  Measured on B200: a
@@ -318,14 +361,16 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         # +70 ms on 1 GPU, +350 ms next to the NCCL exchange on 2), so it is off by default.
         run_async = bool(models & {"bca", "body_parts", "body_regions"}) and os.environ.get("BOA_B200_ASYNC_MEAS", "0") == "1"
         if run_async:
-            background = _Background(ct.device, total_measurements, (ct, res.total))
+            background = _Background(ct.device, measure_total, (ct, res.total))
         else:
-            total_measurements()
+            measure_total()
             mark("total_measurements")
             if stager is not None:
                 stager.stage("ct_pfav", res.ct_pfav)
     if "bca" in models or "body_parts" in models or "body_regions" in models:
         ct5 = resample_thickness(ct, spacing_zyx[0], 5.0)
+        # the spacing the 5 mm volume carries into nnU-Net (totalsegmentator/nnunet.py:457-459: only the thickness changes)
+        sp5 = (5.0 if ct5 is not ct else float(spacing_zyx[0]), float(spacing_zyx[1]), float(spacing_zyx[2]))
         mark("resample")
         want_parts = "bca" in models or "body_parts" in models
         want_regions = "bca" in models or "body_regions" in models
@@ -341,22 +386,27 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
 
         def finish(net_out, fn, name):
             mark(f"{name}_net")
-            if on_5mm:
-                net_out = fn(net_out, weights)
-            out = upsample_labels_nearest(net_out, ct.shape[0])
-            if postprocess and not on_5mm:
-                out = fn(out, None)
+            with nvtx.range(f"boa/postprocess/{name}"):
+                if on_5mm:
+                    net_out = fn(net_out, weights)
+                out = upsample_labels_nearest(net_out, ct.shape[0])
+                if postprocess and not on_5mm:
+                    out = fn(out, None)
             if postprocess:
                 mark(f"{name}_postprocess")
             return out
 
-        if want_parts:
-            res.body_parts = finish(segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx),
+        if want_parts and "body_parts" in precomputed:
+            res.body_parts = precomputed["body_parts"].to(ct.device, torch.uint8).contiguous()
+        elif want_parts:
+            res.body_parts = finish(segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx, sp5),
                                     postprocess_part_segmentation, "body_parts")
             if stager is not None:
                 stager.stage("body_parts", res.body_parts)
-        if want_regions:
-            res.body_regions = finish(segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx),
+        if want_regions and "body_regions" in precomputed:
+            res.body_regions = precomputed["body_regions"].to(ct.device, torch.uint8).contiguous()
+        elif want_regions:
+            res.body_regions = finish(segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx, sp5),
                                       postprocess_region_segmentation, "body_regions")
         if stager is not None:
             stager.stage("body_regions", res.body_regions)
@@ -367,12 +417,14 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         if stager is not None:
             stager.stage("ct_pfav", res.ct_pfav)
     if "bca" in models:
+        nvtx.range_push("boa/bca_measurements")
         res.tissues = bca.subclassify_tissues(ct, res.body_regions, median_filtering)
         if stager is not None:
             stager.stage("tissues", res.tissues)
         sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
         res.bca_measurements, res.vertebrae, _ = bca.build_bca_measurements(
             ct, res.tissues, res.body_parts, res.body_regions, res.total, sx_sy_sz)
+        nvtx.range_pop()
         mark("bca_measurements")
     torch.cuda.synchronize()
     for (n0, e0), (n1, e1) in zip(marks, marks[1:]):

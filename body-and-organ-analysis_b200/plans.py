@@ -58,6 +58,32 @@ def arch_from_plans(plans: dict, configuration: str, num_input_channels: int, nu
     }
 
 
+def macs_per_patch(arch: dict) -> int:
+    """Algorithmic multiply-accumulates of one PlainConvUNet forward over one patch (roofline accounting; equals
+    boa_net_macs_per_patch of the built network)."""
+    feats, n = arch["features"], len(arch["features"])
+    dims, shape = [], list(arch["patch_size"])
+    for s in range(n):
+        shape = [d // st for d, st in zip(shape, arch["strides"][s])]
+        dims.append(list(shape))
+    vox = lambda s: dims[s][0] * dims[s][1] * dims[s][2]
+    k3 = lambda s: arch["kernels"][s][0] * arch["kernels"][s][1] * arch["kernels"][s][2]
+    total, cin = 0, arch["in_channels"]
+    for s in range(n):
+        for _ in range(arch["n_conv_enc"][s]):
+            total += k3(s) * cin * feats[s] * vox(s)
+            cin = feats[s]
+    for j in range(n - 1):
+        below, s = n - 1 - j, n - 2 - j
+        st = arch["strides"][below]
+        total += st[0] * st[1] * st[2] * feats[below] * feats[s] * vox(below)
+        cin = 2 * feats[s]
+        for _ in range(arch["n_conv_dec"][j]):
+            total += k3(s) * cin * feats[s] * vox(s)
+            cin = feats[s]
+    return total + feats[0] * arch["num_classes"] * vox(0)
+
+
 def load_model_folder(model_training_output_dir: str, use_folds, checkpoint_name: str = "checkpoint_final.pth") -> ModelSpec:
     import torch
 

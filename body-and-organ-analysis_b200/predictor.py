@@ -104,6 +104,17 @@ class Network:
         _lib.check(L.boa_net_time_layers(self.handle, cap, ms, _lib.stream_ptr()))
         return [float(ms[i]) for i in range(len(self.describe()))]
 
+    def enable_timing(self, enable: bool) -> None:
+        """CUDA events around every conv kernel of the following forward_accumulate calls (single-lane schedule)."""
+        _lib.check(_lib.lib().boa_net_enable_timing(self.handle, int(enable)))
+
+    def read_timing_kinds(self, reset: bool = True):
+        """[(ms, flop, launches)] per kernel kind (see include/boa_b200.h boa_net_read_timing_kinds)."""
+        n = 7
+        ms, fl, la = (C.c_double * n)(), (C.c_double * n)(), (C.c_int64 * n)()
+        _lib.check(_lib.lib().boa_net_read_timing_kinds(self.handle, n, ms, fl, la, int(reset)))
+        return [(float(ms[i]), float(fl[i]), int(la[i])) for i in range(n)]
+
     def forward_accumulate(self, vol: torch.Tensor, origins: np.ndarray, gaussian: torch.Tensor, acc: torch.Tensor) -> None:
         """vol fp32 [d0,d1,d2] (device), origins int32 [n,3] (host), gaussian fp32 [p0,p1,p2], acc fp32 [C,d0,d1,d2]."""
         assert vol.is_cuda and vol.dtype == torch.float32 and vol.is_contiguous()
@@ -135,15 +146,20 @@ class Network:
 
 
 _weight_sum_cache: dict = {}
+_WEIGHT_SUM_CACHE_ENTRIES = 4
 
 
-def weight_sum(shape, patch, origins: np.ndarray, gaussian: torch.Tensor) -> torch.Tensor:
-    """`n_predictions` (predict_from_raw_data.py:614): input independent, accumulated in slicer order; cached."""
-    key = (tuple(shape), tuple(patch), origins.tobytes(), gaussian.data_ptr(), gaussian.device.index)
+def weight_sum(shape, patch, origins: np.ndarray, gaussian: torch.Tensor, kind: str = "gaussian") -> torch.Tensor:
+    """`n_predictions` (predict_from_raw_data.py:614): input independent, accumulated in slicer order; cached.
+    `kind` names the content of `gaussian` ("gaussian": compute_gaussian(patch, 1/8, 10), "ones"): every predictor owns
+    its own copy of the same map, so the key must not depend on which copy is passed."""
+    key = (tuple(int(v) for v in shape), tuple(int(v) for v in patch), origins.tobytes(), kind, gaussian.device.index)
     hit = _weight_sum_cache.get(key)
     if hit is not None:
+        _weight_sum_cache[key] = _weight_sum_cache.pop(key)  # most recently used last
         return hit
-    _weight_sum_cache.clear()
+    while len(_weight_sum_cache) >= _WEIGHT_SUM_CACHE_ENTRIES:
+        _weight_sum_cache.pop(next(iter(_weight_sum_cache)))
     w = torch.zeros(tuple(shape), dtype=torch.float32, device=gaussian.device)
     o = np.ascontiguousarray(origins, dtype=np.int32)
     _lib.check(_lib.lib().boa_accumulate_weights(o.ctypes.data_as(C.POINTER(C.c_int32)), int(o.shape[0]),
@@ -224,6 +240,10 @@ class nnUNetPredictor:
     def num_classes(self) -> int:
         return self.spec.arch["num_classes"]
 
+    @property
+    def gaussian_kind(self) -> str:
+        return "gaussian" if self.use_gaussian else "ones"
+
     def gaussian(self) -> torch.Tensor:
         if self._gaussian is None:
             if self.use_gaussian:
@@ -263,7 +283,7 @@ class nnUNetPredictor:
         with torch.cuda.device(self.device_index):
             vol, origins, unpad = self._prepare(input_image)
             acc = self.accumulate(vol, origins)
-            w = weight_sum(vol.shape, self.patch_size, origins, self.gaussian())
+            w = weight_sum(vol.shape, self.patch_size, origins, self.gaussian(), self.gaussian_kind)
             acc /= w * float(len(self.networks))
             if not torch.isfinite(acc).all():
                 raise RuntimeError("Encountered inf in predicted array. Aborting... If this problem persists, reduce "
@@ -282,7 +302,7 @@ class nnUNetPredictor:
         with torch.cuda.device(self.device_index):
             vol, origins, unpad = self._prepare(input_image)
             acc = self.accumulate(vol, origins)
-            w = weight_sum(vol.shape, self.patch_size, origins, self.gaussian())
+            w = weight_sum(vol.shape, self.patch_size, origins, self.gaussian(), self.gaussian_kind)
             padded = any(s.start != 0 or s.stop != d for s, d in zip(unpad, vol.shape))
             if padded:
                 lab = finalize_argmax(acc, w, lut)[unpad].contiguous()

@@ -175,7 +175,7 @@ def synthetic_specs(patch=(128, 128, 128), base=32, max_features=320, n_stages=6
     for did, (name, trainer, ncls) in DATASETS.items():
         if datasets is not None and did not in datasets:
             continue
-        spacing = (1.5, 1.5, 1.5) if did < 500 else (5.0, 1.5, 1.5)
+        spacing = (3.0, 3.0, 3.0) if did == 297 else ((1.5, 1.5, 1.5) if did < 500 else (5.0, 1.5, 1.5))
         plans = default_plans(patch, base, max_features, n_stages, spacing, name)
         arch = arch_from_plans(plans, "3d_fullres", 1, ncls)
         nf = 1 if did < 500 else bca_folds

@@ -104,6 +104,12 @@ int64_t boa_net_macs_per_patch(const boa_net* net);
  * timing is enabled (bench only). */
 int boa_net_enable_timing(boa_net* net, int enable);
 int boa_net_read_timing(boa_net* net, double* ms_convs, double* ms_total, int64_t* n_conv_launches, int reset);
+/* The same record split by kernel kind (0 dz-folded tcgen05 conv, 1 stride-2 tap-list conv, 2 SIMT conv, 3 transposed
+ * tap-list conv, 4 SIMT transposed conv, 5 first-layer SIMT conv, 6 head + Gaussian accumulate - for kind 6 `flop`
+ * holds algorithmic BYTES): milliseconds, algorithmic FLOP and launches of the kernels launched by forward_accumulate
+ * calls while timing was enabled (single-lane schedule, exclusive event brackets) - the roofline of bench.py is
+ * computed from these, inside a long step.  Bench only; the reference has no counterpart. */
+int boa_net_read_timing_kinds(boa_net* net, int n_kinds, double* ms, double* flop, int64_t* launches, int reset);
 void boa_net_destroy(boa_net* net);
 
 /* ------------------------------------------------------------------------------------------------------------

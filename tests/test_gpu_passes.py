@@ -121,6 +121,32 @@ def test_finalize_argmax_ties_lut_merge_and_inf(cuda):
         finalize_argmax(_dev(bad), _dev(w))
 
 
+@pytest.mark.parametrize("shape,C", [((31, 33, 35), 25), ((13, 7, 5), 3), ((16, 24, 32), 27), ((9, 10, 11), 1)])
+def test_finalize_argmax_odd_shapes_near_ties_and_tiny_values(cuda, shape, C):
+    """V % 4 != 0 takes the scalar kernel; the vector kernel's division-free fast path must agree with numpy's
+    divide-then-argmax on near ties (quotients that round to the same float), denormal quotients and zeros."""
+    rng = np.random.default_rng(11)
+    acc = rng.standard_normal((C, *shape)).astype(np.float32) * 5
+    w = rng.uniform(5.96e-8, 80.0, size=shape).astype(np.float32)
+    if C > 2:
+        m = rng.random(shape) < 0.3                       # channel 2 one ulp above / below channel 0
+        acc[2][m] = np.nextafter(acc[0][m], np.float32(np.inf))
+        m = rng.random(shape) < 0.3
+        acc[1][m] = np.nextafter(acc[2][m], np.float32(-np.inf))
+        acc[:, 0] *= np.float32(1e-42)                    # quotients underflow into ties
+        acc[:, 1] = 0.0
+        acc[:, 2] = -np.abs(acc[:, 2])                    # all negative
+    ref = (acc / w).argmax(0).astype(np.uint8)
+    lab = finalize_argmax(_dev(acc), _dev(w)).cpu().numpy()
+    assert np.array_equal(lab, ref)
+    # a slab that starts at a misaligned element offset (what a sharded volume hands in)
+    if shape[0] > 4:
+        a = _dev(acc)[:, 1:-1].contiguous()
+        wv = _dev(w)[1:-1]                                # storage offset = Y * X elements: not 16-byte aligned when odd
+        lab2 = finalize_argmax(a, wv).cpu().numpy()
+        assert np.array_equal(lab2, ref[1:-1])
+
+
 def test_weight_sum_and_accumulate_patch(cuda):
     from boa_b200 import _lib
     from boa_b200.geometry import compute_gaussian, sliding_window_origins

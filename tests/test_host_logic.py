@@ -176,3 +176,18 @@ def test_triple_split_ranges_stitch_like_the_reference():
     assert not needs_triple_split((800, 1024, 1024), False)         # single-model tasks only split when forced
     assert not needs_triple_split((150, 2048, 2048), True)          # z <= 200
     assert needs_triple_split((154, 512, 512), False, force_split=True)
+
+
+def test_non_identity_transpose_and_foreign_spacing_raise():
+    from boa_b200.pipeline import check_plan_geometry
+    from boa_b200.plans import ModelSpec
+    spec = ModelSpec(arch={}, intensity={}, labels={}, transpose_forward=[0, 2, 1], transpose_backward=[0, 2, 1],
+                     spacing=[1.5] * 3, configuration="3d_fullres")
+    with pytest.raises(NotImplementedError, match="transpose_forward"):
+        check_plan_geometry(spec, (64, 64, 64), None)
+    spec.transpose_forward = spec.transpose_backward = [0, 1, 2]
+    check_plan_geometry(spec, (64, 64, 64), (1.5, 1.5, 1.5))
+    check_plan_geometry(spec, (64, 64, 64), None)
+    spec.spacing = [5.0, 0.8, 0.8]
+    with pytest.raises(NotImplementedError, match="plan's grid"):
+        check_plan_geometry(spec, (64, 512, 512), (5.0, 0.7, 0.7))
