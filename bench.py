@@ -442,10 +442,10 @@ def run_ours(a):
              6: "head_mma_kernel(+gaussian accumulate)"}
     per_kind = {}
     for n in nets:
-        for k, (t_ms, work, launches) in enumerate(n.read_timing_kinds(reset=True)):
-            if launches:
+        for k, (t_ms, work, n_l) in enumerate(n.read_timing_kinds(reset=True)):
+            if n_l:
                 d = per_kind.setdefault(kinds[k], {"launches": 0, "ms": 0.0, "work": 0.0})
-                d["launches"] += launches; d["ms"] += t_ms; d["work"] += work
+                d["launches"] += n_l; d["ms"] += t_ms; d["work"] += work
         n.enable_timing(False)
     for name, d in per_kind.items():
         rate = d["work"] / (d["ms"] * 1e-3) if d["ms"] > 0 else None

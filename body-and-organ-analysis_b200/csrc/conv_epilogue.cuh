@@ -22,8 +22,32 @@ __device__ __forceinline__ void stats_flush(RunningStats& r, double* __restrict_
   r.s1 = 0.0; r.s2 = 0.0; r.key = -1;
 }
 
+// Optional second destination of a conv output: the space-to-depth copy [B][8 phases][G][D/2][H/2][W/2][8] that the
+// next stage's stride-2 conv reads (phase = (z&1)*4 + (y&1)*2 + (x&1)).  `base` is this thread's voxel (x, y) of the
+// strip's first channel group at z = 0; nullptr = no copy.
+struct S2dDst {
+  uint4* base = nullptr;
+  size_t zpar_stride = 0;   // z odd: + 4 phases
+  size_t zhalf_stride = 0;  // per z >> 1
+  size_t gstride = 0;       // per channel group
+  __device__ __forceinline__ uint4* at(int z) const { return base + (size_t)(z & 1) * zpar_stride + (size_t)(z >> 1) * zhalf_stride; }
+};
+
+__device__ __forceinline__ S2dDst s2d_dst(__half* s2d, int b, int groups, int g0, int D, int H, int W, int y, int x) {
+  S2dDst d;
+  if (!s2d) return d;
+  const size_t hv = (size_t)(D >> 1) * (H >> 1) * (W >> 1);
+  const int ph_xy = (y & 1) * 2 + (x & 1);
+  d.base = reinterpret_cast<uint4*>(s2d) + ((size_t)(b * 8 + ph_xy) * groups + g0) * hv + (size_t)(y >> 1) * (W >> 1) + (x >> 1);
+  d.zpar_stride = (size_t)4 * groups * hv;
+  d.zhalf_stride = (size_t)(H >> 1) * (W >> 1);
+  d.gstride = hv;
+  return d;
+}
+
 __device__ __forceinline__ void epi_store_slot(const uint32_t (&v)[32], const float (&bs)[32], float (&s1)[32],
-                                               float (&s2)[32], uint4* __restrict__ dst, size_t gstride) {
+                                               float (&s2)[32], uint4* __restrict__ dst, size_t gstride,
+                                               uint4* __restrict__ dst2 = nullptr, size_t gstride2 = 0) {
   float f[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) {
@@ -38,6 +62,7 @@ __device__ __forceinline__ void epi_store_slot(const uint32_t (&v)[32], const fl
 #pragma unroll
     for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
     dst[j * gstride] = o;
+    if (dst2) dst2[j * gstride2] = o;
   }
 }
 
@@ -47,7 +72,8 @@ __device__ __forceinline__ void epi_store_slot(const uint32_t (&v)[32], const fl
 __device__ __forceinline__ void conv_epilogue_strip(uint32_t taddr, int slot_cols, int zt, const float* __restrict__ bias32,
                                                     bool rowvalid, int z0, int D, uint4* __restrict__ dst,
                                                     size_t zstride, size_t gstride, int lane, int key,
-                                                    RunningStats& run, double* __restrict__ stats) {
+                                                    RunningStats& run, double* __restrict__ stats,
+                                                    const S2dDst s2d = S2dDst()) {
   float bs[32], s1[32], s2[32];
 #pragma unroll
   for (int c = 0; c < 32; ++c) { bs[c] = __ldg(bias32 + c); s1[c] = 0.f; s2[c] = 0.f; }
@@ -57,11 +83,15 @@ __device__ __forceinline__ void conv_epilogue_strip(uint32_t taddr, int slot_col
   for (int slot = 0; slot < zt; slot += 2) {
     tmem_ld_wait();
     if (slot + 1 < zt) tmem_ld32(taddr + (uint32_t)((slot + 1) * slot_cols), vb);
-    if (rowvalid && z0 + slot < D) epi_store_slot(va, bs, s1, s2, dst + (size_t)slot * zstride, gstride);
+    if (rowvalid && z0 + slot < D)
+      epi_store_slot(va, bs, s1, s2, dst + (size_t)slot * zstride, gstride, s2d.base ? s2d.at(z0 + slot) : nullptr,
+                     s2d.gstride);
     if (slot + 1 < zt) {
       tmem_ld_wait();
       if (slot + 2 < zt) tmem_ld32(taddr + (uint32_t)((slot + 2) * slot_cols), va);
-      if (rowvalid && z0 + slot + 1 < D) epi_store_slot(vb, bs, s1, s2, dst + (size_t)(slot + 1) * zstride, gstride);
+      if (rowvalid && z0 + slot + 1 < D)
+        epi_store_slot(vb, bs, s1, s2, dst + (size_t)(slot + 1) * zstride, gstride,
+                       s2d.base ? s2d.at(z0 + slot + 1) : nullptr, s2d.gstride);
     }
   }
   // transpose-reduce over the 32 lanes: afterwards lane l holds the warp total of channel l of the strip
@@ -84,95 +114,6 @@ __device__ __forceinline__ void conv_epilogue_strip(uint32_t taddr, int slot_col
   }
   run.s1 += (double)s1[0];
   run.s2 += (double)s2[0];
-}
-
-// ---- 16-column strips: the same epilogue at half the register footprint, for kernels that share the register file
-// with more warps (conv3_fold_ldnorm_kernel: 13 warps).  Slower per tile (twice the TMEM round trips), which only
-// matters where the epilogue is exposed - not with double-buffered accumulators.  Two neighbouring strips share one
-// RunningStats16: after a strip's reduction lanes 2c and 2c+1 both hold the total of its channel c; even lanes keep the
-// even strip's totals, odd lanes the odd strip's.
-struct RunningStats16 {  // lane l holds the sums of channel key + 16 * (l & 1) + (l >> 1)
-  double s1 = 0.0, s2 = 0.0;
-  int key = -1;          // (b * Cout + first channel of the EVEN strip) of the run being accumulated
-};
-
-__device__ __forceinline__ void stats_flush16(RunningStats16& r, double* __restrict__ stats, int lane) {
-  if (r.key >= 0 && stats) {
-    double* st = stats + ((size_t)r.key + 16 * (lane & 1) + (lane >> 1)) * 2;
-    atomicAdd(st, r.s1);
-    atomicAdd(st + 1, r.s2);
-  }
-  r.s1 = 0.0; r.s2 = 0.0; r.key = -1;
-}
-
-__device__ __forceinline__ void epi_store_slot16(const uint32_t (&v)[16], const float (&bs)[16], float (&s1)[16],
-                                                 float (&s2)[16], uint4* __restrict__ dst, size_t gstride) {
-  float f[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) {
-    f[c] = __uint_as_float(v[c]) + bs[c];
-    s1[c] += f[c];
-    s2[c] = fmaf(f[c], f[c], s2[c]);
-  }
-#pragma unroll
-  for (int j = 0; j < 2; ++j) {
-    uint4 o;
-    __half2* h = reinterpret_cast<__half2*>(&o);
-#pragma unroll
-    for (int e = 0; e < 4; ++e) h[e] = __floats2half2_rn(f[8 * j + 2 * e], f[8 * j + 2 * e + 1]);
-    dst[j * gstride] = o;
-  }
-}
-
-// One 16-channel strip of one tile for one warp; `key` is the pair's key (first channel of the even strip), `odd` says
-// which strip of the pair this is.  Other arguments as conv_epilogue_strip.
-__device__ __forceinline__ void conv_epilogue_strip16(uint32_t taddr, int slot_cols, int zt, const float* __restrict__ bias16,
-                                                      bool rowvalid, int z0, int D, uint4* __restrict__ dst,
-                                                      size_t zstride, size_t gstride, int lane, int key, int odd,
-                                                      RunningStats16& run, double* __restrict__ stats) {
-  float bs[16], s1[16], s2[16];
-#pragma unroll
-  for (int c = 0; c < 16; ++c) { bs[c] = __ldg(bias16 + c); s1[c] = 0.f; s2[c] = 0.f; }
-  uint32_t va[16], vb[16];
-  tmem_ld16(taddr, va);
-#pragma unroll 1
-  for (int slot = 0; slot < zt; slot += 2) {
-    tmem_ld_wait();
-    if (slot + 1 < zt) tmem_ld16(taddr + (uint32_t)((slot + 1) * slot_cols), vb);
-    if (rowvalid && z0 + slot < D) epi_store_slot16(va, bs, s1, s2, dst + (size_t)slot * zstride, gstride);
-    if (slot + 1 < zt) {
-      tmem_ld_wait();
-      if (slot + 2 < zt) tmem_ld16(taddr + (uint32_t)((slot + 2) * slot_cols), va);
-      if (rowvalid && z0 + slot + 1 < D) epi_store_slot16(vb, bs, s1, s2, dst + (size_t)(slot + 1) * zstride, gstride);
-    }
-  }
-  // transpose-reduce over the 32 lanes: four halving exchanges (16 -> 1 values per lane) and a final pair add;
-  // afterwards lanes 2c and 2c+1 both hold the warp total of channel c of the strip
-#pragma unroll
-  for (int step = 0; step < 4; ++step) {
-    const int off = 16 >> step;   // lane distance of the exchange
-    const int n = 8 >> step;      // values kept
-    const bool upper = (lane & off) != 0;
-#pragma unroll
-    for (int k = 0; k < n; ++k) {
-      const float send1 = upper ? s1[k] : s1[k + n];
-      const float send2 = upper ? s2[k] : s2[k + n];
-      const float r1 = __shfl_xor_sync(0xffffffffu, send1, off);
-      const float r2 = __shfl_xor_sync(0xffffffffu, send2, off);
-      s1[k] = (upper ? s1[k + n] : s1[k]) + r1;
-      s2[k] = (upper ? s2[k + n] : s2[k]) + r2;
-    }
-  }
-  s1[0] += __shfl_xor_sync(0xffffffffu, s1[0], 1);
-  s2[0] += __shfl_xor_sync(0xffffffffu, s2[0], 1);
-  if (run.key != key) {
-    stats_flush16(run, stats, lane);
-    run.key = key;
-  }
-  if ((lane & 1) == odd) {
-    run.s1 += (double)s1[0];
-    run.s2 += (double)s2[0];
-  }
 }
 
 // ---- transposed conv (k = s = 2): GEMM column n = (((pz*2+py) * Cout/8 + cg) * 2 + px) * 8 + e.  The two x-phases

@@ -13,21 +13,24 @@
 //     filled out of bounds (= conv padding).  The (dy,dx) taps are 16-byte address offsets of the same smem tile
 //     (no-swizzle K-major descriptors; M rows = 8 x-voxels x 16 y-rows, SBO = one halo row).
 //   * B operand: weights pre-packed on the host into the exact smem image, one bulk copy per K chunk.
-//   * Persistent CTAs, warp-specialised: warp 0 TMA producer, warp 1 MMA issuer (one elected lane), warps 2-5
-//     epilogue (TMEM -> regs, +bias, InstanceNorm sum / sum^2, fp16 C8 store).  2-stage smem ring over K chunks of
-//     16 input channels; TMEM accumulators double-buffered when zt*NC <= 256.
+//   * Persistent CTAs of three warpgroups (register file re-partitioned with setmaxnreg): WG0 = TMA producer (warp 0) +
+//     MMA issuer (warp 1, one elected lane), WG1 = epilogue (TMEM -> regs, +bias, InstanceNorm sum / sum^2, fp16 C8
+//     store, optional space-to-depth copy), WG2 = operand transform: the input is the producer's RAW conv output and
+//     its InstanceNorm affine + LeakyReLU are applied to the tile in shared memory between the TMA write and the MMAs
+//     (conv_xform.cuh) - there is no standalone normalise pass.  Shared-memory ring over K chunks of 16 input
+//     channels; TMEM accumulators double-buffered when zt*NC <= 256.
 #include <stdlib.h>
 #include <vector>
 #include "net_kernels.cuh"
 #include "conv_epilogue.cuh"
+#include "conv_xform.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
 namespace boa {
 
-constexpr int MMA_THREADS = 192;        // producer warp, MMA warp, 4 epilogue warps
-constexpr int LDN_LOADER_WARPS = 8;     // fused-normalisation variant: loader warps instead of the TMA producer
-constexpr int LDN_THREADS = 32 * (1 + 4 + LDN_LOADER_WARPS);  // MMA warp, 4 epilogue warps, loaders = 416
+constexpr int MMA_THREADS = 384;  // WG0: producer warp + MMA warp (+2 idle), WG1: 4 epilogue warps, WG2: 4 transform warps
+constexpr int REGS_WG0 = 104, REGS_EPI = 248, REGS_XF = 128;  // 128 * (104 + 248 + 128) = 61440 <= 65536 registers
 constexpr int TILE_X = 8, TILE_Y = 16;
 constexpr int XB = TILE_X + 2, YB = TILE_Y + 2, SLAB = XB * YB;  // 180 halo positions per z-plane
 
@@ -39,13 +42,9 @@ struct ConvMmaParams {
   int B, kc_count, Cout, D, H, W, zt;
   int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
   int in_groups_total, in_group_off;
-  // fused input normalisation (conv3_fold_ldnorm_kernel): in_raw holds the producer's RAW conv output; loader warps
-  // apply y = lrelu(x * scale + shift) per (batch item, input channel) on the way from global to shared memory
-  const __half* in_raw;   // base of the raw C8 tensor (same view as the tensor map of the unfused kernel)
-  const float* in_scale;  // [B][in_channels] or nullptr
-  const float* in_shift;
-  int in_channels;
-  float slope;
+  int out_groups_total, out_group_off;  // the output view (a channel-group slice of a concat buffer, or dense)
+  __half* s2d;                          // optional space-to-depth copy of the output (nullptr: none)
+  InXform xf;                           // fused normalisation of the input (xf.scale == nullptr: none)
   int stages;      // shared-memory ring depth of the A operand (2..4)
   int b_resident;  // 1: the weights of ALL K chunks stay in shared memory for the whole kernel (n_ntiles == 1), the
                    //    ring carries only the activation tiles
@@ -112,19 +111,22 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
   uint8_t* const ring = smem + bres_bytes;
   const int nstage = p.stages;
   uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * stage_bytes);
-  uint64_t* full = bars;         // [4] TMA -> MMA
+  uint64_t* full = bars;         // [4] operand ready (TMA, or the transform warps when the input is normalised here) -> MMA
   uint64_t* empty = bars + 4;    // [4] MMA -> TMA
   uint64_t* tfull = bars + 8;    // [2] MMA -> epilogue
   uint64_t* tempty = bars + 10;  // [2] epilogue -> MMA
+  uint64_t* rawfull = bars + 12; // [4] TMA -> transform warps
   uint64_t* bfull = bars + 16;   // [1] resident weights landed
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 17);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nbuf = (p.zt * NC <= 256) ? 2 : 1;
+  const bool xform = p.xf.scale != nullptr;
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], xform ? 4 : 1);
       mbar_init(&empty[i], 1);
+      mbar_init(&rawfull[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -143,81 +145,85 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
   tc_fence_after();
   const uint32_t tbase = *tmem_slot;
 
-  if (warp == 0) {
-    // ===================================================================== TMA producer
-    if (p.b_resident && elect_one()) {  // n_ntiles == 1: one weight set for every tile of this CTA
-      mbar_arrive_expect_tx(bfull, bres_bytes);
-      for (int kc = 0; kc < p.kc_count; ++kc)
-        bulk_load(smem + (size_t)kc * b_bytes, reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)kc * b_bytes,
-                  b_bytes, bfull);
-    }
-    __syncwarp();
-    int st = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int nt, b, tz, ty, tx;
-      decode_tile(tile, p, nt, b, tz, ty, tx);
-      for (int kc = 0; kc < p.kc_count; ++kc) {
-        mbar_wait(&empty[st], ph ^ 1);
-        if (elect_one()) {
-          uint8_t* sa = ring + (size_t)st * stage_bytes;
-          mbar_arrive_expect_tx(&full[st], stage_bytes);
-          tma_load_c8(sa, &tmapA, &full[st], p.tmap_merged, tx * TILE_X - 1, ty * TILE_Y - 1, tz * p.zt - 1,
-                      b * p.in_groups_total + p.in_group_off + 2 * kc);
-          if (!p.b_resident)
-            bulk_load(sa + a_bytes,
-                      reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)(nt * p.kc_count + kc) * b_bytes, b_bytes,
-                      &full[st]);
-        }
-        __syncwarp();
-        if (++st == nstage) { st = 0; ph ^= 1; }
+  if (warp < 4) {
+    reg_dealloc<REGS_WG0>();
+    if (warp == 0) {
+      // ===================================================================== TMA producer
+      if (p.b_resident && elect_one()) {  // n_ntiles == 1: one weight set for every tile of this CTA
+        mbar_arrive_expect_tx(bfull, bres_bytes);
+        for (int kc = 0; kc < p.kc_count; ++kc)
+          bulk_load(smem + (size_t)kc * b_bytes, reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)kc * b_bytes,
+                    b_bytes, bfull);
       }
-    }
-  } else if (warp == 1) {
-    // ===================================================================== MMA issuer (ONE thread runs the loop)
-    if (elect_one()) {
-      uint32_t tcount = 0;
+      __syncwarp();
       int st = 0;
       uint32_t ph = 0;
-      if (p.b_resident) {
-        mbar_wait(bfull, 0);
-        tc_fence_after();
-      }
-      const uint32_t a_lbo = (uint32_t)zb * SLAB * 16u;  // next channel group (K chunk of 8)
-      // descriptors with a zero address field; tap / slab / row-block shifts are added to the low word (16-byte units;
-      // shared memory is < 256 KB so the 14-bit address field never carries)
-      const uint64_t a_desc0 = umma_desc(0, a_lbo, XB * 16u);
-      const uint64_t b_desc0 = umma_desc(0, 3u * NC * 16u, 128u);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0;
-        const uint32_t tph = nbuf == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
-        mbar_wait(&tempty[buf], tph ^ 1);
-        tc_fence_after();
-        const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int nt, b, tz, ty, tx;
+        decode_tile(tile, p, nt, b, tz, ty, tx);
         for (int kc = 0; kc < p.kc_count; ++kc) {
-          mbar_wait(&full[st], ph);
-          tc_fence_after();
-          const uint32_t a0 = smem_u32(ring + (size_t)st * stage_bytes);
-          const uint64_t a_base = a_desc0 + (uint64_t)(a0 >> 4);
-          const uint64_t b_base =
-              b_desc0 + (uint64_t)((p.b_resident ? smem_u32(smem) + (uint32_t)kc * b_bytes : a0 + a_bytes) >> 4);
-          const uint64_t a_tap0 = a_base + (uint64_t)(p.ntaps == 1 ? XB + 1 : 0);
-          if (p.zt == 8) issue_chunk<NC, 8>(a_tap0, b_base, dcol0, kc == 0, p.ntaps == 9, 8);
-          else if (p.zt == 4) issue_chunk<NC, 4>(a_tap0, b_base, dcol0, kc == 0, p.ntaps == 9, 4);
-          else issue_chunk<NC, 0>(a_tap0, b_base, dcol0, kc == 0, p.ntaps == 9, p.zt);
-          umma_commit(&empty[st]);   // smem stage reusable once these MMAs retire
+          mbar_wait(&empty[st], ph ^ 1);
+          if (elect_one()) {
+            uint8_t* sa = ring + (size_t)st * stage_bytes;
+            uint64_t* ready = xform ? &rawfull[st] : &full[st];
+            mbar_arrive_expect_tx(ready, stage_bytes);
+            tma_load_c8(sa, &tmapA, ready, p.tmap_merged, tx * TILE_X - 1, ty * TILE_Y - 1, tz * p.zt - 1,
+                        b * p.in_groups_total + p.in_group_off + 2 * kc);
+            if (!p.b_resident)
+              bulk_load(sa + a_bytes,
+                        reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)(nt * p.kc_count + kc) * b_bytes, b_bytes,
+                        ready);
+          }
+          __syncwarp();
           if (++st == nstage) { st = 0; ph ^= 1; }
         }
-        umma_commit(&tfull[buf]);     // accumulators of this tile complete
       }
+    } else if (warp == 1) {
+      // ===================================================================== MMA issuer (ONE thread runs the loop)
+      if (elect_one()) {
+        uint32_t tcount = 0;
+        int st = 0;
+        uint32_t ph = 0;
+        if (p.b_resident) {
+          mbar_wait(bfull, 0);
+          tc_fence_after();
+        }
+        const uint32_t a_lbo = (uint32_t)zb * SLAB * 16u;  // next channel group (K chunk of 8)
+        // descriptors with a zero address field; tap / slab / row-block shifts are added to the low word (16-byte
+        // units; shared memory is < 256 KB so the 14-bit address field never carries)
+        const uint64_t a_desc0 = umma_desc(0, a_lbo, XB * 16u);
+        const uint64_t b_desc0 = umma_desc(0, 3u * NC * 16u, 128u);
+        for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
+          const uint32_t buf = nbuf == 2 ? (tcount & 1) : 0;
+          const uint32_t tph = nbuf == 2 ? ((tcount >> 1) & 1) : (tcount & 1);
+          mbar_wait(&tempty[buf], tph ^ 1);
+          tc_fence_after();
+          const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
+          for (int kc = 0; kc < p.kc_count; ++kc) {
+            mbar_wait(&full[st], ph);
+            tc_fence_after();
+            const uint32_t a0 = smem_u32(ring + (size_t)st * stage_bytes);
+            const uint64_t a_base = a_desc0 + (uint64_t)(a0 >> 4);
+            const uint64_t b_base =
+                b_desc0 + (uint64_t)((p.b_resident ? smem_u32(smem) + (uint32_t)kc * b_bytes : a0 + a_bytes) >> 4);
+            const uint64_t a_tap0 = a_base + (uint64_t)(p.ntaps == 1 ? XB + 1 : 0);
+            if (p.zt == 8) issue_chunk<NC, 8>(a_tap0, b_base, dcol0, kc == 0, p.ntaps == 9, 8);
+            else if (p.zt == 4) issue_chunk<NC, 4>(a_tap0, b_base, dcol0, kc == 0, p.ntaps == 9, 4);
+            else issue_chunk<NC, 0>(a_tap0, b_base, dcol0, kc == 0, p.ntaps == 9, p.zt);
+            umma_commit(&empty[st]);   // smem stage reusable once these MMAs retire
+            if (++st == nstage) { st = 0; ph ^= 1; }
+          }
+          umma_commit(&tfull[buf]);     // accumulators of this tile complete
+        }
+      }
+      __syncwarp();
     }
-    __syncwarp();
-  } else {
-    // ===================================================================== epilogue (warps 2..5)
+  } else if (warp < 8) {
+    // ===================================================================== epilogue (warps 4..7)
+    reg_alloc<REGS_EPI>();
     const int q = warp & 3;                  // TMEM lane quadrant this warp may read
     const int row = q * 32 + lane;
     uint32_t tcount = 0;
-    const int out_groups = p.Cout / 8;
     RunningStats run[NC / 32];
     for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
       int nt, b, tz, ty, tx;
@@ -234,9 +240,10 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
       for (int chunk = 0; chunk < NC / 32; ++chunk) {
         const int cbase = nt * NC + chunk * 32;
         uint4* dst = reinterpret_cast<uint4*>(p.out) +
-                     ((((size_t)b * out_groups + (cbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
+                     ((((size_t)b * p.out_groups_total + p.out_group_off + (cbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
         conv_epilogue_strip(tlane + chunk * 32, NC, p.zt, p.bias + cbase, rowvalid, tz * p.zt, p.D, dst, zstride, gstride,
-                            lane, b * p.Cout + cbase, run[chunk], p.stats);
+                            lane, b * p.Cout + cbase, run[chunk], p.stats,
+                            s2d_dst(p.s2d, b, p.Cout / 8, cbase >> 3, p.D, p.H, p.W, y, x));
       }
       tc_fence_before();
       __syncwarp();
@@ -244,212 +251,41 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
     }
 #pragma unroll
     for (int chunk = 0; chunk < NC / 32; ++chunk) stats_flush(run[chunk], p.stats, lane);
+  } else {
+    // ===================================================================== operand transform (warps 8..11)
+    reg_dealloc<REGS_XF>();
+    if (xform) {
+      const int tid = threadIdx.x - 256;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int nt, b, tz, ty, tx;
+        decode_tile(tile, p, nt, b, tz, ty, tx);
+        // box index i <-> volume coordinate t * T - 1 + i: the in-volume part of the box
+        const int z0 = tz * p.zt - 1, y0 = ty * TILE_Y - 1, x0 = tx * TILE_X - 1;
+        const int zlo = z0 < 0 ? -z0 : 0, zhi = p.D - z0 < zb ? p.D - z0 : zb;
+        const int ylo = y0 < 0 ? -y0 : 0, yhi = p.H - y0 < YB ? p.H - y0 : YB;
+        const int xlo = x0 < 0 ? -x0 : 0, xhi = p.W - x0 < XB ? p.W - x0 : XB;
+        for (int kc = 0; kc < p.kc_count; ++kc) {
+          const int g0 = 2 * kc;  // first channel group of this K chunk inside the input view
+          const int skip = (g0 < p.xf.ident_groups ? 1 : 0) | (g0 + 1 < p.xf.ident_groups ? 2 : 0) |
+                           (8 * g0 + 8 >= p.xf.channels ? 2 : 0);
+          mbar_wait(&rawfull[st], ph);
+          if (skip != 3)
+            xform_stage<XB, YB, 128>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
+                                     p.xf.scale + (size_t)b * p.xf.channels + 16 * kc,
+                                     p.xf.shift + (size_t)b * p.xf.channels + 16 * kc, skip, p.xf.slope, tid);
+          fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[st]);
+          if (++st == nstage) { st = 0; ph ^= 1; }
+        }
+      }
+    }
   }
   tc_fence_before();
   __syncthreads();
   if (warp == 1) tmem_dealloc(tbase, 512);
-}
-
-// ================================================================================================ fused normalisation
-// conv3_fold_kernel<32> for a layer whose input is the RAW output of the previous conv of the same stage: the
-// InstanceNorm affine + LeakyReLU of that producer is applied while the operand is staged, so the producer's
-// standalone normalise pass (read + write of the whole tensor) disappears.  An earlier variant transformed the tile
-// in place in shared memory after TMA had written it (profiles/r01_fused_norm.txt): a wash, because the extra LDS +
-// STS land on the shared-memory port the N = 96 MMAs already saturate.  Here the TMA producer is REPLACED: eight
-// loader warps read the raw tensor with plain 16-byte loads (8 in flight per thread), transform in registers and
-// store the tile once - the same shared-memory traffic as the TMA write it replaces.  Out-of-volume halo positions
-// are stored as zeros (the conv pads the ACTIVATED tensor).  Same fp32 operations as norm_lrelu_kernel, so the
-// result is bit-identical to the unfused schedule (tests/test_gpu_network.py).  Weights of all K chunks stay resident
-// (Cout = 32: 27 KB per chunk); 13 warps share the register file (ptxas caps 416 threads at 128 registers - the
-// allocation granularity is four warps), hence the 16-column epilogue strips.
-// Measured (B200, 32->32 at 128^3, batch 8): 1.18 ms against 0.81 ms unfused + 0.35 ms for the pass it removes - the
-// loaders (two rounds of 8 loads per stage, ~2 us of exposed latency each) do not keep up with the 3.5 us the MMAs
-// of a stage take; holding a thread's whole share of a stage in registers (15 loads) spills at 128 registers and ran
-// at 2.5 ms.  So this is an opt-in (BOA_B200_LDNORM=1) until the loader is rebuilt on cp.async / 12 warps.
-// ws: warp-private shared-memory slot [8 scale][8 shift] (broadcast float4 reads: the registers go to loads in flight)
-__device__ __forceinline__ uint4 ldn_transform(const uint4& raw, const float* ws, float slope) {
-  uint4 o;
-  const __half2* h = reinterpret_cast<const __half2*>(&raw);
-  __half2* r = reinterpret_cast<__half2*>(&o);
-  const float4 a0 = *reinterpret_cast<const float4*>(ws), a1 = *reinterpret_cast<const float4*>(ws + 4);
-  const float4 s0 = *reinterpret_cast<const float4*>(ws + 8), s1 = *reinterpret_cast<const float4*>(ws + 12);
-  const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-  const float sh[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    float2 f = __half22float2(h[e]);
-    f.x = __fadd_rn(__fmul_rn(f.x, a[2 * e]), sh[2 * e]);
-    f.y = __fadd_rn(__fmul_rn(f.y, a[2 * e + 1]), sh[2 * e + 1]);
-    f.x = f.x > 0.f ? f.x : __fmul_rn(f.x, slope);
-    f.y = f.y > 0.f ? f.y : __fmul_rn(f.y, slope);
-    r[e] = __floats2half2_rn(f.x, f.y);
-  }
-  return o;
-}
-
-__global__ void __launch_bounds__(LDN_THREADS, 1)
-conv3_fold_ldnorm_kernel(const ConvMmaParams p) {
-  constexpr int NC = 32;
-  extern __shared__ __align__(1024) uint8_t smem[];
-  const int zb = p.zt + 2;
-  const uint32_t a_bytes = 2u * zb * SLAB * 16u;
-  constexpr uint32_t b_bytes = 9u * 96u * NC;
-  const uint32_t bres_bytes = (uint32_t)p.kc_count * b_bytes;
-  uint8_t* const ring = smem + bres_bytes;
-  const int nstage = p.stages;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(ring + (size_t)nstage * a_bytes);
-  uint64_t* full = bars;         // [4] loaders (256 arrivals) -> MMA
-  uint64_t* empty = bars + 4;    // [4] MMA -> loaders
-  uint64_t* tfull = bars + 8;    // [2] MMA -> epilogue
-  uint64_t* tempty = bars + 10;  // [2] epilogue -> MMA
-  uint64_t* bfull = bars + 12;   // [1] resident weights landed
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-
-  if (threadIdx.x == 0) {
-    for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], 32 * LDN_LOADER_WARPS);
-      mbar_init(&empty[i], 1);
-    }
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(&tfull[i], 1);
-      mbar_init(&tempty[i], 4);
-    }
-    mbar_init(bfull, 1);
-    fence_barrier_init();
-  }
-  if (warp == 0) {
-    tmem_alloc(tmem_slot, 512);
-    tmem_relinquish();
-  }
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tbase = *tmem_slot;
-
-  if (warp == 0) {
-    // ===================================================================== weights + MMA issuer (one elected thread)
-    if (elect_one()) {
-      mbar_arrive_expect_tx(bfull, bres_bytes);
-      for (int kc = 0; kc < p.kc_count; ++kc)
-        bulk_load(smem + (size_t)kc * b_bytes, reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)kc * b_bytes,
-                  b_bytes, bfull);
-      mbar_wait(bfull, 0);
-      tc_fence_after();
-      uint32_t tcount = 0;
-      int st = 0;
-      uint32_t ph = 0;
-      const uint32_t a_lbo = (uint32_t)zb * SLAB * 16u;
-      const uint64_t a_desc0 = umma_desc(0, a_lbo, XB * 16u);
-      const uint64_t b_desc0 = umma_desc(0, 3u * NC * 16u, 128u);
-      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-        const uint32_t buf = tcount & 1;
-        mbar_wait(&tempty[buf], ((tcount >> 1) & 1) ^ 1);
-        tc_fence_after();
-        const uint32_t dcol0 = tbase + buf * (uint32_t)(p.zt * NC);
-        for (int kc = 0; kc < p.kc_count; ++kc) {
-          mbar_wait(&full[st], ph);
-          tc_fence_after();
-          const uint64_t a_base = a_desc0 + (uint64_t)(smem_u32(ring + (size_t)st * a_bytes) >> 4);
-          const uint64_t b_base = b_desc0 + (uint64_t)((smem_u32(smem) + (uint32_t)kc * b_bytes) >> 4);
-          if (p.zt == 8) issue_chunk<NC, 8>(a_base, b_base, dcol0, kc == 0, true, 8);
-          else if (p.zt == 4) issue_chunk<NC, 4>(a_base, b_base, dcol0, kc == 0, true, 4);
-          else issue_chunk<NC, 0>(a_base, b_base, dcol0, kc == 0, true, p.zt);
-          umma_commit(&empty[st]);
-          if (++st == nstage) { st = 0; ph ^= 1; }
-        }
-        umma_commit(&tfull[buf]);
-      }
-    }
-    __syncwarp();
-  } else if (warp <= 4) {
-    // ===================================================================== epilogue (warps 1..4)
-    const int q = warp & 3;
-    const int row = q * 32 + lane;
-    uint32_t tcount = 0;
-    const int out_groups = p.Cout / 8;
-    RunningStats16 run;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x, ++tcount) {
-      int nt, b, tz, ty, tx;
-      decode_tile(tile, p, nt, b, tz, ty, tx);
-      const uint32_t buf = tcount & 1;
-      mbar_wait(&tfull[buf], (tcount >> 1) & 1);
-      tc_fence_after();
-      const int x = tx * TILE_X + (row & 7), y = ty * TILE_Y + (row >> 3);
-      const bool rowvalid = (x < p.W) && (y < p.H);
-      const uint32_t tlane = tbase + ((uint32_t)(q * 32) << 16) + buf * (uint32_t)(p.zt * NC);
-      const size_t zstride = (size_t)p.H * p.W, gstride = (size_t)p.D * zstride;
-#pragma unroll
-      for (int chunk = 0; chunk < NC / 16; ++chunk) {
-        const int cbase = chunk * 16;
-        uint4* dst = reinterpret_cast<uint4*>(p.out) +
-                     ((((size_t)b * out_groups + (cbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
-        conv_epilogue_strip16(tlane + chunk * 16, NC, p.zt, p.bias + cbase, rowvalid, tz * p.zt, p.D, dst, zstride,
-                              gstride, lane, b * p.Cout, chunk & 1, run, p.stats);
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty[buf]);
-    }
-    stats_flush16(run, p.stats, lane);
-  } else {
-    // ===================================================================== loaders (warps 5..12)
-    const int lt = threadIdx.x - 160;  // 0..255
-    const int g = lt >> 7;             // channel group (of the two of a K chunk) this thread stages
-    const int t = lt & 127;
-    const int per_group = zb * SLAB;
-    // (dynamic shared memory: a static array would make the 227 KB opt-in of the attribute invalid)
-    float* wsl = reinterpret_cast<float*>(bars + 16) + (warp - 5) * 16;
-    constexpr int U = 8;               // loads in flight per thread (two rounds per stage)
-    int st = 0;
-    uint32_t ph = 0;
-    for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
-      int nt, b, tz, ty, tx;
-      decode_tile(tile, p, nt, b, tz, ty, tx);
-      const int z0 = tz * p.zt - 1, y0 = ty * TILE_Y - 1, x0 = tx * TILE_X - 1;
-      for (int kc = 0; kc < p.kc_count; ++kc) {
-        // scale / shift of this warp's 8 channels into its shared-memory slot (previous readers are past it: they
-        // arrived on full[] after their last transform, and a warp runs its stages in order)
-        __syncwarp();
-        if (lane < 16)
-          wsl[lane] = lane < 8 ? __ldg(p.in_scale + (size_t)b * p.in_channels + kc * 16 + g * 8 + lane)
-                               : __ldg(p.in_shift + (size_t)b * p.in_channels + kc * 16 + g * 8 + lane - 8);
-        __syncwarp();
-        const uint4* plane0 = reinterpret_cast<const uint4*>(p.in_raw) +
-                              (size_t)(b * p.in_groups_total + p.in_group_off + 2 * kc + g) * p.D * p.H * p.W;
-        mbar_wait(&empty[st], ph ^ 1);
-        uint4* dst = reinterpret_cast<uint4*>(ring + (size_t)st * a_bytes) + g * per_group;
-        for (int base = t; base < per_group; base += 128 * U) {
-          uint4 r[U];
-          uint32_t okmask = 0;
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int pos = base + u * 128;
-            if (pos < per_group) {
-              const int z = pos / SLAB, rr = pos - z * SLAB, y = rr / XB, x = rr - y * XB;
-              const int gz = z0 + z, gy = y0 + y, gx = x0 + x;
-              if (gz >= 0 && gz < p.D && gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-                okmask |= 1u << u;
-                r[u] = __ldg(plane0 + ((size_t)gz * p.H + gy) * p.W + gx);
-              }
-            }
-          }
-#pragma unroll
-          for (int u = 0; u < U; ++u) {
-            const int pos = base + u * 128;
-            if (pos < per_group)
-              dst[pos] = (okmask >> u) & 1u ? ldn_transform(r[u], wsl, p.slope) : make_uint4(0u, 0u, 0u, 0u);
-          }
-        }
-        fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
-        mbar_arrive(&full[st]);
-        if (++st == nstage) { st = 0; ph ^= 1; }
-      }
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 0) tmem_dealloc(tbase, 512);
 }
 
 // ================================================================================================ host side
@@ -459,15 +295,13 @@ struct ConvMmaPlan {
   __half* d_bpacked = nullptr;
   float* d_bias = nullptr;
   int nc = 32;
-  bool fused = false;  // conv3_fold_ldnorm_kernel: the input is the producer's raw output, normalised while staged
   size_t smem = 0;
   int grid = 0;
   double macs = 0;
 };
 
 ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin_w, int cin_padded, int Cout,
-                                  const ActView& src, int B, __half* d_raw_out, double* d_stats, bool taps_on_k,
-                                  const float* d_in_scale, const float* d_in_shift, float slope) {
+                                  const ActView& src, int B, const ConvIO& io, double* d_stats, bool taps_on_k) {
   // taps_on_k (first layer, Cin = 1): the source tensor carries the 9 in-plane neighbours of every voxel as its
   // channels 0..8, h_w is [Cout][1][27]; only the dz taps remain as (folded) taps.
   const int ntaps = taps_on_k ? 1 : 9;
@@ -493,14 +327,15 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   p.n_ntiles = Cout / NC;
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_z * B * p.n_ntiles;
   p.in_groups_total = src.groups_total; p.in_group_off = src.group_off;
-  p.out = d_raw_out; p.stats = d_stats;
+  p.out = io.out.base; p.out_groups_total = io.out.groups_total; p.out_group_off = io.out.group_off;
+  p.s2d = io.s2d;
+  p.stats = d_stats;
   p.ntaps = ntaps;
   p.tmap_merged = c8_tmap_merged() ? 1 : 0;
-  p.in_scale = d_in_scale; p.in_shift = d_in_shift; p.in_channels = cin_w; p.slope = slope;
-  p.in_raw = src.base;
-  pl->fused = d_in_scale != nullptr;
-  if (pl->fused && (cin_w % 16 != 0 || taps_on_k || NC != 32 || p.n_ntiles != 1)) {
-    set_error("conv_mma: fused input normalisation needs Cin %% 16 == 0 and Cout == 32");
+  p.xf = io.xf;
+  if (io.out.groups < Cout / 8 || (io.s2d && ((src.D | src.H | src.W) & 1)) ||
+      (io.xf.scale && (taps_on_k || io.xf.channels != cin_w || cin_w % 16 != 0))) {
+    set_error("conv_mma: bad output view / space-to-depth copy / input transform for cin=%d cout=%d", cin_w, Cout);
     conv_mma_plan_destroy(pl);
     return nullptr;
   }
@@ -548,13 +383,8 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   const size_t a_stage = 2 * (size_t)(zt + 2) * SLAB * 16, b_chunk = (size_t)ntaps * 96 * (size_t)NC;
   const size_t smem_cap = (size_t)MAX_DYN_SMEM - 1024;  // barriers + the loaders' scale / shift slots
   const char* bres_env = getenv("BOA_B200_BRES");
-  p.b_resident = (p.n_ntiles == 1 && (pl->fused || !(bres_env && atoi(bres_env) == 0)) &&
+  p.b_resident = (p.n_ntiles == 1 && !(bres_env && atoi(bres_env) == 0) &&
                   p.kc_count * b_chunk + 2 * a_stage <= smem_cap) ? 1 : 0;
-  if (pl->fused && !p.b_resident) {
-    set_error("conv_mma: fused input normalisation needs the weights of all %d K chunks resident", p.kc_count);
-    conv_mma_plan_destroy(pl);
-    return nullptr;
-  }
   const size_t stage = a_stage + (p.b_resident ? 0 : b_chunk);
   const size_t fixed = p.b_resident ? p.kc_count * b_chunk : 0;
   int stages = (int)((smem_cap - fixed) / stage);
@@ -567,8 +397,7 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   p.stages = stages;
   pl->smem = fixed + (size_t)stages * stage + 768;
   cudaError_t e = cudaSuccess;
-  for (const void* fn : {(const void*)conv3_fold_kernel<64>, (const void*)conv3_fold_kernel<32>,
-                         (const void*)conv3_fold_ldnorm_kernel}) {
+  for (const void* fn : {(const void*)conv3_fold_kernel<64>, (const void*)conv3_fold_kernel<32>}) {
     cudaError_t e2 = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
     if (e2 != cudaSuccess) e = e2;
   }
@@ -597,9 +426,7 @@ int conv_mma_launch(ConvMmaPlan* pl, cudaStream_t s, int nb) {
     p.B = nb;
     pl->grid = p.total_tiles < sm_count() ? p.total_tiles : sm_count();
   }
-  if (pl->fused)
-    conv3_fold_ldnorm_kernel<<<pl->grid, LDN_THREADS, pl->smem, s>>>(pl->prm);
-  else if (pl->nc == 64)
+  if (pl->nc == 64)
     conv3_fold_kernel<64><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
   else
     conv3_fold_kernel<32><<<pl->grid, MMA_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);

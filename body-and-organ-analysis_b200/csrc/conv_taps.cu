@@ -12,21 +12,24 @@
 // Replaces the cuDNN calls behind nn.Conv3d / nn.ConvTranspose3d of dynamic_network_architectures' PlainConvEncoder /
 // UNetDecoder, invoked at _external/nnunetv2/inference/predict_from_raw_data.py:543.
 //
-// Structure: persistent CTAs, warp 0 = TMA producer, warp 1 = MMA issuer, warps 2-5 = epilogue; A = TMA 5-D halo box
-// of the C8 tensor (zero filled out of bounds = conv padding), taps are 16-byte address offsets into it; B = weights
-// pre-packed on the host into the smem operand image, one bulk copy per chunk; accumulators: one TMEM slot of NC
-// columns per output z-plane of the tile, double buffered.
+// Structure: persistent CTAs of three warpgroups like conv_mma.cu (WG0 = TMA producer + MMA issuer, WG1 = epilogue,
+// WG2 = operand transform: the input is the producer's RAW output, normalised in shared memory, conv_xform.cuh);
+// A = TMA halo box of the C8 tensor (zero filled out of bounds = conv padding), taps are 16-byte address offsets into
+// it; B = weights pre-packed on the host into the smem operand image, one bulk copy per chunk; accumulators: one TMEM
+// slot of NC columns per output z-plane of the tile, double buffered.
 #include <stdlib.h>
 #include <algorithm>
 #include <vector>
 #include "net_kernels.cuh"
 #include "conv_epilogue.cuh"
+#include "conv_xform.cuh"
 #include "ptx.cuh"
 #include "tmap.cuh"
 
 namespace boa {
 
-constexpr int TAPS_THREADS = 192;
+constexpr int TAPS_THREADS = 384;  // three warpgroups, see conv_mma.cu
+constexpr int TREGS_WG0 = 104, TREGS_EPI = 248, TREGS_XF = 128;
 constexpr int TT_X = 8, TT_Y = 16;
 constexpr int TAPS_MAX_OPS = 27;
 constexpr int TAPS_MAX_STAGES = 12;  // smem ring depth: small stages (transposed conv, deep layers) prefetch several tiles ahead
@@ -45,6 +48,9 @@ struct TapsParams {
   int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
   int in_groups_total, in_group_off;
   int out_groups_total, out_group_off, Cout;
+  __half* s2d;   // optional space-to-depth copy of a conv output (nullptr: none)
+  InXform xf;    // fused normalisation of the input (xf.scale == nullptr: none)
+  int halo;      // box = tile + halo per axis: 2 (3x3x3 stride 1), 1 (stride 2 on the s2d tensor), 0 (transposed)
   int stages;
   int tmap_merged;  // tensor map built with the (channel, x) dimensions merged (tmap.cuh)
   uint32_t a_bytes, a_tx_bytes, b_stage_bytes, b_nt_bytes;  // a_bytes: smem placement (128 B multiple), a_tx: TMA box
@@ -67,18 +73,21 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * stage_bytes);
   uint64_t* full = bars;                            // [TAPS_MAX_STAGES] TMA -> MMA
   uint64_t* empty = bars + TAPS_MAX_STAGES;         // [TAPS_MAX_STAGES] MMA -> TMA
-  uint64_t* tfull = bars + 2 * TAPS_MAX_STAGES;     // [2] MMA -> epilogue
+  uint64_t* rawfull = bars + 2 * TAPS_MAX_STAGES;   // [TAPS_MAX_STAGES] TMA -> transform warps
+  uint64_t* tfull = bars + 3 * TAPS_MAX_STAGES;     // [2] MMA -> epilogue
   uint64_t* tempty = tfull + 2;                     // [2] epilogue -> MMA
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty + 2);
   int32_t* stab = reinterpret_cast<int32_t*>(tempty + 4);  // [n_classes][TAB_STRIDE] tap table (<= 8 classes)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nstage = p.stages;
+  const bool xform = p.xf.scale != nullptr;
   for (int i = threadIdx.x; i < p.n_classes * TAB_STRIDE; i += blockDim.x) stab[i] = __ldg(p.table + i);
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TAPS_MAX_STAGES; ++i) {
-      mbar_init(&full[i], 1);
+      mbar_init(&full[i], xform ? 4 : 1);
       mbar_init(&empty[i], 1);
+      mbar_init(&rawfull[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull[i], 1);
@@ -97,6 +106,8 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
   const uint32_t tbase = *tmem_slot;
   const uint32_t buf_cols = (uint32_t)(p.zt * NC);  // <= 256: two accumulator buffers
 
+  if (warp < 4) {
+  reg_dealloc<TREGS_WG0>();
   if (warp == 0) {
     // ===================================================================== TMA producer
     uint32_t it = 0;
@@ -114,12 +125,13 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
         if (elect_one()) {
           uint8_t* sa = smem + (size_t)st * stage_bytes;
           const uint32_t bbytes = (uint32_t)n_ops * NC * 32u;
-          mbar_arrive_expect_tx(&full[st], p.a_tx_bytes + bbytes);
-          tma_load_c8(sa, &tmapA, &full[st], p.tmap_merged, tx * TT_X + p.org, ty * TT_Y + p.org, tz * p.zt + p.org,
+          uint64_t* ready = xform ? &rawfull[st] : &full[st];
+          mbar_arrive_expect_tx(ready, p.a_tx_bytes + bbytes);
+          tma_load_c8(sa, &tmapA, ready, p.tmap_merged, tx * TT_X + p.org, ty * TT_Y + p.org, tz * p.zt + p.org,
                       b * p.in_groups_total + p.in_group_off + 2 * kc);
           bulk_load(sa + p.a_bytes,
                     reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)nt * p.b_nt_bytes + (size_t)b_off * 16u,
-                    bbytes, &full[st]);
+                    bbytes, ready);
         }
         __syncwarp();
         if (++st == nstage) { st = 0; ph ^= 1; }
@@ -163,8 +175,48 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
       }
     }
     __syncwarp();
+  }
+  } else if (warp >= 8) {
+    // ===================================================================== operand transform (warps 8..11)
+    reg_dealloc<TREGS_XF>();
+    if (xform) {
+      const int tid = threadIdx.x - 256;
+      int st = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
+        int nt, b, tz, ty, tx;
+        taps_decode_tile(tile, p, nt, b, tz, ty, tx);
+        // box index i <-> tensor coordinate t * T + org + i: the in-volume part of the box
+        const int z0 = tz * p.zt + p.org, y0 = ty * TT_Y + p.org, x0 = tx * TT_X + p.org;
+        const int zlo = z0 < 0 ? -z0 : 0, zhi = p.D - z0 < p.box_z ? p.D - z0 : p.box_z;
+        const int ylo = y0 < 0 ? -y0 : 0, yhi = p.H - y0 < p.box_y ? p.H - y0 : p.box_y;
+        const int xlo = x0 < 0 ? -x0 : 0, xhi = p.W - x0 < p.box_x ? p.W - x0 : p.box_x;
+        for (int kc = 0; kc < p.kc_count; ++kc) {
+          // channels of this K chunk: the stride-2 gather walks the 8 phases of the space-to-depth tensor, each
+          // holding every channel (chunk index inside the phase = kc % chunks_per_class)
+          const int cc = kc % p.chunks_per_class;
+          const int g0 = 2 * cc;
+          const int skip = (g0 < p.xf.ident_groups ? 1 : 0) | (g0 + 1 < p.xf.ident_groups ? 2 : 0) |
+                           (8 * g0 + 8 >= p.xf.channels ? 2 : 0);
+          mbar_wait(&rawfull[st], ph);
+          if (skip != 3) {
+            uint8_t* sa = smem + (size_t)st * stage_bytes;
+            const float* sc = p.xf.scale + (size_t)b * p.xf.channels + 16 * cc;
+            const float* sh = p.xf.shift + (size_t)b * p.xf.channels + 16 * cc;
+            if (p.halo == 2) xform_stage<TT_X + 2, TT_Y + 2, 128>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+            else if (p.halo == 1) xform_stage<TT_X + 1, TT_Y + 1, 128>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+            else xform_stage<TT_X, TT_Y, 128>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+          }
+          fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&full[st]);
+          if (++st == nstage) { st = 0; ph ^= 1; }
+        }
+      }
+    }
   } else {
-    // ===================================================================== epilogue (warps 2..5)
+    // ===================================================================== epilogue (warps 4..7)
+    reg_alloc<TREGS_EPI>();
     const int q = warp & 3;
     const int row = q * 32 + lane;
     uint32_t tcount = 0;
@@ -184,9 +236,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
         if (p.kind != TAPS_TCONV2) {
           const size_t zstride = (size_t)p.H * p.W, gstride = (size_t)p.D * zstride;
           uint4* dst = reinterpret_cast<uint4*>(p.out) +
-                       ((((size_t)b * (p.Cout / 8) + (nbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
+                       ((((size_t)b * p.out_groups_total + p.out_group_off + (nbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
           conv_epilogue_strip(tlane + chunk * 32, NC, p.zt, p.bias + nbase, rowvalid, tz * p.zt, p.D, dst, zstride,
-                              gstride, lane, b * p.Cout + nbase, run[chunk], p.stats);
+                              gstride, lane, b * p.Cout + nbase, run[chunk], p.stats,
+                              s2d_dst(p.s2d, b, p.Cout / 8, nbase >> 3, p.D, p.H, p.W, y, x));
         } else {
           // transposed conv: GEMM column n = (((pz*2+py) * Cout/8 + cg) * 2 + px) * 8 + e : the two x-phases of a
           // channel group are neighbours on N, so a thread writes 32 contiguous bytes (xo = 2x, 2x+1) per group
@@ -238,7 +291,8 @@ struct ConvTapsPlan {
 static inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
 ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float* h_bias, int cin_w, int Cout,
-                                    const ActView& src, int B, const ActView& dst, double* d_stats) {
+                                    const ActView& src, int B, const ConvIO& io, double* d_stats) {
+  const ActView& dst = io.out;
   const int cin_padded = (cin_w + 15) / 16 * 16;
   const int Ntotal = kind == TAPS_TCONV2 ? 8 * Cout : Cout;
   const int src_cin_groups = kind == TAPS_CONV3_S2 ? src.groups / 8 : src.groups;  // groups per phase for s2d
@@ -263,8 +317,16 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
   p.n_ntiles = Ntotal / NC;
   p.total_tiles = p.tiles_x * p.tiles_y * p.tiles_z * B * p.n_ntiles;
   p.in_groups_total = src.groups_total; p.in_group_off = src.group_off;
-  p.out = kind == TAPS_TCONV2 ? dst.base : dst.base;
+  p.out = dst.base;
   p.out_groups_total = dst.groups_total; p.out_group_off = dst.group_off;
+  p.s2d = kind == TAPS_TCONV2 ? nullptr : io.s2d;
+  p.xf = io.xf;
+  p.halo = halo;
+  if (io.xf.scale && (io.xf.channels != cin_w || cin_w % 16 != 0)) {
+    set_error("conv_taps: fused input normalisation needs Cin %% 16 == 0 (cin=%d, scale row %d)", cin_w, io.xf.channels);
+    conv_taps_plan_destroy(pl);
+    return nullptr;
+  }
   p.stats = kind == TAPS_TCONV2 ? nullptr : d_stats;
 
   // ---- chunk table + packed weights
@@ -369,7 +431,7 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
   }
   p.stages = stages;
   p.tmap_merged = c8_tmap_merged() ? 1 : 0;
-  pl->smem = (size_t)stages * stage + (2 * TAPS_MAX_STAGES + 8) * 8 + 8 * TAB_STRIDE * sizeof(int32_t);
+  pl->smem = (size_t)stages * stage + (3 * TAPS_MAX_STAGES + 8) * 8 + 8 * TAB_STRIDE * sizeof(int32_t);
   // the attribute is per kernel, not per plan: always opt in to the full 227 KB
   cudaError_t e = NC == 128 ? cudaFuncSetAttribute(conv_taps_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)
                             : cudaFuncSetAttribute(conv_taps_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);

@@ -28,26 +28,29 @@ struct HostTensor {
 
 enum StepKind { STEP_CONV_FOLD, STEP_CONV_TAPS, STEP_CONV_SIMT, STEP_TCONV_TAPS, STEP_TCONV_SIMT, STEP_CONV_FIRST };
 
-struct ConvStep {  // conv -> (stats) -> norm + lrelu   |   transposed conv
+struct ConvStep {  // conv -> statistics -> (unfused schedule only: norm + lrelu pass)   |   transposed conv
   StepKind kind;
   bool is_tconv = false;
   ActView src;           // input activation (for CONV_TAPS stride 2: the s2d view)
   ActView src_plain;     // SIMT stride-2 path reads the plain activation
+  InXform xf;            // normalisation of the INPUT applied by this step's kernel (fused schedule; scale == nullptr: none)
   int cin = 0, cout = 0;
   int ks[3] = {3, 3, 3}, stride[3] = {1, 1, 1};
   int Do = 0, Ho = 0, Wo = 0;
-  __half* raw = nullptr;       // conv output before normalisation
-  ActView dst;                 // normalised output (conv) or direct output (tconv)
-  __half* s2d = nullptr;       // optional space-to-depth copy of the normalised output
+  ActView out;                 // where the kernel writes: RAW conv output / transposed-conv output
+  __half* out_s2d = nullptr;   // fused schedule: space-to-depth copy of the raw output, written by the conv epilogue
+  bool norm_pass = false;      // unfused schedule: a standalone normalise pass follows (out -> dst [+ s2d])
+  ActView dst;                 // unfused schedule: normalised output
+  __half* s2d = nullptr;       // unfused schedule: space-to-depth copy of the normalised output
   float *d_w = nullptr, *d_bias = nullptr, *d_gamma = nullptr, *d_beta = nullptr;  // SIMT operands / norm affine
   double* d_stats = nullptr;
   float *d_scale = nullptr, *d_shift = nullptr;
+  float *d_scale2 = nullptr, *d_shift2 = nullptr;  // second copy of scale / shift: rows of a concat's combined table
+  int stride2 = 0, off2 = 0;
   ConvMmaPlan* fold = nullptr;
   ConvTapsPlan* taps = nullptr;
   double macs = 0;
   std::string name;
-  bool norm_fused_downstream = false;  // (tensor-core mode) the consumer normalises this step's raw output itself
-  ActView raw_view;                    // this step's raw output as a C8 tensor
 };
 
 // Scratch memory of one forward (activations, statistics, staging).  Networks of identical geometry run one at a
@@ -91,6 +94,8 @@ struct boa_net {
   Workspace* ws = nullptr;    // shared scratch
   Lane lane[MAX_LANES];
   int n_lanes = 2;  // BOA_B200_LANES (1..MAX_LANES)
+  bool fuse = true;  // fused schedule: every kernel normalises its input itself, no standalone normalise pass
+                     // (BOA_B200_UNFUSED=1 at creation selects the pass-per-layer schedule: cross-check / A-B timing)
   std::map<std::string, float*> wcache;  // device copies of the fp32 parameters, shared by the lanes
   // head
   float *d_head_w = nullptr, *d_head_b = nullptr;
@@ -194,48 +199,43 @@ int run_step(boa_net* net, ConvStep& st, cudaStream_t s) {
   const int B = net->cur_nb > 0 ? net->cur_nb : net->B;
   size_t e0 = 0, e1 = 0;
   const bool time_it = net->timing;
+  const bool pass_only = net->debug_only == 2;  // profiling aid: the HBM-bound passes without the convolutions
   if (time_it) cudaEventRecord(next_event(net, &e0), s);
   int r = BOA_OK;
-  if (net->debug_only == 2) {  // thin passes only
-    if (st.is_tconv) return BOA_OK;
-    if ((r = launch_stats_finalize(st.d_stats, st.d_gamma, st.d_beta, B, st.cout, (double)st.Do * st.Ho * st.Wo, a.eps,
-                                   st.d_scale, st.d_shift, s)))
-      return r;
-    if (st.norm_fused_downstream && net->mode == 0) return BOA_OK;
-    return launch_norm_lrelu(st.raw, B, st.cout / 8, st.Do, st.Ho, st.Wo, st.d_scale, st.d_shift, a.leaky_slope, st.dst,
-                             st.s2d, s);
-  }
   if (st.is_tconv) {
+    if (pass_only) return BOA_OK;
     if (st.kind == STEP_TCONV_TAPS && net->mode == 0) r = conv_taps_launch(st.taps, s, B);
-    else r = launch_tconv_simt(st.src, B, st.d_w, st.d_bias, st.cin, st.cout, st.stride, st.dst, s);
+    else r = launch_tconv_simt(st.src, B, st.d_w, st.d_bias, st.cin, st.cout, st.stride, st.out, s, st.xf);
     if (time_it) {
       cudaEventRecord(next_event(net, &e1), s);
       net->conv_spans.push_back({e0, e1});
-      net->conv_span_info.push_back({(int)st.kind, 2.0 * st.macs * B});
+      net->conv_span_info.push_back({net->mode == 0 ? (int)st.kind : (int)STEP_TCONV_SIMT, 2.0 * st.macs * B});
     }
     return r;
   }
-  if (st.kind == STEP_CONV_FIRST)
-    r = launch_conv_first(st.src.base, B, st.d_w, st.d_bias, st.cout, st.raw, st.Do, st.Ho, st.Wo, st.d_stats, s);
-  else if (net->mode == 0 && st.kind == STEP_CONV_FOLD) r = conv_mma_launch(st.fold, s, B);
-  else if (net->mode == 0 && st.kind == STEP_CONV_TAPS) r = conv_taps_launch(st.taps, s, B);
-  else
-    r = launch_conv_simt(st.src_plain, B, st.d_w, st.d_bias, st.cin, st.cout, st.ks, st.stride, st.raw, st.Do, st.Ho,
-                         st.Wo, st.d_stats, s);
-  if (time_it) {
-    cudaEventRecord(next_event(net, &e1), s);
-    net->conv_spans.push_back({e0, e1});
-    net->conv_span_info.push_back({(net->mode == 0 || st.kind == STEP_CONV_FIRST) ? (int)st.kind : (int)STEP_CONV_SIMT,
-                                   2.0 * st.macs * B});
+  if (!pass_only) {
+    if (st.kind == STEP_CONV_FIRST)
+      r = launch_conv_first(st.src.base, B, st.d_w, st.d_bias, st.cout, st.out.base, st.Do, st.Ho, st.Wo, st.d_stats, s);
+    else if (net->mode == 0 && st.kind == STEP_CONV_FOLD) r = conv_mma_launch(st.fold, s, B);
+    else if (net->mode == 0 && st.kind == STEP_CONV_TAPS) r = conv_taps_launch(st.taps, s, B);
+    else
+      r = launch_conv_simt(st.src_plain, B, st.d_w, st.d_bias, st.cin, st.cout, st.ks, st.stride, st.out, st.Do, st.Ho,
+                           st.Wo, st.d_stats, s, st.xf);
+    if (time_it) {
+      cudaEventRecord(next_event(net, &e1), s);
+      net->conv_spans.push_back({e0, e1});
+      net->conv_span_info.push_back({(net->mode == 0 || st.kind == STEP_CONV_FIRST) ? (int)st.kind : (int)STEP_CONV_SIMT,
+                                     2.0 * st.macs * B});
+    }
+    if (r) return r;
+    if (net->debug_only == 1) return BOA_OK;  // convolutions only
   }
-  if (r) return r;
-  if (net->debug_only == 1) return BOA_OK;  // convolutions only
   if ((r = launch_stats_finalize(st.d_stats, st.d_gamma, st.d_beta, B, st.cout, (double)st.Do * st.Ho * st.Wo, a.eps,
-                                 st.d_scale, st.d_shift, s)))
+                                 st.d_scale, st.d_shift, s, st.d_scale2, st.d_shift2, st.stride2, st.off2)))
     return r;
-  if (st.norm_fused_downstream && net->mode == 0) return BOA_OK;
-  return launch_norm_lrelu(st.raw, B, st.cout / 8, st.Do, st.Ho, st.Wo, st.d_scale, st.d_shift, a.leaky_slope, st.dst,
-                           st.s2d, s);
+  if (!st.norm_pass) return BOA_OK;
+  return launch_norm_lrelu(st.out.base, B, st.cout / 8, st.Do, st.Ho, st.Wo, st.d_scale, st.d_shift, a.leaky_slope,
+                           st.dst, st.s2d, s);
 }
 
 // everything of one forward except the input staging and the head
@@ -257,7 +257,7 @@ int run_front(boa_net* net, Lane& L, cudaStream_t s) {
 // heads of one batch, one launch per patch in slicer order; d_logits != nullptr: raw logits of nb patches instead
 int run_heads(boa_net* net, Lane& L, int nb, float* d_logits, cudaStream_t s) {
   const boa_arch& a = net->arch;
-  const bool fh = L.head_scale && net->mode == 0;
+  const bool fh = L.head_scale != nullptr;
   const size_t pv = (size_t)a.patch[0] * a.patch[1] * a.patch[2];
   if (net->debug_only == 1) return BOA_OK;
   const bool time_it = net->timing && !d_logits;
@@ -334,6 +334,7 @@ extern "C" int boa_net_create(const boa_arch* arch, int device, int max_batch, b
   net->ws = new Workspace();
   const char* nl = getenv("BOA_B200_LANES");
   net->n_lanes = nl ? std::max(1, std::min(MAX_LANES, atoi(nl))) : 2;
+  if (const char* u = getenv("BOA_B200_UNFUSED")) net->fuse = atoi(u) == 0;
   if (const char* d = getenv("BOA_B200_DEBUG_ONLY")) net->debug_only = !strcmp(d, "conv") ? 1 : (!strcmp(d, "thin") ? 2 : 0);
   *out = net;
   return BOA_OK;
@@ -393,10 +394,17 @@ static int need(boa_net* net, const std::string& key, const HostTensor** out, si
   return BOA_OK;
 }
 
+// What a consumer reads: a C8 tensor plus, in the fused schedule, the normalisation still to be applied to it.
+struct Feed {
+  ActView view;
+  InXform xf;
+};
+
 static int build_lane(boa_net* net, int li) {
   Lane& L = net->lane[li];
   const boa_arch& a = net->arch;
   const int n = a.n_stages, B = net->B;
+  const bool fuse = net->fuse;
   // ---- spatial dims per stage
   int dims[BOA_MAX_STAGES][3];
   for (int k = 0; k < 3; ++k) dims[0][k] = a.patch[k];
@@ -415,24 +423,39 @@ static int build_lane(boa_net* net, int li) {
     v.D = dims[s][0]; v.H = dims[s][1]; v.W = dims[s][2];
     return v;
   };
-  // ---- buffers
+  // ---- buffers.  Fused schedule: only RAW tensors exist - two ping-pong buffers per stage, the concat buffers (the
+  // transposed conv writes the lower half, the encoder's last conv of the stage writes its raw output straight into
+  // the upper half) and the space-to-depth copies.  Unfused schedule: plus a normalised copy of everything.
   L.d_patch = wsalloc<__half>(net, li, (size_t)B * 16 * vox(0));
   if (!L.d_patch) return BOA_ERR_CUDA;
-  __half *raw[BOA_MAX_STAGES][2], *mid[BOA_MAX_STAGES][2], *outb[BOA_MAX_STAGES], *cat[BOA_MAX_STAGES],
+  __half *raw[BOA_MAX_STAGES][2], *mid[BOA_MAX_STAGES][2] = {}, *outb[BOA_MAX_STAGES] = {}, *cat[BOA_MAX_STAGES],
       *s2d[BOA_MAX_STAGES];
+  float *comb_scale[BOA_MAX_STAGES] = {}, *comb_shift[BOA_MAX_STAGES] = {};
   for (int s = 0; s < n; ++s) {
     const size_t f = (size_t)a.features[s];
     raw[s][0] = wsalloc<__half>(net, li, B * f * vox(s));
     raw[s][1] = wsalloc<__half>(net, li, B * f * vox(s));
-    mid[s][0] = wsalloc<__half>(net, li, B * f * vox(s));
-    mid[s][1] = wsalloc<__half>(net, li, B * f * vox(s));
-    outb[s] = wsalloc<__half>(net, li, B * f * vox(s));
+    if (!raw[s][0] || !raw[s][1]) return BOA_ERR_CUDA;
+    if (!fuse) {
+      mid[s][0] = wsalloc<__half>(net, li, B * f * vox(s));
+      mid[s][1] = wsalloc<__half>(net, li, B * f * vox(s));
+      outb[s] = wsalloc<__half>(net, li, B * f * vox(s));
+      if (!mid[s][0] || !mid[s][1] || !outb[s]) return BOA_ERR_CUDA;
+    }
     cat[s] = s < n - 1 ? wsalloc<__half>(net, li, B * 2 * f * vox(s)) : nullptr;
     const bool iso2 = s < n - 1 && is3(a.strides[s + 1], 2) && dims[s][0] % 2 == 0 && dims[s][1] % 2 == 0 &&
                       dims[s][2] % 2 == 0;
     s2d[s] = iso2 ? wsalloc<__half>(net, li, B * f * vox(s)) : nullptr;
-    if (!raw[s][0] || !raw[s][1] || !mid[s][0] || !mid[s][1] || !outb[s] || (s < n - 1 && !cat[s]) || (iso2 && !s2d[s]))
-      return BOA_ERR_CUDA;
+    if ((s < n - 1 && !cat[s]) || (iso2 && !s2d[s])) return BOA_ERR_CUDA;
+    if (fuse && s < n - 1) {
+      // combined scale / shift rows of the decoder concat [B][2f]: the transposed-conv half is final (identity, never
+      // read: ident_groups), the skip half is written by the encoder conv's statistics kernel every forward
+      comb_scale[s] = wsalloc<float>(net, li, (size_t)B * 2 * f);
+      comb_shift[s] = wsalloc<float>(net, li, (size_t)B * 2 * f);
+      if (!comb_scale[s] || !comb_shift[s]) return BOA_ERR_CUDA;
+      BOA_CUDA(cudaMemset(comb_scale[s], 0, (size_t)B * 2 * f * sizeof(float)));
+      BOA_CUDA(cudaMemset(comb_shift[s], 0, (size_t)B * 2 * f * sizeof(float)));
+    }
   }
   // ---- schedule
   int n_norm_layers = 0;
@@ -446,27 +469,38 @@ static int build_lane(boa_net* net, int li) {
   int layer_idx = 0;
   double macs = 0;
 
-  // first layer: Cin = 1, 3x3x3, stride 1 runs as a direct convolution from a plain fp16 patch (no C8 padding)
   // first layer (Cin = 1, 3x3x3): on the tensor cores with the 9 in-plane taps moved onto K (K = 16, three folded
   // dz taps) when Cout % 32 == 0, else the direct FP32 kernel from a plain fp16 patch
   const bool first33 = a.in_channels == 1 && is3(a.kernels[0], 3) && a.n_conv_enc[0] >= 1;
-  net->input_mode = (first33 && a.features[0] % 32 == 0) ? 2 : (first33 && conv_first_supported(a.features[0]) ? 1 : 0);
+  // (the direct kernel writes a dense tensor: not usable when the first conv is also the last of its stage in the
+  // fused schedule, where the output goes into the concat buffer)
+  const bool first_dense = !(fuse && a.n_conv_enc[0] == 1 && n > 1);
+  net->input_mode = (first33 && a.features[0] % 32 == 0) ? 2
+                    : (first33 && first_dense && conv_first_supported(a.features[0]) ? 1 : 0);
   bool first_plain = net->input_mode == 1;
   bool first_nb9 = net->input_mode == 2;
   int raw_flip = 0;
-  auto add_conv = [&](const std::string& prefix, ActView src, ActView src_s2d, int cin, int cout, const int* ks,
-                      const int* stride, int s_out, ActView dst, __half* s2d_out, ConvStep* producer) -> int {
+  // final_dst: where the consumer expects this conv's result (fused: the raw output is written there; unfused: the
+  // normalise pass writes there and the raw output goes to a ping-pong buffer).  want_s2d: the next stage's stride-2
+  // conv wants a space-to-depth copy of the result.
+  auto add_conv = [&](const std::string& prefix, const Feed& in, const ActView& in_s2d, int cin, int cout,
+                      const int* ks, const int* stride, int s_out, const ActView& final_dst, __half* want_s2d) -> int {
     ConvStep st;
     st.name = prefix;
     st.cin = cin; st.cout = cout;
     for (int k = 0; k < 3; ++k) { st.ks[k] = ks[k]; st.stride[k] = stride[k]; }
     st.Do = dims[s_out][0]; st.Ho = dims[s_out][1]; st.Wo = dims[s_out][2];
-    st.raw = raw[s_out][raw_flip & 1];
-    ++raw_flip;
-    st.raw_view = view(st.raw, cout / 8, 0, cout / 8, s_out);
-    st.dst = dst;
-    st.s2d = s2d_out;
-    st.src_plain = src;
+    if (fuse) {
+      st.out = final_dst;
+    } else {
+      st.out = view(raw[s_out][raw_flip & 1], cout / 8, 0, cout / 8, s_out);
+      ++raw_flip;
+      st.norm_pass = true;
+      st.dst = final_dst;
+      st.s2d = want_s2d;
+    }
+    st.src_plain = in.view;
+    st.xf = in.xf;
     const size_t k3 = (size_t)ks[0] * ks[1] * ks[2];
     const HostTensor *w, *bi, *g, *be;
     if (int r = need(net, prefix + ".conv.weight", &w, (size_t)cout * cin * k3)) return r;
@@ -486,48 +520,53 @@ static int build_lane(boa_net* net, int li) {
     st.macs = (double)k3 * cin * cout * st.Do * st.Ho * st.Wo;
     macs += st.macs;
     st.kind = STEP_CONV_SIMT;
-    st.src = src;
+    st.src = in.view;
+    ConvIO io;
+    io.out = st.out;
+    io.xf = in.xf;
     const int cin_padded = (cin + 15) / 16 * 16;
+    // a transform in the tensor-core kernels works on whole K chunks of 16 channels
+    const bool xf_ok = !in.xf.scale || cin % 16 == 0;
     if (first_plain) {
       st.kind = STEP_CONV_FIRST;
     } else if (first_nb9) {
-      st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats, true);
+      io.s2d = fuse ? want_s2d : nullptr;
+      st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, in.view, B, io, st.d_stats, true);
       if (!st.fold) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_FOLD;
-    } else if (is3(ks, 3) && is3(stride, 1) && cout % 32 == 0 && cin_padded <= src.groups * 8) {
-      // The producer is the previous conv of this stage and nothing else reads its output: this conv CAN read the RAW
-      // tensor and normalise it while staging the operand (conv3_fold_ldnorm_kernel: loader warps on the global ->
-      // shared path), so that the producer's standalone InstanceNorm / LeakyReLU pass disappears.  Built for Cout = 32
-      // with all weights resident (Cin <= 64) - the two full-resolution conv1 layers.  Bit-identical, but measured
-      // slower than conv + pass (see the kernel): opt-in with BOA_B200_LDNORM=1.
-      const bool fuse = producer && !producer->is_tconv && cin % 16 == 0 && producer->cout == cin && cout == 32 &&
-                        cin <= 64 && getenv("BOA_B200_LDNORM") != nullptr;
-      if (fuse) {
-        st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, producer->raw_view, B, st.raw,
-                                       st.d_stats, false, producer->d_scale, producer->d_shift, a.leaky_slope);
-        if (st.fold) producer->norm_fused_downstream = true;
-      }
-      if (!st.fold)
-        st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, src, B, st.raw, st.d_stats);
+    } else if (is3(ks, 3) && is3(stride, 1) && cout % 32 == 0 && cin_padded <= in.view.groups * 8 && xf_ok) {
+      io.s2d = fuse ? want_s2d : nullptr;
+      st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, in.view, B, io, st.d_stats);
       if (!st.fold) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_FOLD;
-    } else if (is3(ks, 3) && is3(stride, 2) && src_s2d.base && cin % 16 == 0 && cout % 64 == 0) {
-      ActView rawv = dst;  // only dims/base used by the conv epilogue
-      rawv.base = st.raw; rawv.groups_total = cout / 8; rawv.group_off = 0; rawv.groups = cout / 8;
-      st.taps = conv_taps_plan_create(TAPS_CONV3_S2, wr.data(), bi->data.data(), cin, cout, src_s2d, B, rawv,
-                                      st.d_stats);
+    } else if (is3(ks, 3) && is3(stride, 2) && in_s2d.base && cin % 16 == 0 && cout % 64 == 0) {
+      io.s2d = fuse ? want_s2d : nullptr;
+      st.taps = conv_taps_plan_create(TAPS_CONV3_S2, wr.data(), bi->data.data(), cin, cout, in_s2d, B, io, st.d_stats);
       if (!st.taps) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_TAPS;
-      st.src = src_s2d;
+      st.src = in_s2d;
     }
+    if (fuse && (st.kind == STEP_CONV_FOLD || st.kind == STEP_CONV_TAPS)) st.out_s2d = want_s2d;
     first_plain = false;
     first_nb9 = false;
     L.steps.push_back(st);
     return BOA_OK;
   };
+  // what the consumers of the step just added read
+  auto feed_of_last = [&](const ActView& final_dst) {
+    Feed f;
+    f.view = final_dst;
+    if (fuse) {
+      const ConvStep& st = L.steps.back();
+      f.xf.scale = st.d_scale; f.xf.shift = st.d_shift; f.xf.channels = st.cout; f.xf.ident_groups = 0;
+      f.xf.slope = a.leaky_slope;
+    }
+    return f;
+  };
 
   // encoder
-  ActView cur = view(L.d_patch, 2, 0, 2, 0);
+  Feed cur;
+  cur.view = view(L.d_patch, 2, 0, 2, 0);
   ActView cur_s2d;  // s2d copy of `cur` when it exists
   int cur_c = a.in_channels;
   for (int s = 0; s < n; ++s) {
@@ -536,19 +575,24 @@ static int build_lane(boa_net* net, int li) {
       const bool last = i == a.n_conv_enc[s] - 1;
       const int one[3] = {1, 1, 1};
       const int* stride = i == 0 ? a.strides[s] : one;
-      ActView dst = last ? (s < n - 1 ? view(cat[s], 2 * f / 8, f / 8, f / 8, s) : view(outb[s], f / 8, 0, f / 8, s))
-                         : view(mid[s][i & 1], f / 8, 0, f / 8, s);
+      ActView dst;
+      if (last && s < n - 1) dst = view(cat[s], 2 * f / 8, f / 8, f / 8, s);
+      else if (fuse) { dst = view(raw[s][raw_flip & 1], f / 8, 0, f / 8, s); ++raw_flip; }
+      else dst = last ? view(outb[s], f / 8, 0, f / 8, s) : view(mid[s][i & 1], f / 8, 0, f / 8, s);
       __half* s2d_out = (last && s < n - 1) ? s2d[s] : nullptr;
       char name[64];
       snprintf(name, sizeof(name), "encoder.stages.%d.0.convs.%d", s, i);
-      ConvStep* producer = i > 0 ? &L.steps.back() : nullptr;
-      if (int r = add_conv(name, cur, i == 0 ? cur_s2d : ActView(), cur_c, f, a.kernels[s], stride, s, dst, s2d_out,
-                           producer))
+      if (int r = add_conv(name, cur, i == 0 ? cur_s2d : ActView(), cur_c, f, a.kernels[s], stride, s, dst, s2d_out))
         return r;
-      cur = dst;
+      ConvStep& st = L.steps.back();
+      if (fuse && last && s < n - 1) {  // skip producer: its scale / shift also fill the concat's combined table
+        st.d_scale2 = comb_scale[s]; st.d_shift2 = comb_shift[s]; st.stride2 = 2 * f; st.off2 = f;
+      }
+      cur = feed_of_last(dst);
       cur_c = f;
       cur_s2d = ActView();
-      if (s2d_out) {
+      // the copy exists when a pass (unfused) or a tensor-core epilogue (fused) writes it
+      if (s2d_out && (fuse ? st.out_s2d != nullptr : true)) {
         cur_s2d.base = s2d_out; cur_s2d.groups_total = f; cur_s2d.group_off = 0; cur_s2d.groups = f;  // 8 * f/8
         cur_s2d.D = dims[s][0] / 2; cur_s2d.H = dims[s][1] / 2; cur_s2d.W = dims[s][2] / 2;
       }
@@ -566,8 +610,9 @@ static int build_lane(boa_net* net, int li) {
     up.name = name;
     up.cin = cb; up.cout = f;
     for (int k = 0; k < 3; ++k) up.stride[k] = st3[k];
-    up.src = cur;
-    up.dst = view(cat[s], 2 * f / 8, 0, f / 8, s);
+    up.src = cur.view;
+    up.xf = cur.xf;
+    up.out = view(cat[s], 2 * f / 8, 0, f / 8, s);
     const size_t nph = (size_t)st3[0] * st3[1] * st3[2];
     const HostTensor *w, *bi;
     if (int r = need(net, up.name + ".weight", &w, (size_t)cb * f * nph)) return r;
@@ -580,21 +625,30 @@ static int build_lane(boa_net* net, int li) {
     macs += up.macs;
     up.kind = STEP_TCONV_SIMT;
     if (is3(st3, 2) && cb % 16 == 0 && (8 * f) % 64 == 0) {
-      up.taps = conv_taps_plan_create(TAPS_TCONV2, wr.data(), bi->data.data(), cb, f, cur, B, up.dst, nullptr);
+      ConvIO io;
+      io.out = up.out;
+      io.xf = cur.xf;
+      up.taps = conv_taps_plan_create(TAPS_TCONV2, wr.data(), bi->data.data(), cb, f, cur.view, B, io, nullptr);
       if (!up.taps) return BOA_ERR_CUDA;
       up.kind = STEP_TCONV_TAPS;
     }
     L.steps.push_back(up);
-    cur = view(cat[s], 2 * f / 8, 0, 2 * f / 8, s);
+    cur = Feed();
+    cur.view = view(cat[s], 2 * f / 8, 0, 2 * f / 8, s);
+    if (fuse) {
+      cur.xf.scale = comb_scale[s]; cur.xf.shift = comb_shift[s]; cur.xf.channels = 2 * f;
+      cur.xf.ident_groups = f / 8; cur.xf.slope = a.leaky_slope;
+    }
     cur_c = 2 * f;
     for (int i = 0; i < a.n_conv_dec[j]; ++i) {
       const bool last = i == a.n_conv_dec[j] - 1;
       const int one[3] = {1, 1, 1};
-      ActView dst = last ? view(outb[s], f / 8, 0, f / 8, s) : view(mid[s][i & 1], f / 8, 0, f / 8, s);
+      ActView dst;
+      if (fuse) { dst = view(raw[s][raw_flip & 1], f / 8, 0, f / 8, s); ++raw_flip; }
+      else dst = last ? view(outb[s], f / 8, 0, f / 8, s) : view(mid[s][i & 1], f / 8, 0, f / 8, s);
       snprintf(name, sizeof(name), "decoder.stages.%d.convs.%d", j, i);
-      ConvStep* producer = i > 0 ? &L.steps.back() : nullptr;
-      if (int r = add_conv(name, cur, ActView(), cur_c, f, a.kernels[s], one, s, dst, nullptr, producer)) return r;
-      cur = dst;
+      if (int r = add_conv(name, cur, ActView(), cur_c, f, a.kernels[s], one, s, dst, nullptr)) return r;
+      cur = feed_of_last(dst);
       cur_c = f;
     }
   }
@@ -608,12 +662,14 @@ static int build_lane(boa_net* net, int li) {
     net->d_head_w = upload(net, std::string(name) + ".weight", round_fp16(w->data));
     net->d_head_b = upload(net, std::string(name) + ".bias", bi->data);
     if (!net->d_head_w || !net->d_head_b) return BOA_ERR_CUDA;
-    L.head_src = cur;
+    L.head_src = cur.view;
     ConvStep& last = L.steps.back();
-    if (!last.is_tconv && last.cout == a.features[0] && getenv("BOA_B200_NO_FUSE_HEAD") == nullptr) {
-      L.head_src_raw = last.raw_view;
+    BOA_REQUIRE(!last.is_tconv && last.cout == a.features[0], "boa_net_finalize: the decoder must end with a conv block");
+    if (fuse || getenv("BOA_B200_NO_FUSE_HEAD") == nullptr) {
+      // the head normalises the raw output of the last conv itself (free: it is HBM bound)
+      L.head_src_raw = last.out;
       L.head_scale = last.d_scale; L.head_shift = last.d_shift;
-      last.norm_fused_downstream = true;
+      last.norm_pass = false;
     }
     macs += (double)a.num_classes * a.features[0] * vox(0);
   }

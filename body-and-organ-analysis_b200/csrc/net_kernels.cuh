@@ -7,6 +7,7 @@
 // adjacent sub-tensors.
 #pragma once
 #include "common.cuh"
+#include "conv_xform.cuh"
 
 namespace boa {
 
@@ -47,8 +48,10 @@ int launch_conv_first(const __half* d_in, int B, const float* d_w, const float* 
                       int D, int H, int W, double* d_stats, cudaStream_t s);
 int launch_pack_patches(const float* d_patches, int n, int cin, int p0, int p1, int p2, __half* d_out_c8,
                         int groups, cudaStream_t s);
+// d_scale2 / d_shift2 (optional): second copy at [b * stride2 + off2 + c] (rows of a concat's combined table).
 int launch_stats_finalize(const double* d_stats, const float* d_gamma, const float* d_beta, int B, int C,
-                          double n_vox, float eps, float* d_scale, float* d_shift, cudaStream_t s);
+                          double n_vox, float eps, float* d_scale, float* d_shift, cudaStream_t s,
+                          float* d_scale2 = nullptr, float* d_shift2 = nullptr, int stride2 = 0, int off2 = 0);
 // y = lrelu(x * scale + shift) -> fp16, written to dst view and (optionally) to a space-to-depth copy
 // [B][8 phases][groups][D/2][H/2][W/2][8] (phase = (z&1)*4 + (y&1)*2 + (x&1)) that turns the next stage's stride-2
 // convolution into a stride-1 one.
@@ -56,12 +59,13 @@ int launch_norm_lrelu(const __half* d_raw, int B, int groups, int D, int H, int 
                       const float* d_shift, float slope, const ActView& dst, __half* d_s2d, cudaStream_t s);
 // SIMT direct convolution (anisotropic kernels / strides, and the on-device cross-check of the tensor-core kernels).
 // w: fp32 [Cout][cin_w][kz][ky][kx], already rounded to fp16 precision.
+// xf: fused normalisation of the input (the source holds RAW producer output), see conv_xform.cuh.
 int launch_conv_simt(const ActView& src, int B, const float* d_w, const float* d_bias, int cin_w, int Cout,
-                     const int* ks, const int* stride, __half* d_raw_out, int Do, int Ho, int Wo, double* d_stats,
-                     cudaStream_t s);
+                     const int* ks, const int* stride, const ActView& out, int Do, int Ho, int Wo, double* d_stats,
+                     cudaStream_t s, const InXform& xf = InXform());
 // ConvTranspose3d kernel = stride: w fp32 [Cin][Cout][sz][sy][sx]; writes fp16 into dst view.
 int launch_tconv_simt(const ActView& src, int B, const float* d_w, const float* d_bias, int Cin, int Cout,
-                      const int* stride, const ActView& dst, cudaStream_t s);
+                      const int* stride, const ActView& dst, cudaStream_t s, const InXform& xf = InXform());
 // 1x1x1 head. If d_logits_b != nullptr: write raw logits fp32 [C][P] of batch item b. Else accumulate logits*g into
 // the volume accumulator at the origin of batch item b (skipped when b >= call->n_valid); one launch per patch keeps
 // the reference's patch order (predict_from_raw_data.py:603-616).
@@ -70,12 +74,20 @@ int launch_tconv_simt(const ActView& src, int B, const float* d_w, const float* 
 int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias, int Cin, int C, float* d_logits_b,
                 const FwdCall* d_call, const float* d_in_scale, const float* d_in_shift, float slope, cudaStream_t s);
 
+// Where a conv kernel writes and how it reads: the RAW output goes to `out` (a dense tensor or a channel-group slice
+// of a decoder concat buffer) and optionally also to a space-to-depth copy for the next stage's stride-2 conv; `xf`
+// describes the normalisation the kernel applies to its INPUT on the fly (conv_xform.cuh).
+struct ConvIO {
+  ActView out;
+  __half* s2d = nullptr;
+  InXform xf;
+};
+
 // ---- tcgen05 implicit GEMM, 3x3x3 stride 1 with the dz taps folded into N (conv_mma.cu)
 struct ConvMmaPlan;
 ConvMmaPlan* conv_mma_plan_create(const float* h_w /*[Cout][Cin_w][27] fp32*/, const float* h_bias, int cin_w,
-                                  int cin_padded, int Cout, const ActView& src, int B, __half* d_raw_out,
-                                  double* d_stats, bool taps_on_k = false, const float* d_in_scale = nullptr,
-                                  const float* d_in_shift = nullptr, float slope = 0.01f);
+                                  int cin_padded, int Cout, const ActView& src, int B, const ConvIO& io,
+                                  double* d_stats, bool taps_on_k = false);
 void conv_mma_plan_destroy(ConvMmaPlan* p);
 // nb: batch items to process (<= the B the plan was created with; the tensors keep their [B]-strided layout)
 int conv_mma_launch(ConvMmaPlan* p, cudaStream_t s, int nb = -1);
@@ -88,7 +100,7 @@ enum TapsKind { TAPS_CONV3_S1 = 0, TAPS_CONV3_S2 = 1, TAPS_TCONV2 = 2 };
 // TAPS_CONV3_S2: h_w [Cout][cin_w][27], src = s2d view (8*groups);   out = raw at src dims,           stats.
 // TAPS_TCONV2:   h_w [Cin][Cout][8],    src = activation view;       out = dst view at 2x dims (bias, no stats).
 ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float* h_bias, int cin_w, int Cout,
-                                    const ActView& src, int B, const ActView& dst, double* d_stats);
+                                    const ActView& src, int B, const ConvIO& io, double* d_stats);
 void conv_taps_plan_destroy(ConvTapsPlan* p);
 int conv_taps_launch(ConvTapsPlan* p, cudaStream_t s, int nb = -1);
 

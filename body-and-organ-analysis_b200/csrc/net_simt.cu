@@ -239,9 +239,12 @@ pack_patches_kernel(const float* __restrict__ in, int n, int cin, size_t pv, int
 // ------------------------------------------------------------------------------------------ InstanceNorm finalise
 // nn.InstanceNorm3d(eps, affine=True): biased variance over D*H*W per (sample, channel) (plans_handler.py:72-76).
 // scale = gamma * rstd ; shift = beta - mean * gamma * rstd   (fp64 internally)
+// scale2 / shift2 (optional): a second copy at [b * stride2 + off2 + c] - the rows of a decoder concat's combined
+// scale / shift table that belong to this (skip) producer.
 __global__ void stats_finalize_kernel(const double* __restrict__ stats, const float* __restrict__ gamma,
                                       const float* __restrict__ beta, int B, int C, double n_vox, float eps,
-                                      float* __restrict__ scale, float* __restrict__ shift) {
+                                      float* __restrict__ scale, float* __restrict__ shift,
+                                      float* __restrict__ scale2, float* __restrict__ shift2, int stride2, int off2) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * C) return;
   const int c = i % C;
@@ -250,8 +253,14 @@ __global__ void stats_finalize_kernel(const double* __restrict__ stats, const fl
   if (var < 0) var = 0;
   const double rstd = 1.0 / sqrt(var + (double)eps);
   const double g = gamma[c];
-  scale[i] = (float)(g * rstd);
-  shift[i] = (float)((double)beta[c] - mean * g * rstd);
+  const float sc = (float)(g * rstd), sh = (float)((double)beta[c] - mean * g * rstd);
+  scale[i] = sc;
+  shift[i] = sh;
+  if (scale2) {
+    const int j = (i / C) * stride2 + off2 + c;
+    scale2[j] = sc;
+    shift2[j] = sh;
+  }
 }
 
 // ------------------------------------------------------------------------------------------ normalise + LeakyReLU
@@ -371,7 +380,8 @@ struct Int3 { int z, y, x; };
 __global__ void __launch_bounds__(128)
 conv_simt_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off, int Di, int Hi, int Wi,
                  const float* __restrict__ w, const float* __restrict__ bias, int cin_w, int Cout, Int3 ks,
-                 Int3 stride, uint4* __restrict__ out, int Do, int Ho, int Wo, double* __restrict__ stats, int B) {
+                 Int3 stride, uint4* __restrict__ out, int out_groups_total, int out_group_off, int Do, int Ho, int Wo,
+                 double* __restrict__ stats, int B, InXform xf) {
   const size_t ovox = (size_t)Do * Ho * Wo;
   const int ogroups = Cout / 8;
   const size_t total = (size_t)B * ogroups * ovox;
@@ -395,7 +405,17 @@ conv_simt_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group
     const size_t iv = ((size_t)zi * Hi + yi) * Wi + xi;
     for (int g = 0; g * 8 < cin_w; ++g) {
       float f[8];
-      unpack8(__ldg(in + ((size_t)b * in_groups_total + in_group_off + g) * ivox + iv), f);
+      uint4 raw = __ldg(in + ((size_t)b * in_groups_total + in_group_off + g) * ivox + iv);
+      if (xf.scale && g >= xf.ident_groups) {  // RAW producer output: its InstanceNorm affine + LeakyReLU on the fly
+        float a[8], sh[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          a[e] = __ldg(xf.scale + (size_t)b * xf.channels + g * 8 + e);
+          sh[e] = __ldg(xf.shift + (size_t)b * xf.channels + g * 8 + e);
+        }
+        raw = xform8(raw, a, sh, xf.slope);
+      }
+      unpack8(raw, f);
 #pragma unroll
       for (int e = 0; e < 8; ++e) {
         const int ci = g * 8 + e;
@@ -408,7 +428,7 @@ conv_simt_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group
   }
 #pragma unroll
   for (int o = 0; o < 8; ++o) acc[o] += bias[og * 8 + o];
-  if (active) out[ii] = pack8(acc);
+  if (active) out[((size_t)b * out_groups_total + out_group_off + og) * ovox + v] = pack8(acc);
   if (stats) {
     // whole warp in the same (b, og)?  then shuffle-reduce, else per-thread atomics
     const unsigned key = (unsigned)(b * ogroups + og);
@@ -437,7 +457,7 @@ conv_simt_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group
 __global__ void __launch_bounds__(128)
 tconv_simt_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off, int Di, int Hi, int Wi,
                   const float* __restrict__ w, const float* __restrict__ bias, int Cin, int Cout, Int3 st,
-                  uint4* __restrict__ out, int out_groups_total, int out_group_off, int B) {
+                  uint4* __restrict__ out, int out_groups_total, int out_group_off, int B, InXform xf) {
   const int Do = st.z * Di, Ho = st.y * Hi, Wo = st.x * Wi;
   const size_t ovox = (size_t)Do * Ho * Wo, ivox = (size_t)Di * Hi * Wi;
   const int ogroups = Cout / 8;
@@ -456,7 +476,17 @@ tconv_simt_kernel(const uint4* __restrict__ in, int in_groups_total, int in_grou
   for (int o = 0; o < 8; ++o) acc[o] = 0.f;
   for (int g = 0; g < Cin / 8; ++g) {
     float f[8];
-    unpack8(__ldg(in + ((size_t)b * in_groups_total + in_group_off + g) * ivox + iv), f);
+    uint4 raw = __ldg(in + ((size_t)b * in_groups_total + in_group_off + g) * ivox + iv);
+    if (xf.scale && g >= xf.ident_groups) {
+      float a[8], sh[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) {
+        a[e] = __ldg(xf.scale + (size_t)b * xf.channels + g * 8 + e);
+        sh[e] = __ldg(xf.shift + (size_t)b * xf.channels + g * 8 + e);
+      }
+      raw = xform8(raw, a, sh, xf.slope);
+    }
+    unpack8(raw, f);
 #pragma unroll
     for (int e = 0; e < 8; ++e)
 #pragma unroll
@@ -576,8 +606,18 @@ __device__ __forceinline__ void mma_m16n8k16(float (&d)[4], uint32_t a0, uint32_
                : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 
-template <int NT>  // n-tiles of 8 classes: C <= 8 * NT
-__global__ void __launch_bounds__(128, 4)
+// red.global.add.f32: round-to-nearest fp32 addition executed by the L2 (subnormal operands / results are flushed to
+// zero - |logit * gaussian| would have to be below 1.2e-38, the Gaussian's minimum is 6e-8).
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(__cvta_generic_to_global(p)), "f"(v) : "memory");
+}
+
+// RED: the accumulation `logits[v] += pred * g` is issued as a reduction (red.global.add.f32, executed by the L2) instead
+// of a load + add + store in the SM: the same IEEE fp32 addition on the same operands - every address is touched once
+// per launch and launches are stream ordered, so the result is bit-identical - but no accumulator value travels to
+// the SM and back, and the 8 * NT registers of loads in flight per thread are gone.
+template <int NT, bool RED>  // n-tiles of 8 classes: C <= 8 * NT
+__global__ void __launch_bounds__(128, RED ? 6 : 4)
 head_mma_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off, int b, int D, int H, int W,
                 const float* __restrict__ w, const float* __restrict__ bias, int C, float* __restrict__ logits_b,
                 const FwdCall* __restrict__ call, const float* __restrict__ in_scale,
@@ -629,7 +669,7 @@ head_mma_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_
     const bool ok = v < vox;
     float* dst = nullptr;
     float gw = 0.f;
-    float old[8 * NT];
+    float old[RED ? 1 : 8 * NT];
     if (ok) {
       if (logits_b) {
         dst = logits_b + v;
@@ -637,9 +677,11 @@ head_mma_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_
         const int k = v % W, j = (v / W) % H, ii = v / (W * H);
         dst = acc + ((size_t)(o0 + ii) * d1 + (o1 + j)) * d2 + (o2 + k);
         gw = __ldg(gauss + v);
+        if constexpr (!RED) {
 #pragma unroll
-        for (int c = 0; c < 8 * NT; ++c)
-          if (c < C) old[c] = __ldcg(dst + (size_t)c * cstride);
+          for (int c = 0; c < 8 * NT; ++c)
+            if (c < C) old[c] = __ldcg(dst + (size_t)c * cstride);
+        }
       }
     }
     // ---- this thread as an MMA lane: rows v0 + g + 8 i, i = 0..3 (m-tile i / 2, upper half i & 1), channel group t
@@ -688,6 +730,7 @@ head_mma_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_
         if (c < C) {
           const float sres = tb[c][lane] + sbias[c];
           if (logits_b) dst[(size_t)c * cstride] = sres;
+          else if constexpr (RED) red_add_f32(dst + (size_t)c * cstride, __fmul_rn(sres, gw));
           else __stcg(dst + (size_t)c * cstride, __fadd_rn(old[c], __fmul_rn(sres, gw)));
         }
       }
@@ -765,10 +808,11 @@ int launch_pack_patches(const float* d_patches, int n, int cin, int p0, int p1, 
 }
 
 int launch_stats_finalize(const double* d_stats, const float* d_gamma, const float* d_beta, int B, int C,
-                          double n_vox, float eps, float* d_scale, float* d_shift, cudaStream_t s) {
+                          double n_vox, float eps, float* d_scale, float* d_shift, cudaStream_t s, float* d_scale2,
+                          float* d_shift2, int stride2, int off2) {
   BOA_CARVEOUT_ONCE(stats_finalize_kernel);
   stats_finalize_kernel<<<(B * C + 127) / 128, 128, 0, s>>>(d_stats, d_gamma, d_beta, B, C, n_vox, eps, d_scale,
-                                                            d_shift);
+                                                            d_shift, d_scale2, d_shift2, stride2, off2);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }
@@ -801,24 +845,24 @@ int launch_norm_lrelu(const __half* d_raw, int B, int groups, int D, int H, int 
 }
 
 int launch_conv_simt(const ActView& src, int B, const float* d_w, const float* d_bias, int cin_w, int Cout,
-                     const int* ks, const int* stride, __half* d_raw_out, int Do, int Ho, int Wo, double* d_stats,
-                     cudaStream_t s) {
+                     const int* ks, const int* stride, const ActView& out, int Do, int Ho, int Wo, double* d_stats,
+                     cudaStream_t s, const InXform& xf) {
   const size_t total = (size_t)B * (Cout / 8) * Do * Ho * Wo;
   conv_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
       reinterpret_cast<const uint4*>(src.base), src.groups_total, src.group_off, src.D, src.H, src.W, d_w, d_bias,
       cin_w, Cout, Int3{ks[0], ks[1], ks[2]}, Int3{stride[0], stride[1], stride[2]},
-      reinterpret_cast<uint4*>(d_raw_out), Do, Ho, Wo, d_stats, B);
+      reinterpret_cast<uint4*>(out.base), out.groups_total, out.group_off, Do, Ho, Wo, d_stats, B, xf);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }
 
 int launch_tconv_simt(const ActView& src, int B, const float* d_w, const float* d_bias, int Cin, int Cout,
-                      const int* stride, const ActView& dst, cudaStream_t s) {
+                      const int* stride, const ActView& dst, cudaStream_t s, const InXform& xf) {
   const size_t total = (size_t)B * (Cout / 8) * dst.voxels();
   tconv_simt_kernel<<<(unsigned)((total + 127) / 128), 128, 0, s>>>(
       reinterpret_cast<const uint4*>(src.base), src.groups_total, src.group_off, src.D, src.H, src.W, d_w, d_bias, Cin,
       Cout, Int3{stride[0], stride[1], stride[2]}, reinterpret_cast<uint4*>(dst.base), dst.groups_total,
-      dst.group_off, B);
+      dst.group_off, B, xf);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }
@@ -832,13 +876,21 @@ int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias
   const size_t vox = src.voxels();
   if (Cin == 32 && C <= 32 && head_on_mma()) {
     const int nt = (C + 7) / 8;
-    // four blocks of 128 threads per SM (<= 128 registers), each thread with up to 8 * NT + 5 loads in flight
-    const int grid = (int)std::min<size_t>((vox + 127) / 128, (size_t)sm_count() * 4);
+    // BOA_B200_HEAD_RMW=1: load + add + store in the SM (four blocks of 128 threads per SM, up to 8 * NT + 5 loads in
+    // flight per thread) instead of the L2 reduction (six blocks per SM)
+    static const bool red = !(getenv("BOA_B200_HEAD_RMW") && atoi(getenv("BOA_B200_HEAD_RMW")) != 0);
+    const int grid = (int)std::min<size_t>((vox + 127) / 128, (size_t)sm_count() * (red ? 6 : 4));
     const uint4* in4 = reinterpret_cast<const uint4*>(src.base);
 #define BOA_HEAD_MMA(NT_)                                                                                            \
-  BOA_CARVEOUT_ONCE(head_mma_kernel<NT_>);                                                                             \
-  head_mma_kernel<NT_><<<grid, 128, 0, s>>>(in4, src.groups_total, src.group_off, b, src.D, src.H, src.W, d_w, d_bias, \
-                                            C, d_logits_b, d_call, d_in_scale, d_in_shift, slope)
+  if (red) {                                                                                                           \
+    BOA_CARVEOUT_ONCE((head_mma_kernel<NT_, true>));                                                                   \
+    head_mma_kernel<NT_, true><<<grid, 128, 0, s>>>(in4, src.groups_total, src.group_off, b, src.D, src.H, src.W, d_w, \
+                                                    d_bias, C, d_logits_b, d_call, d_in_scale, d_in_shift, slope);     \
+  } else {                                                                                                             \
+    BOA_CARVEOUT_ONCE((head_mma_kernel<NT_, false>));                                                                  \
+    head_mma_kernel<NT_, false><<<grid, 128, 0, s>>>(in4, src.groups_total, src.group_off, b, src.D, src.H, src.W, d_w, \
+                                                     d_bias, C, d_logits_b, d_call, d_in_scale, d_in_shift, slope);    \
+  }
     switch (nt) {
       case 1: BOA_HEAD_MMA(1); break;
       case 2: BOA_HEAD_MMA(2); break;

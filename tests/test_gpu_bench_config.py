@@ -11,7 +11,8 @@ same computation:
 The bar: the north star's "logits within 1e-3 rel" cannot be met by ANY fp16 pipeline of this depth
 against another - so the asserted bar is (a) rel-L2 to the fp16-emulating oracle <= 2.5e-3, (b) our distance to the
 fp32 truth is no larger than the reference GPU path's own distance to it, (c) label maps equal to the fp32 truth's on
-every voxel whose top-2 margin exceeds the fp16 noise, with per-label Dice reported.
+every voxel whose top-2 margin exceeds 8 sigma of the reference GPU path's own logit noise, and per-label Dice no
+worse than the reference GPU path's.
 """
 import numpy as np
 import pytest
@@ -26,7 +27,8 @@ from oracle import passes as op
 from oracle.sliding_window import predict_sliding_window_return_logits, sliding_window_slicers
 
 TOL_EMULATED = 2.5e-3   # two correct fp16 pipelines of this depth, different summation orders
-MARGIN = 0.05           # top-2 logit margin above which fp16 noise cannot flip the argmax
+MARGIN_SIGMAS = 8.0     # a voxel is "safe" when its top-2 margin (fp32 truth) exceeds this many sigmas of the
+                        # reference GPU path's own logit noise: no correct fp16 pipeline may flip it
 
 
 def _rel(a, b):
@@ -81,7 +83,11 @@ def test_benchmarked_configuration_against_three_references(cuda, bench_case):
     rel_emul, rel32, rel32_ref = _rel(ours, emul), _rel(ours, truth), _rel(ref_gpu, truth)
     lab_truth, lab_ref = truth.argmax(0), ref_gpu.argmax(0)
     top2 = np.sort(truth, axis=0)[-2:]
-    safe = (top2[1] - top2[0]) > MARGIN
+    noise = float(np.sqrt(np.mean((ref_gpu - truth) ** 2)))   # per-logit noise of the reference's own fp16 path
+    margin = MARGIN_SIGMAS * noise
+    safe = (top2[1] - top2[0]) > margin
+    flips, flips_ref = labels != lab_truth, lab_ref != lab_truth
+    m = top2[1] - top2[0]
     agree, agree_ref = float((labels == lab_truth).mean()), float((lab_ref == lab_truth).mean())
     dice, dice_ref = _dice_per_label(labels, lab_truth, 25), _dice_per_label(lab_ref, lab_truth, 25)
     print(f"\nbench configuration (12 patches of 128^3, batch 8, two lanes, C = 25):\n"
@@ -91,11 +97,14 @@ def test_benchmarked_configuration_against_three_references(cuda, bench_case):
           f"  label agreement with the fp32 truth: ours {agree:.6f}, reference GPU path {agree_ref:.6f}\n"
           f"  per-label Dice vs truth: ours min {min(dice):.5f} mean {np.mean(dice):.5f}; "
           f"reference GPU path min {min(dice_ref):.5f} mean {np.mean(dice_ref):.5f}\n"
-          f"  voxels with top-2 margin > {MARGIN}: {safe.mean():.4f} of the volume")
+          f"  reference-path logit noise (rms) {noise:.4f}; voxels with top-2 margin > {MARGIN_SIGMAS:g} sigma = "
+          f"{margin:.3f}: {safe.mean():.4f} of the volume\n"
+          f"  largest margin of a flipped voxel: ours {m[flips].max() if flips.any() else 0:.4f}, "
+          f"reference GPU path {m[flips_ref].max() if flips_ref.any() else 0:.4f}")
     assert np.isfinite(ours).all()
     assert rel_emul <= TOL_EMULATED
     assert rel32 <= rel32_ref * 1.02, "further from the fp32 truth than the reference's own GPU path"
     assert agree >= agree_ref - 1e-4
     assert np.array_equal(labels[safe], lab_truth[safe]), "label flip on a voxel whose margin exceeds the fp16 noise"
-    assert min(dice) > 0.99
+    assert min(dice) >= min(dice_ref) - 2e-3 and np.mean(dice) >= np.mean(dice_ref) - 1e-3
     pred.networks[0].close()

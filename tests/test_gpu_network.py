@@ -78,22 +78,29 @@ def test_totalseg_geometry_one_patch(cuda):
 
 
 def test_fused_input_normalisation_is_bit_identical(cuda, monkeypatch):
-    """conv3_fold_ldnorm_kernel (the conv1 layers with 32 outputs read the RAW output of conv0 and normalise it on the
-    global -> shared path) against the unfused schedule (standalone normalise pass): same fp32 operations, so the
-    logits must be identical bit for bit - also for a partial batch and a volume that is not a multiple of the tile."""
-    for patch, n_patches, max_batch in (((32, 32, 32), 3, 2), ((24, 40, 16), 2, 4)):
-        arch = _arch(patch, 32, 128, 3, 5)
+    """Default schedule (every conv / transposed conv / head normalises the RAW output of its producer while staging
+    its operand - conv_xform.cuh - and there is no standalone InstanceNorm + LeakyReLU pass) against the unfused
+    schedule (BOA_B200_UNFUSED=1: one normalise pass per layer, consumers read the normalised copy): same fp32
+    operations on the same values, so the logits must be identical bit for bit - for the fold / stride-2 / transposed
+    kernels, a concat input (identity half + normalised half), a partial batch, a volume that is not a multiple of the
+    tile, and the SIMT kernels."""
+    cases = (((32, 32, 32), 32, 128, 3, 3, 2), ((24, 40, 16), 32, 128, 3, 2, 4), ((64, 64, 64), 32, 320, 5, 2, 2))
+    for patch, base, maxf, stages, n_patches, max_batch in cases:
+        arch = _arch(patch, base, maxf, stages, 5)
         sd = zoo.random_state_dict(arch, 17)
         x = torch.from_numpy(np.random.default_rng(1).standard_normal((n_patches, 1, *patch)).astype(np.float32)).cuda()
-        outs = []
-        for no_fuse in (False, True):
-            if no_fuse:
-                monkeypatch.delenv("BOA_B200_LDNORM", raising=False)
-            else:
-                monkeypatch.setenv("BOA_B200_LDNORM", "1")
-            net = Network(arch, sd, 0, max_batch)
-            net.set_graph(False)
-            outs.append(net.forward_logits(x).cpu().numpy())
-            net.close()
-        assert np.isfinite(outs[0]).all()
-        assert np.array_equal(outs[0], outs[1]), np.abs(outs[0] - outs[1]).max()
+        for mode in (0, 1):
+            outs = []
+            for unfused in (False, True):
+                if unfused:
+                    monkeypatch.setenv("BOA_B200_UNFUSED", "1")
+                else:
+                    monkeypatch.delenv("BOA_B200_UNFUSED", raising=False)
+                net = Network(arch, sd, 0, max_batch)
+                net.set_graph(False)
+                net.set_mode(mode)
+                outs.append(net.forward_logits(x).cpu().numpy())
+                net.close()
+            assert np.isfinite(outs[0]).all()
+            assert np.array_equal(outs[0], outs[1]), (patch, mode, np.abs(outs[0] - outs[1]).max())
+    monkeypatch.delenv("BOA_B200_UNFUSED", raising=False)
