@@ -29,8 +29,10 @@
 
 namespace boa {
 
-constexpr int MMA_THREADS = 384;  // WG0: producer warp + MMA warp (+2 idle), WG1: 4 epilogue warps, WG2: 4 transform warps
-constexpr int REGS_WG0 = 104, REGS_EPI = 248, REGS_XF = 128;  // 128 * (104 + 248 + 128) = 61440 <= 65536 registers
+// WG0: producer warp + MMA warp (+2 idle), WG1: 4 epilogue warps, WG2 + WG3: 8 transform warps.  512 threads start with
+// 128 registers each; the transform warps give theirs to the epilogue: 128 * (128 + 248 + 64 + 64) = 64512 <= 65536.
+constexpr int MMA_THREADS = 512;
+constexpr int REGS_EPI = 248, REGS_XF = 64, XF_THREADS = 256;
 constexpr int TILE_X = 8, TILE_Y = 16;
 constexpr int XB = TILE_X + 2, YB = TILE_Y + 2, SLAB = XB * YB;  // 180 halo positions per z-plane
 
@@ -124,7 +126,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], xform ? 4 : 1);
+      mbar_init(&full[i], xform ? XF_THREADS / 32 : 1);
       mbar_init(&empty[i], 1);
       mbar_init(&rawfull[i], 1);
     }
@@ -146,7 +148,6 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
   const uint32_t tbase = *tmem_slot;
 
   if (warp < 4) {
-    reg_dealloc<REGS_WG0>();
     if (warp == 0) {
       // ===================================================================== TMA producer
       if (p.b_resident && elect_one()) {  // n_ntiles == 1: one weight set for every tile of this CTA
@@ -252,7 +253,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
 #pragma unroll
     for (int chunk = 0; chunk < NC / 32; ++chunk) stats_flush(run[chunk], p.stats, lane);
   } else {
-    // ===================================================================== operand transform (warps 8..11)
+    // ===================================================================== operand transform (warps 8..15)
     reg_dealloc<REGS_XF>();
     if (xform) {
       const int tid = threadIdx.x - 256;
@@ -272,7 +273,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
                            (8 * g0 + 8 >= p.xf.channels ? 2 : 0);
           mbar_wait(&rawfull[st], ph);
           if (skip != 3)
-            xform_stage<XB, YB, 128>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
+            xform_stage<XB, YB, XF_THREADS, 4, 3>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
                                      p.xf.scale + (size_t)b * p.xf.channels + 16 * kc,
                                      p.xf.shift + (size_t)b * p.xf.channels + 16 * kc, skip, p.xf.slope, tid);
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads

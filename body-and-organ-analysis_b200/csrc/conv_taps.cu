@@ -28,8 +28,8 @@
 
 namespace boa {
 
-constexpr int TAPS_THREADS = 384;  // three warpgroups, see conv_mma.cu
-constexpr int TREGS_WG0 = 104, TREGS_EPI = 248, TREGS_XF = 128;
+constexpr int TAPS_THREADS = 512;  // four warpgroups (the last two transform), see conv_mma.cu
+constexpr int TREGS_EPI = 248, TREGS_XF = 64, TXF_THREADS = 256;
 constexpr int TT_X = 8, TT_Y = 16;
 constexpr int TAPS_MAX_OPS = 27;
 constexpr int TAPS_MAX_STAGES = 12;  // smem ring depth: small stages (transposed conv, deep layers) prefetch several tiles ahead
@@ -85,7 +85,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TAPS_MAX_STAGES; ++i) {
-      mbar_init(&full[i], xform ? 4 : 1);
+      mbar_init(&full[i], xform ? TXF_THREADS / 32 : 1);
       mbar_init(&empty[i], 1);
       mbar_init(&rawfull[i], 1);
     }
@@ -107,7 +107,6 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
   const uint32_t buf_cols = (uint32_t)(p.zt * NC);  // <= 256: two accumulator buffers
 
   if (warp < 4) {
-  reg_dealloc<TREGS_WG0>();
   if (warp == 0) {
     // ===================================================================== TMA producer
     uint32_t it = 0;
@@ -203,9 +202,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
             uint8_t* sa = smem + (size_t)st * stage_bytes;
             const float* sc = p.xf.scale + (size_t)b * p.xf.channels + 16 * cc;
             const float* sh = p.xf.shift + (size_t)b * p.xf.channels + 16 * cc;
-            if (p.halo == 2) xform_stage<TT_X + 2, TT_Y + 2, 128>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
-            else if (p.halo == 1) xform_stage<TT_X + 1, TT_Y + 1, 128>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
-            else xform_stage<TT_X, TT_Y, 128>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+            // box_z <= 6: z phases of 2, at most 3 planes per item
+            if (p.halo == 2) xform_stage<TT_X + 2, TT_Y + 2, TXF_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+            else if (p.halo == 1) xform_stage<TT_X + 1, TT_Y + 1, TXF_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+            else xform_stage<TT_X, TT_Y, TXF_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
           }
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
           __syncwarp();

@@ -6,8 +6,8 @@
 // tensor: 18 % of the GPU time and 10 of 26 GB of DRAM traffic per batch in round 1) does not exist.
 //   reference op: dynamic_network_architectures ConvDropoutNormReLU = Conv3d -> InstanceNorm3d(affine) -> LeakyReLU,
 //   kwargs from _external/nnunetv2/utilities/plans_handling/plans_handler.py:72-82.
-// Same fp32 operations as norm_lrelu_kernel (mul, add, LeakyReLU, round to fp16), so the fused and the unfused
-// schedules are bit-identical (tests/test_gpu_network.py).  Positions outside the volume were zero-filled by TMA and
+// Same fp32 operations as norm_lrelu_kernel (fma, LeakyReLU, round to fp16), so the fused and the unfused schedules
+// are bit-identical (tests/test_gpu_network.py).  Positions outside the volume were zero-filled by TMA and
 // must stay zero (the conv pads the ACTIVATED tensor), so only the in-volume part of the halo box is touched.
 // Channel groups that are final already (the transposed-conv half of a decoder concat) are skipped.
 #pragma once
@@ -24,6 +24,9 @@ struct InXform {
   float slope = 0.01f;
 };
 
+// y = lrelu(fma(x, a, s)) for the 8 channels of one voxel.  ONE definition for every kernel that normalises (the
+// tensor-core kernels' transform warps, the SIMT kernels, the head, the standalone pass of the unfused schedule), so
+// that all schedules are bit-identical.  slope < 1: lrelu(z) = max(z, z * slope).
 __device__ __forceinline__ uint4 xform8(const uint4& raw, const float (&a)[8], const float (&sh)[8], float slope) {
   uint4 o;
   const __half2* h = reinterpret_cast<const __half2*>(&raw);
@@ -31,10 +34,10 @@ __device__ __forceinline__ uint4 xform8(const uint4& raw, const float (&a)[8], c
 #pragma unroll
   for (int e = 0; e < 4; ++e) {
     float2 f = __half22float2(h[e]);
-    f.x = __fadd_rn(__fmul_rn(f.x, a[2 * e]), sh[2 * e]);
-    f.y = __fadd_rn(__fmul_rn(f.y, a[2 * e + 1]), sh[2 * e + 1]);
-    f.x = f.x > 0.f ? f.x : __fmul_rn(f.x, slope);
-    f.y = f.y > 0.f ? f.y : __fmul_rn(f.y, slope);
+    f.x = fmaf(f.x, a[2 * e], sh[2 * e]);
+    f.y = fmaf(f.y, a[2 * e + 1], sh[2 * e + 1]);
+    f.x = fmaxf(f.x, __fmul_rn(f.x, slope));
+    f.y = fmaxf(f.y, __fmul_rn(f.y, slope));
     r[e] = __floats2half2_rn(f.x, f.y);
   }
   return o;
@@ -43,7 +46,9 @@ __device__ __forceinline__ uint4 xform8(const uint4& raw, const float (&a)[8], c
 // One operand stage: 2 channel groups x [bz][BY][BX] positions x 16 bytes, in place.  Called by NT threads (tid).
 // [zlo,zhi) x [ylo,yhi) x [xlo,xhi): in-volume part of the box.  sc / sh: scale / shift of the 16 channels of this
 // K chunk for this batch item.  skip: bit g set = group g is final (or does not exist).
-template <int BX, int BY, int NT>
+// Work items are (z phase of ZS, in-plane position): a thread's (y, x) is fixed per item, so the bounds test and the
+// index arithmetic happen once per item and the planes of an item are loaded together before they are transformed.
+template <int BX, int BY, int NT, int ZS, int MAXP>
 __device__ __forceinline__ void xform_stage(uint8_t* sa, int bz, int zlo, int zhi, int ylo, int yhi, int xlo, int xhi,
                                             const float* __restrict__ sc, const float* __restrict__ sh, int skip,
                                             float slope, int tid) {
@@ -60,10 +65,19 @@ __device__ __forceinline__ void xform_stage(uint8_t* sa, int bz, int zlo, int zh
       s[0] = s0.x; s[1] = s0.y; s[2] = s0.z; s[3] = s0.w; s[4] = s1.x; s[5] = s1.y; s[6] = s1.z; s[7] = s1.w;
     }
     uint4* t = reinterpret_cast<uint4*>(sa) + g * per_group;
-#pragma unroll 4
-    for (int e = tid; e < per_group; e += NT) {
-      const int z = e / SL, r = e - z * SL, y = r / BX, x = r - y * BX;
-      if (z >= zlo && z < zhi && y >= ylo && y < yhi && x >= xlo && x < xhi) t[e] = xform8(t[e], a, s, slope);
+#pragma unroll 1
+    for (int it = tid; it < ZS * SL; it += NT) {
+      const int zp = it / SL, r = it - zp * SL, y = r / BX, x = r - y * BX;
+      if (y < ylo || y >= yhi || x < xlo || x >= xhi) continue;
+      // planes zlo <= z < zhi with z % ZS == zp
+      int z = zlo + ((zp - zlo) % ZS + ZS) % ZS;
+      uint4 v[MAXP];
+#pragma unroll
+      for (int k = 0; k < MAXP; ++k)
+        if (z + k * ZS < zhi) v[k] = t[(z + k * ZS) * SL + r];
+#pragma unroll
+      for (int k = 0; k < MAXP; ++k)
+        if (z + k * ZS < zhi) t[(z + k * ZS) * SL + r] = xform8(v[k], a, s, slope);
     }
   }
 }

@@ -295,14 +295,7 @@ norm_lrelu_kernel(const uint4* __restrict__ raw, int groups, int D, int H, int W
     for (int u = 0; u < U; ++u) {
       const size_t v = v0 + u * stride;
       if (v >= vox) break;
-      float f[8];
-      unpack8(r[u], f);
-#pragma unroll
-      for (int e = 0; e < 8; ++e) {
-        const float z = __fadd_rn(__fmul_rn(f[e], a[e]), sh[e]);
-        f[e] = z > 0.f ? z : __fmul_rn(z, slope);
-      }
-      const uint4 o = pack8(f);
+      const uint4 o = xform8(r[u], a, sh, slope);
       if (out) out[v] = o;
       if (out2) {
         const int x = (int)(v % W), y = (int)((v / W) % H), z = (int)(v / ((size_t)W * H));
@@ -352,14 +345,10 @@ norm_lrelu_thin_kernel(const uint4* __restrict__ raw, int planes, int groups, in
 #pragma unroll
     for (int u = 0; u < THIN_U; ++u) {
       if (u * 256 < nrem) {
-        float f[8];
-        unpack8(r[u], f);
+        float a[8], sh[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float z = __fadd_rn(__fmul_rn(f[e], wsl[e]), wsl[8 + e]);
-          f[e] = z > 0.f ? z : __fmul_rn(z, slope);
-        }
-        const uint4 o = pack8(f);
+        for (int e = 0; e < 8; ++e) { a[e] = wsl[e]; sh[e] = wsl[8 + e]; }
+        const uint4 o = xform8(r[u], a, sh, slope);
         if (out) out[u * 256] = o;
         if (out2) {
           const int v = vbase + u * 256;
@@ -547,8 +536,8 @@ head_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_off,
       // rounding the standalone pass would have stored (same operations as norm_lrelu_kernel)
 #pragma unroll
       for (int c = 0; c < CIN; ++c) {
-        const float z = __fadd_rn(__fmul_rn(x[c], ssc[c]), ssh[c]);
-        x[c] = __half2float(__float2half_rn(z > 0.f ? z : __fmul_rn(z, slope)));
+        const float z = fmaf(x[c], ssc[c], ssh[c]);
+        x[c] = __half2float(__float2half_rn(fmaxf(z, __fmul_rn(z, slope))));
       }
     }
     float* a = nullptr;
@@ -694,14 +683,10 @@ head_mma_kernel(const uint4* __restrict__ in, int in_groups_total, int in_group_
       if (in_scale) {
         // RAW output of the last conv: its InstanceNorm affine + LeakyReLU and the fp16 rounding of the standalone
         // pass (same operations as norm_lrelu_kernel)
-        float f[8];
-        unpack8(raw, f);
+        float a8[8], s8[8];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const float z = __fadd_rn(__fmul_rn(f[e], sc[e]), sh[e]);
-          f[e] = z > 0.f ? z : __fmul_rn(z, slope);
-        }
-        raw = pack8(f);
+        for (int e = 0; e < 8; ++e) { a8[e] = sc[e]; s8[e] = sh[e]; }
+        raw = xform8(raw, a8, s8, slope);
       }
       a[i][0] = raw.x; a[i][1] = raw.y; a[i][2] = raw.z; a[i][3] = raw.w;
     }

@@ -81,12 +81,60 @@ struct Lut256 {
   uint8_t v[256];
 };
 
+// Where the accumulated logits of a voxel come from.
+// LocalSrc: one accumulator [C][V] in this GPU's memory.
+struct LocalSrc {
+  const float* acc;
+  size_t V;
+  template <int VEC>
+  __device__ __forceinline__ void load(int c, size_t v0, float (&x)[VEC]) const {
+    if constexpr (VEC == 4) {
+      const float4 t = __ldcs(reinterpret_cast<const float4*>(acc + (size_t)c * V + v0));
+      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
+    } else {
+      x[0] = __ldcs(acc + (size_t)c * V + v0);
+    }
+  }
+};
+// PeerSrc (multi-GPU, dist.py): rank r holds the partial sums of ITS patches in a private buffer
+// [C][zhi[r] - zlo[r]][Y][X] covering the slices its patches touch; the owner of a dim-0 slab reads every rank's part
+// of its slab straight from that rank's memory (NVLink peer loads; base[r] is the IPC-mapped buffer) and adds them in
+// RANK ORDER - the exchange, the reduction and the argmax are one kernel, the summed logits are never stored.
+// v0 is relative to the owner's slab, which starts at absolute slice z0.  VEC == 4 needs plane % 4 == 0.
+constexpr int MAX_PEERS = 8;
+struct PeerSrc {
+  const float* base[MAX_PEERS];
+  int zlo[MAX_PEERS], zhi[MAX_PEERS];
+  int n;
+  int z0;
+  size_t plane;  // Y * X
+  template <int VEC>
+  __device__ __forceinline__ void load(int c, size_t v0, float (&x)[VEC]) const {
+    const int z = z0 + (int)(v0 / plane);
+    const size_t rem = v0 - (size_t)(z - z0) * plane;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) x[k] = 0.f;
+#pragma unroll
+    for (int r = 0; r < MAX_PEERS; ++r) {
+      if (r < n && z >= zlo[r] && z < zhi[r]) {
+        const float* p = base[r] + ((size_t)c * (zhi[r] - zlo[r]) + (z - zlo[r])) * plane + rem;
+        if constexpr (VEC == 4) {
+          const float4 t = __ldcs(reinterpret_cast<const float4*>(p));
+          x[0] = __fadd_rn(x[0], t.x); x[1] = __fadd_rn(x[1], t.y); x[2] = __fadd_rn(x[2], t.z); x[3] = __fadd_rn(x[3], t.w);
+        } else {
+          x[0] = __fadd_rn(x[0], __ldcs(p));
+        }
+      }
+    }
+  }
+};
+
 // predict_from_raw_data.py:620-625 (divide, isinf) ; label_handling.py:178 (argmax(0), first max wins) ;
 // totalsegmentator/nnunet.py:553-556 (part label -> global label, non-zero overwrite)
-template <int VEC>
-__device__ __forceinline__ void argmax_group(const float* __restrict__ acc, const float* __restrict__ wacc, int C,
-                                             size_t V, size_t v0, const Lut256& lut, int overwrite_nz,
-                                             uint8_t* __restrict__ label, int& bad) {
+template <int VEC, typename Src>
+__device__ __forceinline__ void argmax_group(const Src& src, const float* __restrict__ wacc, int C, size_t v0,
+                                             const Lut256& lut, int overwrite_nz, uint8_t* __restrict__ label,
+                                             int& bad) {
   float w[VEC], best[VEC];
   int arg[VEC];
   if constexpr (VEC == 4) {
@@ -99,12 +147,7 @@ __device__ __forceinline__ void argmax_group(const float* __restrict__ acc, cons
   for (int k = 0; k < VEC; ++k) { best[k] = 0.f; arg[k] = 0; }
   for (int c = 0; c < C; ++c) {
     float x[VEC];
-    if constexpr (VEC == 4) {
-      float4 t = __ldg(reinterpret_cast<const float4*>(acc + (size_t)c * V + v0));
-      x[0] = t.x; x[1] = t.y; x[2] = t.z; x[3] = t.w;
-    } else {
-      x[0] = __ldg(acc + (size_t)c * V + v0);
-    }
+    src.template load<VEC>(c, v0, x);
 #pragma unroll
     for (int k = 0; k < VEC; ++k) {
       const float q = __fdiv_rn(x[k], w[k]);
@@ -144,10 +187,10 @@ __device__ __forceinline__ void argmax_group(const float* __restrict__ acc, cons
 // with the channel loads issued UNR at a time, and only a voxel group that is suspicious - near tie, tiny maximum
 // (quotients may underflow to a tie), non-finite input, w == 0 or an overflowing quotient - is redone by the exact
 // per-channel division of argmax_group<> (bit-identical result in every case, tests/test_gpu_passes.py).
-template <int UNR>
+template <int UNR, typename Src>
 __global__ void __launch_bounds__(256)
-finalize_argmax_kernel(const float* __restrict__ acc, const float* __restrict__ wacc, int C, size_t V, Lut256 lut,
-                       int overwrite_nz, uint8_t* __restrict__ label, int* __restrict__ nonfinite) {
+finalize_argmax_kernel(const Src src, const float* __restrict__ wacc, int C, size_t V, Lut256 lut, int overwrite_nz,
+                       uint8_t* __restrict__ label, int* __restrict__ nonfinite) {
   int bad = 0;
   const size_t nvec = V / 4;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
@@ -161,21 +204,21 @@ finalize_argmax_kernel(const float* __restrict__ acc, const float* __restrict__ 
 #pragma unroll
     for (int k = 0; k < 4; ++k) { m1[k] = -INFINITY; m2[k] = -INFINITY; mabs[k] = 0.f; arg[k] = 0; }
     for (int c0 = 0; c0 < C; c0 += UNR) {
-      float4 x4[UNR];
+      float x4[UNR][4];
 #pragma unroll
       for (int u = 0; u < UNR; ++u)
-        if (c0 + u < C) x4[u] = __ldcs(reinterpret_cast<const float4*>(acc + (size_t)(c0 + u) * V + v0));
+        if (c0 + u < C) src.template load<4>(c0 + u, v0, x4[u]);
 #pragma unroll
       for (int u = 0; u < UNR; ++u) {
         if (c0 + u < C) {
-          const float x[4] = {x4[u].x, x4[u].y, x4[u].z, x4[u].w};
 #pragma unroll
           for (int k = 0; k < 4; ++k) {
-            odd |= !(fabsf(x[k]) <= 3.0e38f);  // NaN / inf (and the few finite values above: handled exactly below)
-            mabs[k] = fmaxf(mabs[k], fabsf(x[k]));
-            m2[k] = fmaxf(m2[k], fminf(m1[k], x[k]));
-            if (x[k] > m1[k]) arg[k] = c0 + u;
-            m1[k] = fmaxf(m1[k], x[k]);
+            const float x = x4[u][k];
+            odd |= !(fabsf(x) <= 3.0e38f);  // NaN / inf (and the few finite values above: handled exactly below)
+            mabs[k] = fmaxf(mabs[k], fabsf(x));
+            m2[k] = fmaxf(m2[k], fminf(m1[k], x));
+            if (x > m1[k]) arg[k] = c0 + u;
+            m1[k] = fmaxf(m1[k], x);
           }
         }
       }
@@ -189,7 +232,7 @@ finalize_argmax_kernel(const float* __restrict__ acc, const float* __restrict__ 
       odd |= fabsf(m1[k]) < 1e-30f;                                      // quotients may underflow into a tie
     }
     if (odd) {
-      argmax_group<4>(acc, wacc, C, V, v0, lut, overwrite_nz, label, bad);
+      argmax_group<4>(src, wacc, C, v0, lut, overwrite_nz, label, bad);
       continue;
     }
     uint8_t out[4];
@@ -205,20 +248,21 @@ finalize_argmax_kernel(const float* __restrict__ acc, const float* __restrict__ 
     *reinterpret_cast<uchar4*>(label + v0) = make_uchar4(out[0], out[1], out[2], out[3]);
   }
   for (size_t v = nvec * 4 + (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride)
-    argmax_group<1>(acc, wacc, C, V, v, lut, overwrite_nz, label, bad);
+    argmax_group<1>(src, wacc, C, v, lut, overwrite_nz, label, bad);
   bad = __reduce_add_sync(0xffffffffu, bad);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nonfinite, bad);
 }
 
 // Scalar variant for channel planes that are not 16-byte aligned (V % 4 != 0: odd-sized volumes, or slabs of a sharded
 // volume): same exact arithmetic, one voxel per thread (coalesced 4-byte accesses).
+template <typename Src>
 __global__ void __launch_bounds__(256)
-finalize_argmax_scalar_kernel(const float* __restrict__ acc, const float* __restrict__ wacc, int C, size_t V, Lut256 lut,
+finalize_argmax_scalar_kernel(const Src src, const float* __restrict__ wacc, int C, size_t V, Lut256 lut,
                               int overwrite_nz, uint8_t* __restrict__ label, int* __restrict__ nonfinite) {
   int bad = 0;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride)
-    argmax_group<1>(acc, wacc, C, V, v, lut, overwrite_nz, label, bad);
+    argmax_group<1>(src, wacc, C, v, lut, overwrite_nz, label, bad);
   bad = __reduce_add_sync(0xffffffffu, bad);
   if ((threadIdx.x & 31) == 0 && bad) atomicAdd(nonfinite, bad);
 }
@@ -534,12 +578,50 @@ extern "C" int boa_finalize_argmax(const float* d_logits_acc, const float* d_wei
   // anything else (odd-sized volumes, slabs of a sharded volume) takes the scalar kernel
   const bool vec = V % 4 == 0 && aligned16(d_logits_acc) && aligned16(d_weight_acc) &&
                    (reinterpret_cast<uintptr_t>(d_label_inout) & 3) == 0;
+  const LocalSrc src{d_logits_acc, V};
   if (vec)
-    finalize_argmax_kernel<8><<<grid_for(V / 4, 256, 8), 256, 0, s>>>(d_logits_acc, d_weight_acc, C, V, lut,
-                                                                      overwrite_nonzero_only, d_label_inout, d_nonfinite);
+    finalize_argmax_kernel<8, LocalSrc><<<grid_for(V / 4, 256, 8), 256, 0, s>>>(
+        src, d_weight_acc, C, V, lut, overwrite_nonzero_only, d_label_inout, d_nonfinite);
   else
-    finalize_argmax_scalar_kernel<<<grid_for(V, 256, 8), 256, 0, s>>>(d_logits_acc, d_weight_acc, C, V, lut,
-                                                                      overwrite_nonzero_only, d_label_inout, d_nonfinite);
+    finalize_argmax_scalar_kernel<LocalSrc><<<grid_for(V, 256, 8), 256, 0, s>>>(
+        src, d_weight_acc, C, V, lut, overwrite_nonzero_only, d_label_inout, d_nonfinite);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+// Multi-GPU: exchange + rank-ordered reduction + finalize of one dim-0 slab in ONE kernel over peer memory (PeerSrc).
+extern "C" int boa_reduce_finalize_peers(const void* const* d_peer_bases, const int32_t* zlo, const int32_t* zhi,
+                                         int n_ranks, int slab_lo, int slab_hi, int Y, int X,
+                                         const float* d_weight_slab, int C, const uint8_t* h_lut,
+                                         int overwrite_nonzero_only, uint8_t* d_label_slab, int32_t* d_nonfinite,
+                                         void* stream) {
+  BOA_REQUIRE(d_peer_bases && zlo && zhi && d_weight_slab && h_lut && d_label_slab && d_nonfinite,
+              "boa_reduce_finalize_peers: null");
+  BOA_REQUIRE(n_ranks >= 1 && n_ranks <= MAX_PEERS, "boa_reduce_finalize_peers: %d ranks (max %d)", n_ranks, MAX_PEERS);
+  BOA_REQUIRE(C > 0 && C <= 256 && slab_hi >= slab_lo && Y > 0 && X > 0, "boa_reduce_finalize_peers: bad shape");
+  if (slab_hi == slab_lo) return BOA_OK;
+  PeerSrc src;
+  src.n = n_ranks; src.z0 = slab_lo; src.plane = (size_t)Y * X;
+  bool vec = src.plane % 4 == 0 && aligned16(d_weight_slab) && (reinterpret_cast<uintptr_t>(d_label_slab) & 3) == 0;
+  for (int r = 0; r < MAX_PEERS; ++r) {
+    src.base[r] = r < n_ranks ? static_cast<const float*>(d_peer_bases[r]) : nullptr;
+    src.zlo[r] = r < n_ranks ? zlo[r] : 0;
+    src.zhi[r] = r < n_ranks ? zhi[r] : 0;
+    if (r < n_ranks && zhi[r] > zlo[r]) {
+      BOA_REQUIRE(src.base[r], "boa_reduce_finalize_peers: rank %d has patches but no buffer", r);
+      vec = vec && aligned16(src.base[r]);
+    }
+  }
+  Lut256 lut;
+  for (int c = 0; c < 256; ++c) lut.v[c] = c < C ? h_lut[c] : 0;
+  const size_t V = (size_t)(slab_hi - slab_lo) * src.plane;
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (vec)
+    finalize_argmax_kernel<4, PeerSrc><<<grid_for(V / 4, 256, 8), 256, 0, s>>>(
+        src, d_weight_slab, C, V, lut, overwrite_nonzero_only, d_label_slab, d_nonfinite);
+  else
+    finalize_argmax_scalar_kernel<PeerSrc><<<grid_for(V, 256, 8), 256, 0, s>>>(
+        src, d_weight_slab, C, V, lut, overwrite_nonzero_only, d_label_slab, d_nonfinite);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }
