@@ -73,6 +73,15 @@ _SIGS = {
                                 C.c_int, _P, _P, _P, _P, _P, _P]),
     "boa_paint_label": (C.c_int, [_P, C.c_size_t, C.c_int, _P, _P]),
     "boa_add_slab": (C.c_int, [_P, _P, C.c_size_t, _P]),
+    "boa_add_slab_strided": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.c_int, C.c_size_t, _P]),
+    "boa_comm_alloc": (C.c_int, [C.c_size_t, C.POINTER(_P), C.POINTER(C.c_ubyte)]),
+    "boa_comm_open": (C.c_int, [C.POINTER(C.c_ubyte), C.POINTER(_P)]),
+    "boa_comm_close": (C.c_int, [_P]),
+    "boa_comm_free": (C.c_int, [_P]),
+    "boa_comm_zero": (C.c_int, [_P, C.c_size_t, _P]),
+    "boa_reduce_finalize_peers": (C.c_int, [C.POINTER(_P), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int, C.c_int,
+                                            C.c_int, C.c_int, C.c_int, _P, C.c_int, C.POINTER(C.c_uint8), C.c_int, _P,
+                                            _P, _P]),
 }
 EXPORTS = sorted(_SIGS)
 

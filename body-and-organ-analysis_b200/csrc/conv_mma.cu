@@ -33,6 +33,10 @@ namespace boa {
 // 128 registers each; the transform warps give theirs to the epilogue: 128 * (128 + 248 + 64 + 64) = 64512 <= 65536.
 constexpr int MMA_THREADS = 512;
 constexpr int REGS_EPI = 248, REGS_XF = 64, XF_THREADS = 256;
+// The transform warps work in XF_GROUPS independent groups that take the ring stages round robin, so that the latency
+// chain of one stage (barrier wait, scale / shift loads, LDS -> math -> STS, proxy fence, arrive) overlaps the next
+// stage's instead of serialising with it.
+constexpr int XF_GROUPS = 2, XF_GROUP_THREADS = XF_THREADS / XF_GROUPS;
 constexpr int TILE_X = 8, TILE_Y = 16;
 constexpr int XB = TILE_X + 2, YB = TILE_Y + 2, SLAB = XB * YB;  // 180 halo positions per z-plane
 
@@ -126,7 +130,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], xform ? XF_THREADS / 32 : 1);
+      mbar_init(&full[i], xform ? XF_GROUP_THREADS / 32 : 1);
       mbar_init(&empty[i], 1);
       mbar_init(&rawfull[i], 1);
     }
@@ -256,9 +260,9 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
     // ===================================================================== operand transform (warps 8..15)
     reg_dealloc<REGS_XF>();
     if (xform) {
-      const int tid = threadIdx.x - 256;
-      int st = 0;
-      uint32_t ph = 0;
+      const int grp = (threadIdx.x - 256) / XF_GROUP_THREADS;
+      const int tid = (threadIdx.x - 256) % XF_GROUP_THREADS;
+      uint32_t cnt = 0;  // ring stage counter over (tile, kc) - the same sequence the producer and the MMA warp walk
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, b, tz, ty, tx;
         decode_tile(tile, p, nt, b, tz, ty, tx);
@@ -267,19 +271,22 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
         const int zlo = z0 < 0 ? -z0 : 0, zhi = p.D - z0 < zb ? p.D - z0 : zb;
         const int ylo = y0 < 0 ? -y0 : 0, yhi = p.H - y0 < YB ? p.H - y0 : YB;
         const int xlo = x0 < 0 ? -x0 : 0, xhi = p.W - x0 < XB ? p.W - x0 : XB;
-        for (int kc = 0; kc < p.kc_count; ++kc) {
+        for (int kc = 0; kc < p.kc_count; ++kc, ++cnt) {
+          if ((int)(cnt % XF_GROUPS) != grp) continue;
+          const int st = (int)(cnt % (uint32_t)nstage);
+          const uint32_t ph = (cnt / (uint32_t)nstage) & 1u;
           const int g0 = 2 * kc;  // first channel group of this K chunk inside the input view
           const int skip = (g0 < p.xf.ident_groups ? 1 : 0) | (g0 + 1 < p.xf.ident_groups ? 2 : 0) |
                            (8 * g0 + 8 >= p.xf.channels ? 2 : 0);
           mbar_wait(&rawfull[st], ph);
           if (skip != 3)
-            xform_stage<XB, YB, XF_THREADS, 4, 3>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
-                                     p.xf.scale + (size_t)b * p.xf.channels + 16 * kc,
-                                     p.xf.shift + (size_t)b * p.xf.channels + 16 * kc, skip, p.xf.slope, tid);
+            xform_stage<XB, YB, XF_GROUP_THREADS, 4, 3>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
+                                                        p.xf.scale + (size_t)b * p.xf.channels + 16 * kc,
+                                                        p.xf.shift + (size_t)b * p.xf.channels + 16 * kc, skip,
+                                                        p.xf.slope, tid);
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[st]);
-          if (++st == nstage) { st = 0; ph ^= 1; }
         }
       }
     }

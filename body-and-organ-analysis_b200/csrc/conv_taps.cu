@@ -30,6 +30,9 @@ namespace boa {
 
 constexpr int TAPS_THREADS = 512;  // four warpgroups (the last two transform), see conv_mma.cu
 constexpr int TREGS_EPI = 248, TREGS_XF = 64, TXF_THREADS = 256;
+// transform warps in groups that take the ring stages round robin (conv_mma.cu): the stages of these kernels are small
+// (a few hundred cycles of MMAs), so four stages are transformed concurrently
+constexpr int TXF_GROUPS = 4, TXF_GROUP_THREADS = TXF_THREADS / TXF_GROUPS;
 constexpr int TT_X = 8, TT_Y = 16;
 constexpr int TAPS_MAX_OPS = 27;
 constexpr int TAPS_MAX_STAGES = 12;  // smem ring depth: small stages (transposed conv, deep layers) prefetch several tiles ahead
@@ -85,7 +88,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TAPS_MAX_STAGES; ++i) {
-      mbar_init(&full[i], xform ? TXF_THREADS / 32 : 1);
+      mbar_init(&full[i], xform ? TXF_GROUP_THREADS / 32 : 1);
       mbar_init(&empty[i], 1);
       mbar_init(&rawfull[i], 1);
     }
@@ -179,9 +182,9 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
     // ===================================================================== operand transform (warps 8..11)
     reg_dealloc<TREGS_XF>();
     if (xform) {
-      const int tid = threadIdx.x - 256;
-      int st = 0;
-      uint32_t ph = 0;
+      const int grp = (threadIdx.x - 256) / TXF_GROUP_THREADS;
+      const int tid = (threadIdx.x - 256) % TXF_GROUP_THREADS;
+      uint32_t cnt = 0;  // ring stage counter over (tile, kc)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, b, tz, ty, tx;
         taps_decode_tile(tile, p, nt, b, tz, ty, tx);
@@ -190,7 +193,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
         const int zlo = z0 < 0 ? -z0 : 0, zhi = p.D - z0 < p.box_z ? p.D - z0 : p.box_z;
         const int ylo = y0 < 0 ? -y0 : 0, yhi = p.H - y0 < p.box_y ? p.H - y0 : p.box_y;
         const int xlo = x0 < 0 ? -x0 : 0, xhi = p.W - x0 < p.box_x ? p.W - x0 : p.box_x;
-        for (int kc = 0; kc < p.kc_count; ++kc) {
+        for (int kc = 0; kc < p.kc_count; ++kc, ++cnt) {
+          if ((int)(cnt % TXF_GROUPS) != grp) continue;
+          const int st = (int)(cnt % (uint32_t)nstage);
+          const uint32_t ph = (cnt / (uint32_t)nstage) & 1u;
           // channels of this K chunk: the stride-2 gather walks the 8 phases of the space-to-depth tensor, each
           // holding every channel (chunk index inside the phase = kc % chunks_per_class)
           const int cc = kc % p.chunks_per_class;
@@ -203,14 +209,13 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
             const float* sc = p.xf.scale + (size_t)b * p.xf.channels + 16 * cc;
             const float* sh = p.xf.shift + (size_t)b * p.xf.channels + 16 * cc;
             // box_z <= 6: z phases of 2, at most 3 planes per item
-            if (p.halo == 2) xform_stage<TT_X + 2, TT_Y + 2, TXF_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
-            else if (p.halo == 1) xform_stage<TT_X + 1, TT_Y + 1, TXF_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
-            else xform_stage<TT_X, TT_Y, TXF_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+            if (p.halo == 2) xform_stage<TT_X + 2, TT_Y + 2, TXF_GROUP_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+            else if (p.halo == 1) xform_stage<TT_X + 1, TT_Y + 1, TXF_GROUP_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+            else xform_stage<TT_X, TT_Y, TXF_GROUP_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
           }
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[st]);
-          if (++st == nstage) { st = 0; ph ^= 1; }
         }
       }
     }

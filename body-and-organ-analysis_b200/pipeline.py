@@ -25,7 +25,7 @@ from .dist import DistContext, exchange_slabs, gather_label_slabs, plan_shards
 from .labels import BODY_PARTS_TASK_ID, BODY_REGIONS_TASK_ID, TOTAL_FAST_TASK_ID, TOTAL_TASK_IDS, part_luts
 from .measurements import compute_measurements_on_device
 from .plans import find_model_folder, load_model_folder
-from .predictor import finalize_argmax, nnUNetPredictor, weight_sum
+from .predictor import finalize_argmax, nnUNetPredictor, raise_if_nonfinite, weight_sum
 
 TRAINERS = {**{t: "nnUNetTrainerNoMirroring" for t in TOTAL_TASK_IDS},
             TOTAL_FAST_TASK_ID: "nnUNetTrainer_4000epochs_NoMirroring",
@@ -87,10 +87,12 @@ def nonzero_bbox(vol: torch.Tensor):
 
 
 def predict_labels_sharded(pred: nnUNetPredictor, data: torch.Tensor, lut=None, label_inout=None,
-                           overwrite_nonzero_only=False, dist_ctx: DistContext | None = None) -> torch.Tensor:
-    """predict_labels with the patches of the volume sharded over the ranks of dist_ctx (see dist.py)."""
+                           overwrite_nonzero_only=False, dist_ctx: DistContext | None = None,
+                           defer: list | None = None) -> torch.Tensor:
+    """predict_labels with the patches of the volume sharded over the ranks of dist_ctx (dist.py, NCCL path: one
+    exchange, one finalize and one label all-gather per network)."""
     if dist_ctx is None or dist_ctx.world_size == 1:
-        return pred.predict_labels(data, lut, label_inout, overwrite_nonzero_only)
+        return pred.predict_labels(data, lut, label_inout, overwrite_nonzero_only, defer=defer)
     with torch.cuda.device(pred.device_index):
         vol, origins, unpad = pred._prepare(data)
         plan = plan_shards(origins, pred.patch_size[0], vol.shape[0], dist_ctx.world_size, dist_ctx.rank)
@@ -104,7 +106,7 @@ def predict_labels_sharded(pred: nnUNetPredictor, data: torch.Tensor, lut=None, 
         del acc
         w = weight_sum(vol.shape, pred.patch_size, origins, pred.gaussian(), pred.gaussian_kind)
         lo, hi = plan.slabs[dist_ctx.rank]
-        lab_slab = finalize_argmax(slab, w[lo:hi], lut) if hi > lo else torch.zeros(
+        lab_slab = finalize_argmax(slab, w[lo:hi], lut, defer=defer) if hi > lo else torch.zeros(
             (0, *vol.shape[1:]), dtype=torch.uint8, device=pred.device)
         lab = gather_label_slabs(lab_slab, plan, dist_ctx)[unpad].contiguous()
         if label_inout is None:
@@ -140,9 +142,11 @@ def check_plan_geometry(spec, cropped_shape, spacing_zyx) -> None:
             "configuration spacing (and of the logits back) is not implemented")
 
 
-def _preprocess(ct: torch.Tensor, spec, spacing_zyx=None) -> tuple[torch.Tensor, list]:
-    """crop_to_nonzero -> CTNormalization (fp32).  Returns the [1, z, y, x] network input and the crop box."""
-    box = nonzero_bbox(ct)
+def _preprocess(ct: torch.Tensor, spec, spacing_zyx=None, box=None) -> tuple[torch.Tensor, list]:
+    """crop_to_nonzero -> CTNormalization (fp32).  Returns the [1, z, y, x] network input and the crop box (pass `box`
+    when it is known already: it depends on the volume only, and finding it costs three device -> host reads)."""
+    if box is None:
+        box = nonzero_bbox(ct)
     crop = ct[box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]].contiguous()
     check_plan_geometry(spec, crop.shape, spacing_zyx)
     p = spec.intensity
@@ -167,20 +171,77 @@ def segment_task(ct: torch.Tensor, zoo: ModelZoo, task_ids, folds, step_size: fl
     return _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spacing_zyx)
 
 
+def _segment_task_peers(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spacing_zyx, ex) -> torch.Tensor | None:
+    """Multi-GPU, peer-memory path (dist.PeerExchange): every network's patches go into this rank's private buffer; one
+    fused kernel per network reduces this rank's dim-0 slab over NVLink, finalises it and merges the part labels into
+    the rank's label slab; ONE all-gather of the uint8 slabs per task.  Returns None when the volume needs the
+    general path (cropped by crop_to_nonzero, or smaller than the patch) - decided from the volume alone, so every rank
+    decides the same."""
+    box = nonzero_bbox(ct)
+    if not all(b == 0 and e == s for (b, e), s in zip(box, ct.shape)):
+        return None
+    preds = [zoo.get(tid, folds, step_size) for tid in task_ids]
+    if any(int(s) < int(p) for pr in preds for s, p in zip(ct.shape, pr.patch_size)):
+        return None
+    rank, world = dist_ctx.rank, dist_ctx.world_size
+    Y, X = int(ct.shape[1]), int(ct.shape[2])
+    plans = []
+    need = 0
+    for pred in preds:
+        from .geometry import sliding_window_origins
+        origins = sliding_window_origins(ct.shape, pred.patch_size, pred.tile_step_size)
+        plan = plan_shards(origins, pred.patch_size[0], int(ct.shape[0]), world, rank)
+        plans.append((origins, plan))
+        need = max(need, max((hi - lo) for lo, hi in plan.touched) * pred.num_classes * Y * X * 4)
+    ex.ensure(need)  # collective; `need` is the same number on every rank
+    multi = len(task_ids) > 1
+    lo, hi = plans[0][1].slabs[rank]
+    lab_slab = torch.zeros((hi - lo, Y, X), dtype=torch.uint8, device=ct.device)
+    bad = torch.zeros(1, dtype=torch.int32, device=ct.device)
+    for i, (tid, pred) in enumerate(zip(task_ids, preds)):
+        nvtx.range_push(f"boa/network/{tid}")
+        data, _ = _preprocess(ct, pred.spec, spacing_zyx, box)
+        vol = data[0]
+        origins, plan = plans[i]
+        b = ex.next_buffer()
+        if plan.end > plan.begin:
+            ex.zero(b, pred.num_classes * (plan.zhi - plan.zlo) * Y * X * 4)
+            local = origins[plan.begin:plan.end].copy()
+            local[:, 0] -= plan.zlo
+            pred.accumulate(vol[plan.zlo:plan.zhi], local, ex.local[b])
+        ex.barrier()
+        if hi > lo:
+            w = weight_sum(vol.shape, pred.patch_size, origins, pred.gaussian(), pred.gaussian_kind)
+            ex.reduce_finalize(b, plan, Y, X, w[lo:hi], pred.num_classes, luts[i] if luts is not None else None,
+                               multi, lab_slab, bad)
+        nvtx.range_pop()
+    out = gather_label_slabs(lab_slab, plans[0][1], dist_ctx)
+    raise_if_nonfinite([bad])
+    return out
+
+
 def _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spacing_zyx=None) -> torch.Tensor:
+    if dist_ctx is not None and dist_ctx.world_size > 1 and ct.is_cuda:
+        ex = dist_ctx.peer_exchange(ct.device)
+        if ex is not None:
+            out = _segment_task_peers(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spacing_zyx, ex)
+            if out is not None:
+                return out
     out = torch.zeros(ct.shape, dtype=torch.uint8, device=ct.device)
     multi = len(task_ids) > 1
+    flags: list = []
+    box0 = nonzero_bbox(ct)
     for i, tid in enumerate(task_ids):
         pred = zoo.get(tid, folds, step_size)
         nvtx.range_push(f"boa/network/{tid}")
-        data, box = _preprocess(ct, pred.spec, spacing_zyx)
+        data, box = _preprocess(ct, pred.spec, spacing_zyx, box0)
         sl = tuple(slice(b, e) for b, e in box)
         full = all(b == 0 and e == s for (b, e), s in zip(box, ct.shape))
         lut = luts[i] if luts is not None else None
         if full:
-            predict_labels_sharded(pred, data, lut, out, overwrite_nonzero_only=multi, dist_ctx=dist_ctx)
+            predict_labels_sharded(pred, data, lut, out, overwrite_nonzero_only=multi, dist_ctx=dist_ctx, defer=flags)
         else:
-            lab = predict_labels_sharded(pred, data, lut, dist_ctx=dist_ctx)
+            lab = predict_labels_sharded(pred, data, lut, dist_ctx=dist_ctx, defer=flags)
             if multi:
                 view = out[sl]
                 nz = lab != 0
@@ -188,6 +249,7 @@ def _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spa
             else:
                 out[sl] = lab
         nvtx.range_pop()
+    raise_if_nonfinite(flags)  # one device -> host read per task (predict_from_raw_data.py:622-625)
     return out
 
 
@@ -387,11 +449,12 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         def finish(net_out, fn, name):
             mark(f"{name}_net")
             with nvtx.range(f"boa/postprocess/{name}"):
+                kw_d = {"dist_ctx": dist_ctx} if fn is postprocess_part_segmentation else {}
                 if on_5mm:
-                    net_out = fn(net_out, weights)
+                    net_out = fn(net_out, weights, **kw_d)
                 out = upsample_labels_nearest(net_out, ct.shape[0])
                 if postprocess and not on_5mm:
-                    out = fn(out, None)
+                    out = fn(out, None, **kw_d)
             if postprocess:
                 mark(f"{name}_postprocess")
             return out

@@ -80,18 +80,26 @@ def postprocess_region_segmentation(body_regions: torch.Tensor, weights: torch.T
 
 
 def postprocess_part_segmentation(body_parts: torch.Tensor, weights: torch.Tensor | None = None,
-                                  threshold: int = SMALL_OBJECT_THRESHOLD, labels=None) -> torch.Tensor:
+                                  threshold: int = SMALL_OBJECT_THRESHOLD, labels=None, dist_ctx=None) -> torch.Tensor:
     """remove_small_labeled_objects (body_parts/postprocess.py:7-52): per label (ascending) fill the external contours
     of every slice, drop 26-connected objects of fewer than `threshold` voxels, close 26-connected holes of fewer than
-    `threshold` voxels, paint the label (later labels overwrite earlier ones)."""
+    `threshold` voxels, paint the label (later labels overwrite earlier ones).
+
+    Every label is processed from the ORIGINAL map and painting in ascending order means "the largest label that
+    claims a voxel wins", so with several GPUs (dist_ctx) the labels are dealt out to the ranks round robin and the
+    per-rank results are combined with an element-wise MAX all-reduce - the same map on every rank."""
     from . import passes
 
     if labels is None:
         present = torch.bincount(body_parts.flatten().to(torch.int64), minlength=256).cpu().numpy()
         labels = [int(v) for v in np.nonzero(present)[0] if v > 0]  # np.unique(mask), labels > 0
+    labels = sorted(labels)
+    world = dist_ctx.world_size if dist_ctx is not None else 1
+    if world > 1:
+        labels = labels[dist_ctx.rank::world]
     out = torch.zeros_like(body_parts)
-    scratch = _Scratch(body_parts, need_border=True)
-    for label in sorted(labels):
+    scratch = _Scratch(body_parts, need_border=True) if labels else None
+    for label in labels:
         filled = passes.label_set_mask(body_parts, [label])  # uint8 0 / 1
         # slice-wise external-contour fill == background that no 4-connected path links to the slice border
         _cc_filter(filled, (1,), True, MODE_SLICE_4, OP_FILL_ENCLOSED, 0, 1, None, scratch)
@@ -99,4 +107,7 @@ def postprocess_part_segmentation(body_parts: torch.Tensor, weights: torch.Tenso
         _cc_filter(filled, (1,), True, MODE_26, OP_REMOVE_SMALL, threshold - 1, 1, weights, scratch)
         with torch.cuda.device(out.device):
             _lib.check(_lib.lib().boa_paint_label(_lib.ptr(filled), filled.numel(), label, _lib.ptr(out), _lib.stream_ptr()))
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(out, op=dist.ReduceOp.MAX, group=dist_ctx.group)
     return out

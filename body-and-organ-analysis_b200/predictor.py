@@ -115,14 +115,19 @@ class Network:
         _lib.check(_lib.lib().boa_net_read_timing_kinds(self.handle, n, ms, fl, la, int(reset)))
         return [(float(ms[i]), float(fl[i]), int(la[i])) for i in range(n)]
 
-    def forward_accumulate(self, vol: torch.Tensor, origins: np.ndarray, gaussian: torch.Tensor, acc: torch.Tensor) -> None:
-        """vol fp32 [d0,d1,d2] (device), origins int32 [n,3] (host), gaussian fp32 [p0,p1,p2], acc fp32 [C,d0,d1,d2]."""
+    def forward_accumulate(self, vol: torch.Tensor, origins: np.ndarray, gaussian: torch.Tensor, acc) -> None:
+        """vol fp32 [d0,d1,d2] (device), origins int32 [n,3] (host), gaussian fp32 [p0,p1,p2], acc fp32 [C,d0,d1,d2]:
+        a tensor, or the device address (int) of such a buffer (dist.PeerExchange memory)."""
         assert vol.is_cuda and vol.dtype == torch.float32 and vol.is_contiguous()
-        assert acc.is_cuda and acc.dtype == torch.float32 and acc.is_contiguous()
+        if isinstance(acc, torch.Tensor):
+            assert acc.is_cuda and acc.dtype == torch.float32 and acc.is_contiguous()
+            acc_ptr = _lib.ptr(acc)
+        else:
+            acc_ptr = C.c_void_p(int(acc))
         origins = np.ascontiguousarray(origins, dtype=np.int32)
         _lib.check(_lib.lib().boa_net_forward_accumulate(
             self.handle, _lib.ptr(vol), _lib.i32x3(vol.shape), origins.ctypes.data_as(C.POINTER(C.c_int32)),
-            int(origins.shape[0]), _lib.ptr(gaussian), _lib.ptr(acc), _lib.stream_ptr()))
+            int(origins.shape[0]), _lib.ptr(gaussian), acc_ptr, _lib.stream_ptr()))
 
     def forward_logits(self, patches: torch.Tensor) -> torch.Tensor:
         """Parity entry: patches fp32 [n,Cin,p0,p1,p2] (device) -> raw logits fp32 [n,C,p0,p1,p2]."""
@@ -169,10 +174,22 @@ def weight_sum(shape, patch, origins: np.ndarray, gaussian: torch.Tensor, kind: 
     return w
 
 
+INF_MESSAGE = ("Encountered inf in predicted array. Aborting... If this problem persists, reduce "
+               "value_scaling_factor in compute_gaussian or increase the dtype of predicted_logits to fp32")
+
+
+def raise_if_nonfinite(flags) -> None:
+    """predict_from_raw_data.py:622-625 for flags collected with finalize_argmax(..., defer=flags): ONE device -> host
+    read per task instead of one per network (each read drains the launch queue)."""
+    if flags and int(torch.stack([f.reshape(()) for f in flags]).sum().item()) != 0:
+        raise RuntimeError(INF_MESSAGE)
+
+
 def finalize_argmax(acc: torch.Tensor, wsum: torch.Tensor, lut=None, label_inout: torch.Tensor | None = None,
-                    overwrite_nonzero_only: bool = False) -> torch.Tensor:
+                    overwrite_nonzero_only: bool = False, defer: list | None = None) -> torch.Tensor:
     """`logits /= n`, isinf check, argmax(0) (first max wins), part->global LUT, non-zero overwrite merge
-    (predict_from_raw_data.py:620-625; label_handling.py:178; totalsegmentator/nnunet.py:553-556) in one pass."""
+    (predict_from_raw_data.py:620-625; label_handling.py:178; totalsegmentator/nnunet.py:553-556) in one pass.
+    defer: a list that collects the non-finite flag instead of reading it here (see raise_if_nonfinite)."""
     Cn = acc.shape[0]
     V = wsum.numel()
     if label_inout is None:
@@ -182,9 +199,10 @@ def finalize_argmax(acc: torch.Tensor, wsum: torch.Tensor, lut=None, label_inout
     _lib.check(_lib.lib().boa_finalize_argmax(_lib.ptr(acc), _lib.ptr(wsum), Cn, V, lut_arr,
                                               int(overwrite_nonzero_only), _lib.ptr(label_inout), _lib.ptr(bad),
                                               _lib.stream_ptr()))
-    if int(bad.item()) != 0:
-        raise RuntimeError("Encountered inf in predicted array. Aborting... If this problem persists, reduce "
-                           "value_scaling_factor in compute_gaussian or increase the dtype of predicted_logits to fp32")
+    if defer is not None:
+        defer.append(bad)
+    elif int(bad.item()) != 0:
+        raise RuntimeError(INF_MESSAGE)
     return label_inout
 
 
@@ -268,8 +286,9 @@ class nnUNetPredictor:
         origins = sliding_window_origins(vol.shape, self.patch_size, self.tile_step_size)
         return vol, origins, unpad
 
-    def accumulate(self, vol: torch.Tensor, origins: np.ndarray, acc: torch.Tensor | None = None) -> torch.Tensor:
-        """Run every fold over the given patch origins, adding `logits * gaussian` into `acc` [C, *vol.shape]."""
+    def accumulate(self, vol: torch.Tensor, origins: np.ndarray, acc=None):
+        """Run every fold over the given patch origins, adding `logits * gaussian` into `acc` [C, *vol.shape] (a tensor
+        or a device address, see Network.forward_accumulate)."""
         if acc is None:
             acc = torch.zeros((self.num_classes, *vol.shape), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device_index):
@@ -297,7 +316,7 @@ class nnUNetPredictor:
 
     @torch.inference_mode()
     def predict_labels(self, input_image: torch.Tensor, lut=None, label_inout: torch.Tensor | None = None,
-                       overwrite_nonzero_only: bool = False) -> torch.Tensor:
+                       overwrite_nonzero_only: bool = False, defer: list | None = None) -> torch.Tensor:
         """[c,x,y,z] -> uint8 label map [x,y,z] on the device; logits never leave HBM."""
         with torch.cuda.device(self.device_index):
             vol, origins, unpad = self._prepare(input_image)
@@ -305,7 +324,7 @@ class nnUNetPredictor:
             w = weight_sum(vol.shape, self.patch_size, origins, self.gaussian(), self.gaussian_kind)
             padded = any(s.start != 0 or s.stop != d for s, d in zip(unpad, vol.shape))
             if padded:
-                lab = finalize_argmax(acc, w, lut)[unpad].contiguous()
+                lab = finalize_argmax(acc, w, lut, defer=defer)[unpad].contiguous()
                 if label_inout is None:
                     return lab
                 if overwrite_nonzero_only:
@@ -313,4 +332,4 @@ class nnUNetPredictor:
                 else:
                     label_inout.copy_(lab)
                 return label_inout
-            return finalize_argmax(acc, w, lut, label_inout, overwrite_nonzero_only)
+            return finalize_argmax(acc, w, lut, label_inout, overwrite_nonzero_only, defer=defer)

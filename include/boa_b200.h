@@ -214,8 +214,34 @@ int boa_cc_filter(uint8_t* d_seg, const int32_t* shape, const uint8_t* h_label_s
 /* d_out[v] = label where d_mask[v] != 0 (body_parts/postprocess.py:50). */
 int boa_paint_label(const uint8_t* d_mask, size_t n, int label, uint8_t* d_out, void* stream);
 
-/* Multi-GPU exchange, device side: d_dst[i] += d_src[i] (fp32, round-to-nearest, fixed order chosen by the caller). */
+/* ------------------------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU).  The reference has no multi-GPU inference path: these entry points
+ * replace nothing, they extend predict_sliding_window_return_logits (predict_from_raw_data.py:560-631) across GPUs.
+ * ------------------------------------------------------------------------------------------------------------ */
+/* NCCL path, device side: d_dst[i] += d_src[i] (fp32, round-to-nearest, fixed order chosen by the caller). */
 int boa_add_slab(float* d_dst, const float* d_src, size_t n, void* stream);
+/* d_dst[c * dst_cstride + i] += d_src[c * src_cstride + i] for c < C, i < n (strides in elements): one launch per
+ * received piece [C, len, Y, X]. */
+int boa_add_slab_strided(float* d_dst, size_t dst_cstride, const float* d_src, size_t src_cstride, int C, size_t n,
+                         void* stream);
+/* Peer-memory path.  boa_comm_alloc: device memory that other processes of the box can map - returns the pointer and
+ * its 64-byte CUDA IPC handle; boa_comm_open maps a peer's buffer (lazy peer access over NVLink), boa_comm_close
+ * unmaps it, boa_comm_free releases an own buffer, boa_comm_zero clears it on a stream. */
+#define BOA_IPC_HANDLE_BYTES 64
+int boa_comm_alloc(size_t bytes, void** d_ptr, unsigned char* ipc_handle_out);
+int boa_comm_open(const unsigned char* ipc_handle, void** d_ptr);
+int boa_comm_close(void* d_ptr);
+int boa_comm_free(void* d_ptr);
+int boa_comm_zero(void* d_ptr, size_t bytes, void* stream);
+/* Exchange + reduction + finalize of ONE dim-0 slab in one kernel: rank r's private buffer d_peer_bases[r] holds the
+ * partial sums [C][zhi[r] - zlo[r]][Y][X] of its patches (slices zlo[r] .. zhi[r] of the volume); the caller owns the
+ * slices slab_lo .. slab_hi, reads every rank's part of them through the mapped pointers, adds them in rank order and
+ * then does exactly what boa_finalize_argmax does (divide by d_weight_slab, non-finite flag, argmax with first maximum,
+ * LUT, optional non-zero overwrite) into d_label_slab [slab_hi - slab_lo][Y][X].  n_ranks <= 8. */
+int boa_reduce_finalize_peers(const void* const* d_peer_bases, const int32_t* zlo, const int32_t* zhi, int n_ranks,
+                              int slab_lo, int slab_hi, int Y, int X, const float* d_weight_slab, int C,
+                              const uint8_t* h_lut, int overwrite_nonzero_only, uint8_t* d_label_slab,
+                              int32_t* d_nonfinite, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,4 +1,6 @@
-"""GPU, 2 ranks over NCCL (skipped on a single-GPU box): sharded prediction equals the single-GPU prediction."""
+"""GPU, 2 ranks (skipped on a single-GPU box): the sharded prediction - over the peer-memory path (CUDA-IPC buffers,
+fused reduce + finalize kernel reading the peers over NVLink) and over the NCCL send / recv path - equals the single-GPU
+prediction, the two paths are bit-identical to each other, and the sharded post-processing / full pipeline agree."""
 import os
 import socket
 
@@ -25,25 +27,59 @@ def _worker(rank, world, port, out_dir):
     from boa_b200 import zoo
     from boa_b200.dist import DistContext
     from boa_b200.labels import part_luts
-    from boa_b200.pipeline import ModelZoo, segment_task
-    specs = zoo.synthetic_specs((32, 32, 32), 32, 64, 3, bca_folds=1, seed=1, datasets=[291, 292])
+    from boa_b200.pipeline import ModelZoo, analyze_volume, segment_task
+    specs = zoo.synthetic_specs((32, 32, 32), 32, 64, 3, bca_folds=2, seed=1, datasets=[291, 292, 293, 294, 295, 542, 543])
     mz = ModelZoo.from_specs(specs, device=torch.device("cuda", rank), max_batch=2)
-    ct = torch.from_numpy(zoo.synthetic_ct((72, 48, 40), seed=2)).cuda()
-    lab = segment_task(ct, mz, [291, 292], [0], 0.8, part_luts()[:2], DistContext(rank, world, None))
+    # odd in-plane size: slab offsets that are not 16-byte aligned take the scalar kernels
+    for name, shape in (("even", (72, 48, 40)), ("odd", (70, 45, 39))):
+        ct = torch.from_numpy(zoo.synthetic_ct(shape, seed=2)).cuda()
+        ctx = DistContext(rank, world, None)
+        peers = segment_task(ct, mz, [291, 292], [0], 0.8, part_luts()[:2], ctx)
+        used_peers = ctx._peers is not None
+        os.environ["BOA_B200_EXCHANGE"] = "nccl"
+        nccl = segment_task(ct, mz, [291, 292], [0], 0.8, part_luts()[:2], DistContext(rank, world, None))
+        del os.environ["BOA_B200_EXCHANGE"]
+        if rank == 0:
+            single = segment_task(ct, mz, [291, 292], [0], 0.8, part_luts()[:2], None)
+            np.savez(os.path.join(out_dir, f"seg_{name}.npz"), peers=peers.cpu().numpy(), nccl=nccl.cpu().numpy(),
+                     single=single.cpu().numpy(), used_peers=used_peers)
+    # whole pipeline, sharded vs single: label maps, post-processing (labels dealt out to the ranks), measurements
+    ct = torch.from_numpy(zoo.synthetic_ct((96, 64, 64), seed=5)).cuda()
+    res = analyze_volume(ct, (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=False, dist_ctx=DistContext(rank, world, None))
     if rank == 0:
-        single = segment_task(ct, mz, [291, 292], [0], 0.8, part_luts()[:2], None)
-        np.save(os.path.join(out_dir, "sharded.npy"), lab.cpu().numpy())
-        np.save(os.path.join(out_dir, "single.npy"), single.cpu().numpy())
+        ref = analyze_volume(ct, (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=False)
+        import json
+        np.savez(os.path.join(out_dir, "pipeline.npz"),
+                 **{f"{k}_{w}": getattr(r, k).cpu().numpy() for w, r in (("dist", res), ("single", ref))
+                    for k in ("total", "body_parts", "body_regions", "tissues")})
+        with open(os.path.join(out_dir, "meas.json"), "w") as f:
+            json.dump({"dist": [res.total_measurements, res.bca_measurements],
+                       "single": [ref.total_measurements, ref.bca_measurements]}, f)
     dist.barrier()
     dist.destroy_process_group()
 
 
-def test_two_rank_nccl_matches_single_gpu(cuda, tmp_path):
+def test_two_ranks_match_single_gpu(cuda, tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
+    import json
+
     import torch.multiprocessing as mp
     mp.spawn(_worker, args=(2, _free_port(), str(tmp_path)), nprocs=2, join=True)
-    a, b = np.load(tmp_path / "sharded.npy"), np.load(tmp_path / "single.npy")
-    # the owner adds the two partial sums in rank order, the single GPU adds patches in slicer order: fp32 sums may
-    # differ in the last bit, argmax only flips on exact near-ties
-    assert (a == b).mean() > 0.9999
+    for name in ("even", "odd"):
+        z = np.load(tmp_path / f"seg_{name}.npz")
+        assert bool(z["used_peers"]), "the peer-memory path was not taken on a 2-GPU box"
+        # same additions in the same (rank) order on both paths
+        assert np.array_equal(z["peers"], z["nccl"]), name
+        # the owner adds the two partial sums in rank order, the single GPU adds patches in slicer order: fp32 sums may
+        # differ in the last bit, argmax only flips on exact near-ties
+        assert (z["peers"] == z["single"]).mean() > 0.9999, name
+    p = np.load(tmp_path / "pipeline.npz")
+    for k in ("total", "body_parts", "body_regions", "tissues"):
+        agree = (p[f"{k}_dist"] == p[f"{k}_single"]).mean()
+        print(f"pipeline {k}: sharded == single on {agree:.6f} of the voxels")
+        assert agree > 0.999, k
+    m = json.load(open(tmp_path / "meas.json"))
+    # the measurement dicts are functions of the label maps: same keys, and equal wherever the maps are equal
+    assert m["dist"][0]["segmentations"]["total"].keys() == m["single"][0]["segmentations"]["total"].keys()
+    assert m["dist"][1].keys() == m["single"][1].keys()
