@@ -76,91 +76,136 @@ def _window(hist_row: np.ndarray, lo: int, hi: int, hu_min: int = HU_MIN) -> np.
     return out
 
 
-def _occupied_range(hist_dev: torch.Tensor) -> tuple[int, int]:
-    """[lo, hi) of the histogram columns any label uses: a CT occupies ~4 000 of the 65 536 int16 bins, and every
-    per-label statistic below walks its whole row."""
-    idx = torch.nonzero((hist_dev != 0).any(dim=0)).flatten()
-    if idx.numel() == 0:
-        return 0, 1
-    return int(idx[0]), int(idx[-1]) + 1
+def _to_host_async(t: torch.Tensor) -> torch.Tensor:
+    """Device -> pinned host copy on the current stream (no host synchronisation; see PendingMeasurements)."""
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    return h
 
 
-def _masked_hist(ct: torch.Tensor, mask: torch.Tensor) -> np.ndarray:
-    hist, _ = passes.label_hu_hist(ct, mask, 2, HU_MIN, N_BINS)
-    return hist[1].cpu().numpy().view(np.uint32)
+def _masked_hist_dev(ct: torch.Tensor, mask: torch.Tensor, hu_lo: int, n_bins: int) -> torch.Tensor:
+    hist, _ = passes.label_hu_hist(ct, mask, 2, hu_lo, n_bins)
+    return hist[1]
 
 
-def _eroded_region_hist(ct, labels, ids, minus_fat: bool) -> np.ndarray:
+def _eroded_region_hist_dev(ct, labels, ids, minus_fat: bool, hu_lo: int, n_bins: int) -> torch.Tensor:
     mask = passes.label_set_mask(labels, ids, ct, ADIPOSE_TISSUE[0], ADIPOSE_TISSUE[1], 2 if minus_fat else 0)
-    return _masked_hist(ct, passes.erode_box(mask, 3, 2))
+    return _masked_hist_dev(ct, passes.erode_box(mask, 3, 2), hu_lo, n_bins)
 
 
-def compute_measurements_on_device(ct: torch.Tensor, segmentations: dict[str, torch.Tensor], spacing,
-                                   cnr_adjustment: bool = False, return_ct_pfav_mask: bool = False):
-    """ct int16 [z,y,x] on the device; segmentations: model name -> uint8 label map (same shape); spacing as
-    SimpleITK's GetSpacing().  Returns the dict compute_measurements returns (+ the ct_pfav mask tensor on request)."""
-    measurements: dict[str, Any] = {"segmentations": {}, "info": {}}
-    pfav_mask = None
+class PendingMeasurements:
+    """Device work of compute_measurements is enqueued (histograms, eroded-region histograms, the ct_pfav mask) and the
+    small tables are on their way to pinned host memory; finish() waits for them and does the host arithmetic.  The
+    pipeline calls finish() after the following networks are enqueued, so the ~300 per-name statistics (tens of ms of
+    numpy) run while the GPU is busy instead of between two networks."""
+
+    def __init__(self, spacing, cnr_adjustment: bool):
+        self.spacing, self.cnr_adjustment = spacing, cnr_adjustment
+        self.models: list = []      # (model_name, label_map, hu_lo, hist_host, aut_hist_host | None, {region: hist_host})
+        self.pfav_mask = None
+        self.event = None
+
+    def finish(self):
+        if self.event is not None:
+            self.event.synchronize()
+        spacing = self.spacing
+        measurements: dict[str, Any] = {"segmentations": {}, "info": {}}
+        aut_mean = aut_std = None
+        for model_name, label_map, hu0, hist_h, aut_h, adj_h in self.models:
+            hist = hist_h.numpy().view(np.uint32)
+            if aut_h is not None:
+                h = aut_h.numpy().view(np.uint32)
+                if h.sum() > 0:
+                    ref = metrics_from_hist(h, hu0, None, None, spacing)
+                    aut_mean, aut_std = ref["mean_hu"], ref["std_hu"]
+            res, per_label = {}, {}
+            for region, label in label_map.items():
+                # ~60 % of the names are aliases of a label id that was evaluated already (total_v1_*, total_mr_*, ...)
+                if label not in per_label:
+                    per_label[label] = metrics_from_hist(hist[label], hu0, aut_mean, aut_std, spacing)
+                res[region] = dict(per_label[label])
+            if "autochthon_left" in label_map and "autochthon_right" in label_map:
+                union = hist[label_map["autochthon_left"]].astype(np.int64) + hist[label_map["autochthon_right"]]
+                res["autochthon"] = metrics_from_hist(union, hu0, aut_mean, aut_std, spacing)
+            if model_name == "total":
+                def lung(names):
+                    u = np.zeros(hist.shape[1], dtype=np.int64)
+                    for nme in names:
+                        u += _window(hist[label_map[nme]], *ADIPOSE_TISSUE, hu_min=hu0)
+                    return metrics_from_hist(u, hu0, aut_mean, aut_std, spacing)
+                for nme in LUNG_MASKS:
+                    res["ct_pfav_" + nme] = lung([nme])
+                for side in ("left", "right"):
+                    res[f"ct_pfav_lobe_{side}"] = lung([ll for ll in LUNG_MASKS if ll.endswith(side)])
+                res["ct_pfav_lungs"] = lung(LUNG_MASKS)
+            measurements["segmentations"][model_name] = res
+            if (self.cnr_adjustment and model_name in CNR_ADJUSTED_REGIONS and aut_mean is not None
+                    and aut_std is not None):
+                adj = {}
+                sel = {r: v for r, v in label_map.items() if r in CNR_ADJUSTED_REGIONS[model_name]}
+                for region, label in sel.items():
+                    if hist[label].sum() == 0:
+                        adj[region] = {"present": False}
+                        continue
+                    adj[region] = metrics_from_hist(adj_h[region].numpy().view(np.uint32), hu0, aut_mean, aut_std,
+                                                    spacing, cnr_none=region.partition("_")[0] == "autochthon")
+                if "autochthon_left" in sel and "autochthon_right" in sel:
+                    if sum(int(hist[i].sum()) for i in (sel["autochthon_left"], sel["autochthon_right"])) == 0:
+                        adj["autochthon"] = {"present": False}
+                    else:
+                        adj["autochthon"] = metrics_from_hist(aut_h.numpy().view(np.uint32), hu0, aut_mean, aut_std,
+                                                              spacing, cnr_none=True)
+                measurements.setdefault("cnr_adjusted", {}).update(adj)
+        measurements["info"]["autochthon_mean"] = aut_mean
+        measurements["info"]["autochthon_std"] = aut_std
+        return measurements, self.pfav_mask
+
+
+def enqueue_measurements(ct: torch.Tensor, segmentations: dict[str, torch.Tensor], spacing,
+                         cnr_adjustment: bool = False, return_ct_pfav_mask: bool = False,
+                         hu_range: tuple[int, int] | None = None) -> PendingMeasurements:
+    """Device half of compute_measurements (compute/measurements.py:244-343).  hu_range = (min, max) HU of the CT if
+    the caller knows it (the histograms then cover exactly that range); None: read it here (one host sync)."""
+    pend = PendingMeasurements(spacing, cnr_adjustment)
     if not segmentations:
-        return (measurements, None) if return_ct_pfav_mask else measurements
+        return pend
     if ct.dtype != torch.int16:
         raise TypeError("compute_measurements_on_device needs an int16 CT (exact integer-HU histograms)")
-    aut_mean = aut_std = None
+    if hu_range is None:
+        lo_t, hi_t = torch.aminmax(ct)
+        hu_range = (int(lo_t), int(hi_t))
+    hu_lo, n_bins = int(hu_range[0]), int(hu_range[1]) - int(hu_range[0]) + 1
     for model_name in sorted(segmentations, key=lambda m: m != "total"):
         labels = segmentations[model_name]
         if labels.shape != ct.shape:
             raise ValueError("The spacing of the image and of the segmentation should be the same")
         label_map = measurement_label_map(model_name)
         n_labels = max(label_map.values()) + 1
-        hist_dev, _ = passes.label_hu_hist(ct, labels, n_labels, HU_MIN, N_BINS)
-        col_lo, col_hi = _occupied_range(hist_dev)
-        hist = hist_dev[:, col_lo:col_hi].contiguous().cpu().numpy().view(np.uint32)
-        hu0 = HU_MIN + col_lo  # hist[label][i] = #voxels of the label with HU == hu0 + i
+        hist_dev, _ = passes.label_hu_hist(ct, labels, n_labels, hu_lo, n_bins)
+        hist_h = _to_host_async(hist_dev)
+        aut_h, adj_h = None, {}
         if model_name == "total":
             ids = [label_map["autochthon_right"], label_map["autochthon_left"]]
-            h = _eroded_region_hist(ct, labels, ids, minus_fat=True)
-            if h.sum() > 0:
-                ref = metrics_from_hist(h, HU_MIN, None, None, spacing)
-                aut_mean, aut_std = ref["mean_hu"], ref["std_hu"]
-        res = {}
-        for region, label in label_map.items():
-            res[region] = metrics_from_hist(hist[label], hu0, aut_mean, aut_std, spacing)
-        if "autochthon_left" in label_map and "autochthon_right" in label_map:
-            union = hist[label_map["autochthon_left"]].astype(np.int64) + hist[label_map["autochthon_right"]]
-            res["autochthon"] = metrics_from_hist(union, hu0, aut_mean, aut_std, spacing)
-        if model_name == "total":
-            def lung(names):
-                u = np.zeros(hist.shape[1], dtype=np.int64)
-                for nme in names:
-                    u += _window(hist[label_map[nme]], *ADIPOSE_TISSUE, hu_min=hu0)
-                return metrics_from_hist(u, hu0, aut_mean, aut_std, spacing)
-            for nme in LUNG_MASKS:
-                res["ct_pfav_" + nme] = lung([nme])
-            for side in ("left", "right"):
-                res[f"ct_pfav_lobe_{side}"] = lung([ll for ll in LUNG_MASKS if ll.endswith(side)])
-            res["ct_pfav_lungs"] = lung(LUNG_MASKS)
+            # the same histogram serves the autochthon reference (:42-58) and the CNR-adjusted "autochthon" entry
+            aut_h = _to_host_async(_eroded_region_hist_dev(ct, labels, ids, True, hu_lo, n_bins))
             if return_ct_pfav_mask:
-                pfav_mask = passes.label_set_mask(labels, [label_map[ll] for ll in LUNG_MASKS], ct,
-                                                  ADIPOSE_TISSUE[0], ADIPOSE_TISSUE[1], 1)
-        measurements["segmentations"][model_name] = res
-        if cnr_adjustment and model_name in CNR_ADJUSTED_REGIONS and aut_mean is not None and aut_std is not None:
-            adj = {}
-            sel = {r: v for r, v in label_map.items() if r in CNR_ADJUSTED_REGIONS[model_name]}
-            for region, label in sel.items():
-                if hist[label].sum() == 0:
-                    adj[region] = {"present": False}
-                    continue
-                h = _eroded_region_hist(ct, labels, [label], minus_fat="autochthon" in region)
-                adj[region] = metrics_from_hist(h, HU_MIN, aut_mean, aut_std, spacing,
-                                                cnr_none=region.partition("_")[0] == "autochthon")
-            if "autochthon_left" in sel and "autochthon_right" in sel:
-                ids = [sel["autochthon_left"], sel["autochthon_right"]]
-                if sum(int(hist[i].sum()) for i in ids) == 0:
-                    adj["autochthon"] = {"present": False}
-                else:
-                    h = _eroded_region_hist(ct, labels, ids, minus_fat=True)
-                    adj["autochthon"] = metrics_from_hist(h, HU_MIN, aut_mean, aut_std, spacing, cnr_none=True)
-            measurements.setdefault("cnr_adjusted", {}).update(adj)
-    measurements["info"]["autochthon_mean"] = aut_mean
-    measurements["info"]["autochthon_std"] = aut_std
-    return (measurements, pfav_mask) if return_ct_pfav_mask else measurements
+                pend.pfav_mask = passes.label_set_mask(labels, [label_map[ll] for ll in LUNG_MASKS], ct,
+                                                       ADIPOSE_TISSUE[0], ADIPOSE_TISSUE[1], 1)
+        if cnr_adjustment and model_name in CNR_ADJUSTED_REGIONS:
+            for region, label in label_map.items():
+                if region in CNR_ADJUSTED_REGIONS[model_name]:
+                    adj_h[region] = _to_host_async(_eroded_region_hist_dev(ct, labels, [label], "autochthon" in region,
+                                                                           hu_lo, n_bins))
+        pend.models.append((model_name, label_map, hu_lo, hist_h, aut_h, adj_h))
+    pend.event = torch.cuda.Event()
+    pend.event.record()
+    return pend
+
+
+def compute_measurements_on_device(ct: torch.Tensor, segmentations: dict[str, torch.Tensor], spacing,
+                                   cnr_adjustment: bool = False, return_ct_pfav_mask: bool = False,
+                                   hu_range: tuple[int, int] | None = None):
+    """ct int16 [z,y,x] on the device; segmentations: model name -> uint8 label map (same shape); spacing as
+    SimpleITK's GetSpacing().  Returns the dict compute_measurements returns (+ the ct_pfav mask tensor on request)."""
+    m, pfav = enqueue_measurements(ct, segmentations, spacing, cnr_adjustment, return_ct_pfav_mask, hu_range).finish()
+    return (m, pfav) if return_ct_pfav_mask else m

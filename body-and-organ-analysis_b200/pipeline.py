@@ -14,6 +14,7 @@ few KB.  Logits never leave HBM.
 from __future__ import annotations
 
 import os
+import time
 from dataclasses import dataclass, field
 
 import numpy as np
@@ -23,7 +24,7 @@ from torch.cuda import nvtx  # NVTX ranges around the stages (visible in nsys / 
 from . import bca, passes
 from .dist import DistContext, exchange_slabs, gather_label_slabs, plan_shards
 from .labels import BODY_PARTS_TASK_ID, BODY_REGIONS_TASK_ID, TOTAL_FAST_TASK_ID, TOTAL_TASK_IDS, part_luts
-from .measurements import compute_measurements_on_device
+from .measurements import compute_measurements_on_device, enqueue_measurements
 from .plans import find_model_folder, load_model_folder
 from .predictor import finalize_argmax, nnUNetPredictor, raise_if_nonfinite, weight_sum
 
@@ -290,45 +291,6 @@ class VolumeResult:
     timings: dict = field(default_factory=dict)
 
 
-class _Background:
-    """Run fn() on a helper thread with its own CUDA stream, ordered after everything enqueued so far on the caller's
-    stream; join() re-raises what fn raised, makes the caller's stream wait for the side stream and returns the host
-    seconds fn took.  `inputs` are tensors produced on the caller's stream that fn reads."""
-
-    def __init__(self, device, fn, inputs=()):
-        import threading
-        import time
-
-        self.device = torch.device(device)
-        self.stream = torch.cuda.Stream(self.device)
-        ready = torch.cuda.Event()
-        ready.record(torch.cuda.current_stream(self.device))
-        for t in inputs:
-            t.record_stream(self.stream)
-        self.error = None
-        self.seconds = 0.0
-
-        def run():
-            t0 = time.perf_counter()
-            try:
-                with torch.cuda.device(self.device), torch.cuda.stream(self.stream):
-                    self.stream.wait_event(ready)
-                    fn()
-            except BaseException as e:  # noqa: BLE001 - re-raised by join()
-                self.error = e
-            self.seconds = time.perf_counter() - t0
-
-        self.thread = threading.Thread(target=run, name="boa-b200-measurements", daemon=True)
-        self.thread.start()
-
-    def join(self) -> float:
-        self.thread.join()
-        torch.cuda.current_stream(self.device).wait_stream(self.stream)
-        if self.error is not None:
-            raise self.error
-        return self.seconds
-
-
 class HostStager:
     """Device -> host staging of the label maps for callers that hold host buffers: each map is copied into a pinned
     buffer on a side stream as soon as it is final, so the transfer overlaps the networks that follow (the reference
@@ -380,7 +342,11 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
     models = set(models)
     if "bca" in models:
         models.add("total")  # compute/config.py:54-55
-    background = None
+    pending_total = None
+    # HU range of the CT: sizes the per-label histograms exactly; read once here, before any network is enqueued (the
+    # only device -> host read ahead of the label maps)
+    lo_t, hi_t = torch.aminmax(ct)
+    hu_range = (int(lo_t), int(hi_t))
     ev = lambda: torch.cuda.Event(enable_timing=True)
     marks = [("start", ev())]
     marks[-1][1].record()
@@ -410,22 +376,14 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
             stager.stage("total", res.total)
         sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
 
-        def measure_total():
-            if not total_measurements:
-                return
+        # `total-measurements.json` needs only the CT and the `total` label map: its device passes are enqueued here and
+        # the small tables travel to pinned host memory; the ~300 per-name statistics (host numpy) are evaluated at the
+        # end, after the body-composition networks are enqueued, i.e. while the GPU is busy.
+        if total_measurements:
             with nvtx.range("boa/total_measurements"):
-                res.total_measurements, res.ct_pfav = compute_measurements_on_device(
-                    ct, {"total": res.total}, sx_sy_sz, cnr_adjustment, return_ct_pfav_mask=True)
-
-        # `total-measurements.json` needs only the CT and the `total` label map, so it CAN run on a side stream driven
-        # by a helper thread while the body-composition networks follow (BOA_B200_ASYNC_MEAS=1).  Measured on B200: a
-        # loss - the helper's 60 ms of Python compete with the launch loop of the networks for the GIL (bca_nets
-        # +70 ms on 1 GPU, +350 ms next to the NCCL exchange on 2), so it is off by default.
-        run_async = bool(models & {"bca", "body_parts", "body_regions"}) and os.environ.get("BOA_B200_ASYNC_MEAS", "0") == "1"
-        if run_async:
-            background = _Background(ct.device, measure_total, (ct, res.total))
-        else:
-            measure_total()
+                pending_total = enqueue_measurements(ct, {"total": res.total}, sx_sy_sz, cnr_adjustment,
+                                                     return_ct_pfav_mask=True, hu_range=hu_range)
+            res.ct_pfav = pending_total.pfav_mask
             mark("total_measurements")
             if stager is not None:
                 stager.stage("ct_pfav", res.ct_pfav)
@@ -474,11 +432,10 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         if stager is not None:
             stager.stage("body_regions", res.body_regions)
         mark("bca_nets")
-    if background is not None:
-        res.timings["total_measurements_async_host"] = background.join()
-        mark("total_measurements_join")
-        if stager is not None:
-            stager.stage("ct_pfav", res.ct_pfav)
+    if pending_total is not None:
+        t_host = time.perf_counter()
+        res.total_measurements, _ = pending_total.finish()
+        res.timings["total_measurements_host"] = time.perf_counter() - t_host
     if "bca" in models:
         nvtx.range_push("boa/bca_measurements")
         res.tissues = bca.subclassify_tissues(ct, res.body_regions, median_filtering)
