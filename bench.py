@@ -39,12 +39,17 @@ def parse():
     ap.add_argument("--fast-bca", action="store_true", help="fold 0 only for the body-composition nets (--fast-bca)")
     ap.add_argument("--models", default="total+bca")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--mode", default="latency", choices=["latency", "throughput"],
+                    help="latency (default): the patches of ONE volume are sharded over the GPUs (BASELINE config 3); "
+                         "throughput: every GPU processes its own volumes, no collectives (BASELINE config 4)")
+    ap.add_argument("--quick", action="store_true", help="skip the roofline / baseline legs (extra configurations)")
     return ap.parse_args()
 
 
 def workload_name(a) -> str:
     return (f"synthetic CT {a.shape[0]}x{a.shape[1]}x{a.shape[2]} @1.5mm, --models {a.models}"
-            f"{' --fast-bca' if a.fast_bca else ''}, patch {a.patch}^3")
+            f"{' --fast-bca' if a.fast_bca else ''}, patch {a.patch}^3"
+            f"{', one volume per GPU (throughput mode)' if getattr(a, 'mode', 'latency') == 'throughput' else ''}")
 
 
 def count_forwards(a) -> dict:
@@ -71,8 +76,10 @@ def bench_config(a, world: int) -> dict:
     return {"workload": workload_name(a), "forwards_per_volume": n, "patch_batch": a.batch,
             "tflop_per_volume": 2.0 * macs_per_patch(arch) * (n["total"] + n["bca"]) / 1e12,
             "l2": "inputs larger than L2 (268 MB CT, >1 GB activations per layer batch)",
-            "parallelism": (f"patches of one volume sharded over {world} GPU(s), one NCCL slab exchange per network"
-                            if world > 1 else "1 GPU")}
+            "parallelism": ("1 GPU" if world == 1 else
+                            f"{world} replicas, one volume per GPU, no collectives" if getattr(a, "mode", "") == "throughput"
+                            else f"patches of one volume sharded over {world} GPUs, one peer-memory slab reduction "
+                                 "per network")}
 
 
 # ------------------------------------------------------------------------------------------------ clocks
@@ -343,11 +350,14 @@ def run_ours(a):
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist_ctx = None
+    throughput = a.mode == "throughput"
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=dev)
         from boa_b200.pipeline import DistContext
-        dist_ctx = DistContext(rank=rank, world_size=world, group=None)
+        # throughput mode: replicas only - NCCL is used for the timing barrier and the max over ranks, never on the
+        # data path
+        dist_ctx = None if throughput else DistContext(rank=rank, world_size=world, group=None)
 
     from boa_b200 import _lib, zoo
     from boa_b200.pipeline import ModelZoo, analyze_from_host, analyze_volume
@@ -356,7 +366,7 @@ def run_ours(a):
     datasets = [291, 292, 293, 294, 295] + ([542, 543] if "bca" in models else [])
     specs = zoo.synthetic_specs((a.patch,) * 3, 32, 320, 6, bca_folds=1 if a.fast_bca else 5, datasets=datasets)
     mz = ModelZoo.from_specs(specs, device=dev, max_batch=a.batch)
-    ct_np = zoo.synthetic_ct(tuple(a.shape), seed=3)
+    ct_np = zoo.synthetic_ct(tuple(a.shape), seed=3 + (rank if throughput else 0))
     ct_host = torch.from_numpy(ct_np).pin_memory()
     ct_dev = ct_host.to(dev)
     spacing = (1.5, 1.5, 1.5)
@@ -388,6 +398,8 @@ def run_ours(a):
         import torch.distributed as dist
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_step = float(ms.item()) / a.steps
+    if throughput:
+        ms_step /= world  # `world` volumes finish per round of steps
 
     # end to end through the public API, host buffers (one untimed call first: the pinned staging buffers of the
     # label maps are allocated on first use)
@@ -404,6 +416,8 @@ def run_ours(a):
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    if throughput:
+        e2e_s /= world
     d2h = sum(int(out[k].numel()) for k in ("total", "body_parts", "body_regions", "tissues", "ct_pfav") if out.get(k) is not None)
     d2h += len(json.dumps(out["total_measurements"])) + len(json.dumps(out["bca_measurements"] or {}))
 
@@ -412,7 +426,7 @@ def run_ours(a):
     maps = {k: getattr(res, k) for k in ("total", "body_parts", "body_regions", "tissues") if getattr(res, k) is not None}
     checksum = {k: f"{zlib.crc32(v.cpu().numpy().tobytes()):08x}" for k, v in maps.items()} if rank == 0 else None
     vs_single = None
-    if world > 1 and rank == 0:
+    if world > 1 and rank == 0 and not throughput:
         single = analyze_volume(ct_dev, spacing, mz, **dict(kw, dist_ctx=None))
         vs_single = {}
         for k, v in maps.items():
@@ -423,6 +437,24 @@ def run_ours(a):
                                             for k in maps}
         del single
     barrier()
+    if a.quick:
+        if rank == 0:
+            n = count_forwards(a)
+            net = mz.get(291, [0], 0.8).networks[0]
+            flop_per_volume = 2.0 * net.macs_per_patch * (n["total"] + n["bca"])
+            print(json.dumps({
+                "metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": a.steps,
+                "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+                "scaling": "weak" if throughput else "strong", "vs_baseline": None, "dtype": "f16", "data": "synthetic",
+                "config": bench_config(a, world), "achieved_tflops_whole_step": flop_per_volume / (ms_step * 1e-3) / 1e12,
+                "e2e": {"value": 1.0 / float(e2e_s.item()), "unit": UNIT, "h2d_bytes_per_step": int(ct_host.numel() * 2),
+                        "d2h_bytes_per_step": int(d2h)},
+                "gpu_launches": launches, "clocks": clocks, "label_checksum": checksum, "vs_single_gpu": vs_single,
+                "stage_seconds": res.timings if res is not None else None}))
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
 
     # ---- roofline of the dominant kernel (dz-folded tcgen05 conv): CUDA events around EVERY launch of every conv
     # kernel inside one more whole-volume step, run right after the timed region (same clocks / power state as the
@@ -498,7 +530,8 @@ def run_ours(a):
         flop_per_volume = 2.0 * net.macs_per_patch * (n["total"] + n["bca"])
         line = {
             "metric": METRIC, "value": 1e3 / ms_step, "unit": UNIT, "n_gpus": world, "steps": a.steps,
-            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong",
+            "warmup": a.warmup, "ms_per_step": ms_step, "higher_is_better": True,
+            "scaling": "weak" if throughput else "strong",
             "vs_baseline": None, "dtype": "f16", "data": "synthetic",
             "config": bench_config(a, world),
             "achieved_tflops_whole_step": flop_per_volume / (ms_step * 1e-3) / 1e12,

@@ -29,13 +29,17 @@
 
 namespace boa {
 
-// WG0: producer warp + MMA warp (+2 idle), WG1: 4 epilogue warps, WG2 + WG3: 8 transform warps.  512 threads start with
-// 128 registers each; the transform warps give theirs to the epilogue: 128 * (128 + 248 + 64 + 64) = 64512 <= 65536.
-constexpr int MMA_THREADS = 512;
-constexpr int REGS_EPI = 248, REGS_XF = 64, XF_THREADS = 256;
-// The transform warps work in XF_GROUPS independent groups that take the ring stages round robin, so that the latency
-// chain of one stage (barrier wait, scale / shift loads, LDS -> math -> STS, proxy fence, arrive) overlaps the next
-// stage's instead of serialising with it.
+// WG0: producer warp + MMA warp (+2 idle), WG1: 4 epilogue warps, WG2: 4 transform warps.  384 threads start with 168
+// registers each; WG0 and WG2 go down to 128 and the epilogue up to 248: 128 * (128 + 248 + 128) = 64512 <= 65536.
+// (Eight transform warps at 64 registers spilled the scale / shift arrays to local memory inside the element loop -
+// ncu source view, profiles/r02_taps_fused_stalls.txt - and ran slower than four warps that keep them in registers.)
+constexpr int MMA_THREADS = 384;
+constexpr int REGS_WG0 = 128, REGS_EPI = 248, REGS_XF = 128, XF_THREADS = 128;
+// The transform warps work in XF_GROUPS independent groups; group g owns the ring SLOTS s with s % XF_GROUPS == g, so
+// that the latency chain of one stage (barrier wait, scale / shift loads, LDS -> math -> STS, proxy fence, arrive)
+// overlaps the next stage's instead of serialising with it.  (Ownership by slot, not by stage number: a group then
+// waits for the phases of a slot in order - a group that could reach phase k + 1 of a slot before phase k has
+// completed would see the parity wait succeed at once.)
 constexpr int XF_GROUPS = 2, XF_GROUP_THREADS = XF_THREADS / XF_GROUPS;
 constexpr int TILE_X = 8, TILE_Y = 16;
 constexpr int XB = TILE_X + 2, YB = TILE_Y + 2, SLAB = XB * YB;  // 180 halo positions per z-plane
@@ -51,6 +55,7 @@ struct ConvMmaParams {
   int out_groups_total, out_group_off;  // the output view (a channel-group slice of a concat buffer, or dense)
   __half* s2d;                          // optional space-to-depth copy of the output (nullptr: none)
   InXform xf;                           // fused normalisation of the input (xf.scale == nullptr: none)
+  int xf_debug;                         // profiling aid (BOA_B200_XF_DEBUG): 1 = transform warps only relay the barrier
   int stages;      // shared-memory ring depth of the A operand (2..4)
   int b_resident;  // 1: the weights of ALL K chunks stay in shared memory for the whole kernel (n_ntiles == 1), the
                    //    ring carries only the activation tiles
@@ -152,6 +157,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
   const uint32_t tbase = *tmem_slot;
 
   if (warp < 4) {
+    reg_dealloc<REGS_WG0>();
     if (warp == 0) {
       // ===================================================================== TMA producer
       if (p.b_resident && elect_one()) {  // n_ntiles == 1: one weight set for every tile of this CTA
@@ -257,7 +263,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
 #pragma unroll
     for (int chunk = 0; chunk < NC / 32; ++chunk) stats_flush(run[chunk], p.stats, lane);
   } else {
-    // ===================================================================== operand transform (warps 8..15)
+    // ===================================================================== operand transform (warps 8..11)
     reg_dealloc<REGS_XF>();
     if (xform) {
       const int grp = (threadIdx.x - 256) / XF_GROUP_THREADS;
@@ -272,14 +278,14 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
         const int ylo = y0 < 0 ? -y0 : 0, yhi = p.H - y0 < YB ? p.H - y0 : YB;
         const int xlo = x0 < 0 ? -x0 : 0, xhi = p.W - x0 < XB ? p.W - x0 : XB;
         for (int kc = 0; kc < p.kc_count; ++kc, ++cnt) {
-          if ((int)(cnt % XF_GROUPS) != grp) continue;
           const int st = (int)(cnt % (uint32_t)nstage);
+          if (st % XF_GROUPS != grp) continue;
           const uint32_t ph = (cnt / (uint32_t)nstage) & 1u;
           const int g0 = 2 * kc;  // first channel group of this K chunk inside the input view
           const int skip = (g0 < p.xf.ident_groups ? 1 : 0) | (g0 + 1 < p.xf.ident_groups ? 2 : 0) |
                            (8 * g0 + 8 >= p.xf.channels ? 2 : 0);
           mbar_wait(&rawfull[st], ph);
-          if (skip != 3)
+          if (skip != 3 && p.xf_debug != 1)
             xform_stage<XB, YB, XF_GROUP_THREADS, 4, 3>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
                                                         p.xf.scale + (size_t)b * p.xf.channels + 16 * kc,
                                                         p.xf.shift + (size_t)b * p.xf.channels + 16 * kc, skip,
@@ -341,6 +347,7 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   p.ntaps = ntaps;
   p.tmap_merged = c8_tmap_merged() ? 1 : 0;
   p.xf = io.xf;
+  p.xf_debug = getenv("BOA_B200_XF_DEBUG") ? atoi(getenv("BOA_B200_XF_DEBUG")) : 0;
   if (io.out.groups < Cout / 8 || (io.s2d && ((src.D | src.H | src.W) & 1)) ||
       (io.xf.scale && (taps_on_k || io.xf.channels != cin_w || cin_w % 16 != 0))) {
     set_error("conv_mma: bad output view / space-to-depth copy / input transform for cin=%d cout=%d", cin_w, Cout);

@@ -28,10 +28,10 @@
 
 namespace boa {
 
-constexpr int TAPS_THREADS = 512;  // four warpgroups (the last two transform), see conv_mma.cu
-constexpr int TREGS_EPI = 248, TREGS_XF = 64, TXF_THREADS = 256;
-// transform warps in groups that take the ring stages round robin (conv_mma.cu): the stages of these kernels are small
-// (a few hundred cycles of MMAs), so four stages are transformed concurrently
+constexpr int TAPS_THREADS = 384;  // three warpgroups, see conv_mma.cu
+constexpr int TREGS_WG0 = 128, TREGS_EPI = 248, TREGS_XF = 128, TXF_THREADS = 128;
+// transform warps in groups that own ring slots (conv_mma.cu): the stages of these kernels are small (a few hundred
+// cycles of MMAs), so four stages are transformed concurrently, one warp each
 constexpr int TXF_GROUPS = 4, TXF_GROUP_THREADS = TXF_THREADS / TXF_GROUPS;
 constexpr int TT_X = 8, TT_Y = 16;
 constexpr int TAPS_MAX_OPS = 27;
@@ -53,6 +53,7 @@ struct TapsParams {
   int out_groups_total, out_group_off, Cout;
   __half* s2d;   // optional space-to-depth copy of a conv output (nullptr: none)
   InXform xf;    // fused normalisation of the input (xf.scale == nullptr: none)
+  int xf_debug;  // profiling aid (BOA_B200_XF_DEBUG): 1 = transform warps only relay the barrier
   int halo;      // box = tile + halo per axis: 2 (3x3x3 stride 1), 1 (stride 2 on the s2d tensor), 0 (transposed)
   int stages;
   int tmap_merged;  // tensor map built with the (channel, x) dimensions merged (tmap.cuh)
@@ -110,6 +111,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
   const uint32_t buf_cols = (uint32_t)(p.zt * NC);  // <= 256: two accumulator buffers
 
   if (warp < 4) {
+  reg_dealloc<TREGS_WG0>();
   if (warp == 0) {
     // ===================================================================== TMA producer
     uint32_t it = 0;
@@ -194,8 +196,8 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
         const int ylo = y0 < 0 ? -y0 : 0, yhi = p.H - y0 < p.box_y ? p.H - y0 : p.box_y;
         const int xlo = x0 < 0 ? -x0 : 0, xhi = p.W - x0 < p.box_x ? p.W - x0 : p.box_x;
         for (int kc = 0; kc < p.kc_count; ++kc, ++cnt) {
-          if ((int)(cnt % TXF_GROUPS) != grp) continue;
           const int st = (int)(cnt % (uint32_t)nstage);
+          if (st % TXF_GROUPS != grp) continue;
           const uint32_t ph = (cnt / (uint32_t)nstage) & 1u;
           // channels of this K chunk: the stride-2 gather walks the 8 phases of the space-to-depth tensor, each
           // holding every channel (chunk index inside the phase = kc % chunks_per_class)
@@ -204,7 +206,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
           const int skip = (g0 < p.xf.ident_groups ? 1 : 0) | (g0 + 1 < p.xf.ident_groups ? 2 : 0) |
                            (8 * g0 + 8 >= p.xf.channels ? 2 : 0);
           mbar_wait(&rawfull[st], ph);
-          if (skip != 3) {
+          if (skip != 3 && p.xf_debug != 1) {
             uint8_t* sa = smem + (size_t)st * stage_bytes;
             const float* sc = p.xf.scale + (size_t)b * p.xf.channels + 16 * cc;
             const float* sh = p.xf.shift + (size_t)b * p.xf.channels + 16 * cc;
@@ -326,6 +328,7 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
   p.out_groups_total = dst.groups_total; p.out_group_off = dst.group_off;
   p.s2d = kind == TAPS_TCONV2 ? nullptr : io.s2d;
   p.xf = io.xf;
+  p.xf_debug = getenv("BOA_B200_XF_DEBUG") ? atoi(getenv("BOA_B200_XF_DEBUG")) : 0;
   p.halo = halo;
   if (io.xf.scale && (io.xf.channels != cin_w || cin_w % 16 != 0)) {
     set_error("conv_taps: fused input normalisation needs Cin %% 16 == 0 (cin=%d, scale row %d)", cin_w, io.xf.channels);
