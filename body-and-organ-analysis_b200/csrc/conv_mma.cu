@@ -29,12 +29,15 @@
 
 namespace boa {
 
-// WG0: producer warp + MMA warp (+2 idle), WG1: 4 epilogue warps, WG2: 4 transform warps.  384 threads start with 168
-// registers each; WG0 and WG2 go down to 128 and the epilogue up to 248: 128 * (128 + 248 + 128) = 64512 <= 65536.
-// (Eight transform warps at 64 registers spilled the scale / shift arrays to local memory inside the element loop -
-// ncu source view, profiles/r02_taps_fused_stalls.txt - and ran slower than four warps that keep them in registers.)
-constexpr int MMA_THREADS = 384;
-constexpr int REGS_WG0 = 128, REGS_EPI = 248, REGS_XF = 128, XF_THREADS = 128;
+// WG0: producer warp + MMA warp (+2 idle), WG1: 4 epilogue warps, WG2 + WG3: 8 transform warps.  512 threads start with
+// 128 registers each and re-partition them with setmaxnreg.  (Eight transform warps at 64 registers spilled the scale /
+// shift arrays to local memory inside the element loop - ncu source view, profiles/r02_taps_fused_stalls.txt; four
+// warps at 128 registers did not spill but had too little issue bandwidth.)
+// Measured (B200, batch 8, tools/perf_probe.py): the transform is bound by instruction issue of its own warps (~36 ALU
+// instructions per 16-byte element, 1.8x the tensor's elements because of the halo), so it wants as many warps as the
+// register file allows: 16 warps per CTA = 128 * (96 + 224 + 96 + 96) = 65536 registers.
+constexpr int MMA_THREADS = 512;
+constexpr int REGS_WG0 = 96, REGS_EPI = 224, REGS_XF = 96, XF_THREADS = 256;
 // The transform warps work in XF_GROUPS independent groups; group g owns the ring SLOTS s with s % XF_GROUPS == g, so
 // that the latency chain of one stage (barrier wait, scale / shift loads, LDS -> math -> STS, proxy fence, arrive)
 // overlaps the next stage's instead of serialising with it.  (Ownership by slot, not by stage number: a group then
@@ -263,7 +266,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
 #pragma unroll
     for (int chunk = 0; chunk < NC / 32; ++chunk) stats_flush(run[chunk], p.stats, lane);
   } else {
-    // ===================================================================== operand transform (warps 8..11)
+    // ===================================================================== operand transform (warps 8..15)
     reg_dealloc<REGS_XF>();
     if (xform) {
       const int grp = (threadIdx.x - 256) / XF_GROUP_THREADS;

@@ -28,10 +28,10 @@
 
 namespace boa {
 
-constexpr int TAPS_THREADS = 384;  // three warpgroups, see conv_mma.cu
-constexpr int TREGS_WG0 = 128, TREGS_EPI = 248, TREGS_XF = 128, TXF_THREADS = 128;
+constexpr int TAPS_THREADS = 512;  // four warpgroups (the last two transform), see conv_mma.cu
+constexpr int TREGS_WG0 = 96, TREGS_EPI = 224, TREGS_XF = 96, TXF_THREADS = 256;
 // transform warps in groups that own ring slots (conv_mma.cu): the stages of these kernels are small (a few hundred
-// cycles of MMAs), so four stages are transformed concurrently, one warp each
+// cycles of MMAs), so four stages are transformed concurrently, two warps each
 constexpr int TXF_GROUPS = 4, TXF_GROUP_THREADS = TXF_THREADS / TXF_GROUPS;
 constexpr int TT_X = 8, TT_Y = 16;
 constexpr int TAPS_MAX_OPS = 27;
@@ -181,7 +181,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
     __syncwarp();
   }
   } else if (warp >= 8) {
-    // ===================================================================== operand transform (warps 8..11)
+    // ===================================================================== operand transform (warps 8..15)
     reg_dealloc<TREGS_XF>();
     if (xform) {
       const int grp = (threadIdx.x - 256) / TXF_GROUP_THREADS;
