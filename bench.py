@@ -179,7 +179,7 @@ def cpu_reference_sample(a, n_patches: int = 2) -> dict:
 
 
 # ------------------------------------------------------------------------------------------------ GPU baseline
-def gpu_reference_sample(a, dev, cpu: dict | None, n_patches: int = 16) -> dict | None:
+def gpu_reference_sample(a, dev, cpu: dict | None, n_patches: int = 24) -> dict | None:
     """The "reference's single-GPU PyTorch/nnU-Net path" of BASELINE.json, restated on stock PyTorch (baseline/): the
     torch.nn PlainConvUNet under torch.autocast(fp16) with cudnn.benchmark and the reference's loop (producer thread,
     fp16 accumulators, three elementwise launches per patch, final divide + isinf), then what the reference does with
@@ -205,17 +205,24 @@ def gpu_reference_sample(a, dev, cpu: dict | None, n_patches: int = 16) -> dict 
         # warm-up: cuDNN autotuning of every layer shape happens on the first patches
         reference_loop.predict_sliding_window_return_logits(net, data, arch["patch_size"], step, dev, patch_range=(0, 3))
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        logits = reference_loop.predict_sliding_window_return_logits(net, data, arch["patch_size"], step, dev,
-                                                                     patch_range=(0, n_patches))
-        torch.cuda.synchronize()
-        t_loop = time.perf_counter() - t0
+        t_loop = None
+        for _ in range(2):  # the faster of two runs: the baseline gets the benefit of the doubt
+            logits = None
+            t0 = time.perf_counter()
+            logits = reference_loop.predict_sliding_window_return_logits(net, data, arch["patch_size"], step, dev,
+                                                                         patch_range=(0, n_patches))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            t_loop = dt if t_loop is None else min(t_loop, dt)
         # the loop's fixed part (allocation of the accumulators, the divide and the isinf scan over the whole volume)
         # is inside t_loop once; separate it with a second, patch-free call
-        t0 = time.perf_counter()
-        reference_loop.predict_sliding_window_return_logits(net, data, arch["patch_size"], step, dev, patch_range=(0, 1))
-        torch.cuda.synchronize()
-        t_one = time.perf_counter() - t0
+        t_one = None
+        for _ in range(2):
+            t0 = time.perf_counter()
+            reference_loop.predict_sliding_window_return_logits(net, data, arch["patch_size"], step, dev, patch_range=(0, 1))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            t_one = dt if t_one is None else min(t_one, dt)
         t_patch = (t_loop - t_one) / (n_patches - 1)
         t_fixed = max(t_one - t_patch, 0.0)
         t0 = time.perf_counter()

@@ -43,7 +43,7 @@ constexpr int REGS_WG0 = 96, REGS_EPI = 224, REGS_XF = 96, XF_THREADS = 256;
 // overlaps the next stage's instead of serialising with it.  (Ownership by slot, not by stage number: a group then
 // waits for the phases of a slot in order - a group that could reach phase k + 1 of a slot before phase k has
 // completed would see the parity wait succeed at once.)
-constexpr int XF_GROUPS = 2, XF_GROUP_THREADS = XF_THREADS / XF_GROUPS;
+// The number of groups divides the ring depth (every group gets the same share of the stages): p.xf_groups.
 constexpr int TILE_X = 8, TILE_Y = 16;
 constexpr int XB = TILE_X + 2, YB = TILE_Y + 2, SLAB = XB * YB;  // 180 halo positions per z-plane
 
@@ -58,6 +58,7 @@ struct ConvMmaParams {
   int out_groups_total, out_group_off;  // the output view (a channel-group slice of a concat buffer, or dense)
   __half* s2d;                          // optional space-to-depth copy of the output (nullptr: none)
   InXform xf;                           // fused normalisation of the input (xf.scale == nullptr: none)
+  int xf_groups;                        // transform warp groups (divides `stages`)
   int xf_debug;                         // profiling aid (BOA_B200_XF_DEBUG): 1 = transform warps only relay the barrier
   int stages;      // shared-memory ring depth of the A operand (2..4)
   int b_resident;  // 1: the weights of ALL K chunks stay in shared memory for the whole kernel (n_ntiles == 1), the
@@ -138,7 +139,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < 4; ++i) {
-      mbar_init(&full[i], xform ? XF_GROUP_THREADS / 32 : 1);
+      mbar_init(&full[i], xform ? XF_THREADS / 32 / p.xf_groups : 1);
       mbar_init(&empty[i], 1);
       mbar_init(&rawfull[i], 1);
     }
@@ -269,8 +270,9 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
     // ===================================================================== operand transform (warps 8..15)
     reg_dealloc<REGS_XF>();
     if (xform) {
-      const int grp = (threadIdx.x - 256) / XF_GROUP_THREADS;
-      const int tid = (threadIdx.x - 256) % XF_GROUP_THREADS;
+      const int gthreads = XF_THREADS / p.xf_groups;
+      const int grp = (threadIdx.x - 256) / gthreads;
+      const int tid = (threadIdx.x - 256) % gthreads;
       uint32_t cnt = 0;  // ring stage counter over (tile, kc) - the same sequence the producer and the MMA warp walk
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, b, tz, ty, tx;
@@ -282,17 +284,16 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
         const int xlo = x0 < 0 ? -x0 : 0, xhi = p.W - x0 < XB ? p.W - x0 : XB;
         for (int kc = 0; kc < p.kc_count; ++kc, ++cnt) {
           const int st = (int)(cnt % (uint32_t)nstage);
-          if (st % XF_GROUPS != grp) continue;
+          if (st % p.xf_groups != grp) continue;
           const uint32_t ph = (cnt / (uint32_t)nstage) & 1u;
           const int g0 = 2 * kc;  // first channel group of this K chunk inside the input view
           const int skip = (g0 < p.xf.ident_groups ? 1 : 0) | (g0 + 1 < p.xf.ident_groups ? 2 : 0) |
                            (8 * g0 + 8 >= p.xf.channels ? 2 : 0);
           mbar_wait(&rawfull[st], ph);
           if (skip != 3 && p.xf_debug != 1)
-            xform_stage<XB, YB, XF_GROUP_THREADS, 4, 3>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
-                                                        p.xf.scale + (size_t)b * p.xf.channels + 16 * kc,
-                                                        p.xf.shift + (size_t)b * p.xf.channels + 16 * kc, skip,
-                                                        p.xf.slope, tid);
+            xform_stage<XB, YB, 4, 3>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
+                                      p.xf.scale + (size_t)b * p.xf.channels + 16 * kc,
+                                      p.xf.shift + (size_t)b * p.xf.channels + 16 * kc, skip, p.xf.slope, tid, gthreads);
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[st]);
@@ -413,6 +414,7 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
     return nullptr;
   }
   p.stages = stages;
+  p.xf_groups = stages % 2 == 0 ? 2 : 1;
   pl->smem = fixed + (size_t)stages * stage + 768;
   cudaError_t e = cudaSuccess;
   for (const void* fn : {(const void*)conv3_fold_kernel<64>, (const void*)conv3_fold_kernel<32>}) {

@@ -1,14 +1,16 @@
 // tcgen05 implicit GEMM over an explicit per-K-chunk tap list, for sm_100a.
 //
-// Covers the convolution shapes of PlainConvUNet that the dz-folded kernel (conv_mma.cu) does not:
-//   * 3x3x3 STRIDE-2 convs (first conv of encoder stages 1..n): run as a stride-1 gather over the space-to-depth copy
-//     of the input ([B][8 phases][C/8][D/2][H/2][W/2][8], written by the producer's normalise pass).  Output voxel o
-//     reads input 2o-1, 2o, 2o+1 per axis = (odd phase, o-1), (even phase, o), (odd phase, o): a K chunk of 16
-//     channels belongs to one phase and only carries the 1, 2, 4 or 8 taps that phase can serve - 27 in total, no
-//     wasted MACs.
-//   * ConvTranspose3d k=2,s=2 (decoder up-sampling): a single tap, the 8 output phases sit on N
-//     (n = phase * Cout + co) and the epilogue scatters them into the concat buffer.
-//   * plain 3x3x3 stride 1 (27 taps per chunk) as an independent cross-check of the folded kernel.
+// Covers the convolution shapes of PlainConvUNet that the dz-folded kernel (conv_mma.cu) does not.  Per axis the
+// kernel size is 1 or 3 and the stride 1 or 2 (nnU-Net plans for anisotropic data - the 5 mm body-composition models -
+// carry [1,3,3] kernels and [1,2,2] pools, _external/body_composition_analysis/tasks.py:15-48 + plans_handler.py:36-97):
+//   * STRIDED convs (first conv of encoder stages 1..n): a stride-1 gather over the space-to-depth copy of the input
+//     ([B][phases][C/8][D/sz][H/sy][W/sx][8], phases = sz*sy*sx, written by the producing conv's epilogue).  On a
+//     stride-2 axis output o reads input 2o-1, 2o, 2o+1 = (odd phase, o-1), (even phase, o), (odd phase, o): a K chunk
+//     of 16 channels belongs to one phase and only carries the taps that phase can serve - no wasted MACs.
+//   * ConvTranspose3d kernel = stride in {1,2}^2 x {2} (decoder up-sampling): a single tap, the output phases sit on N
+//     and the epilogue scatters them into the concat buffer.
+//   * stride-1 convs with kernels other than 3x3x3 ([1,3,3]: 9 taps per chunk), and plain 3x3x3 (27 taps per chunk)
+//     as an independent cross-check of the folded kernel.
 // Replaces the cuDNN calls behind nn.Conv3d / nn.ConvTranspose3d of dynamic_network_architectures' PlainConvEncoder /
 // UNetDecoder, invoked at _external/nnunetv2/inference/predict_from_raw_data.py:543.
 //
@@ -32,11 +34,13 @@ constexpr int TAPS_THREADS = 512;  // four warpgroups (the last two transform), 
 constexpr int TREGS_WG0 = 96, TREGS_EPI = 224, TREGS_XF = 96, TXF_THREADS = 256;
 // transform warps in groups that own ring slots (conv_mma.cu): the stages of these kernels are small (a few hundred
 // cycles of MMAs), so four stages are transformed concurrently, two warps each
-constexpr int TXF_GROUPS = 4, TXF_GROUP_THREADS = TXF_THREADS / TXF_GROUPS;
+// The number of groups (p.xf_groups) divides the ring depth, which is trimmed to a multiple of four for that.
 constexpr int TT_X = 8, TT_Y = 16;
 constexpr int TAPS_MAX_OPS = 27;
 constexpr int TAPS_MAX_STAGES = 12;  // smem ring depth: small stages (transposed conv, deep layers) prefetch several tiles ahead
-constexpr int TAB_STRIDE = 32;  // ints per class-table entry: [0] n_ops, [1] ops of all earlier chunks, [2..] a_off
+constexpr int TAB_STRIDE = 32;  // ints per class-table entry: [0] n_ops, [1] ops of all earlier chunks, [2..28] a_off,
+                                //                             [30] first channel group of the class's phase
+constexpr int TAB_GBASE = 30;
 
 struct TapsParams {
   const __half* bpacked;
@@ -47,12 +51,15 @@ struct TapsParams {
   int n_classes, chunks_per_class;
   int kind;
   int B, kc_count, Ntotal, D, H, W, zt;
-  int box_x, box_y, box_z, org;
+  int box_x, box_y, box_z, org_x, org_y, org_z;
+  int tsz, tsy;  // transposed conv: output phases along z and y (1 or 2; x is always 2)
   int tiles_x, tiles_y, tiles_z, n_ntiles, total_tiles;
   int in_groups_total, in_group_off;
   int out_groups_total, out_group_off, Cout;
   __half* s2d;   // optional space-to-depth copy of a conv output (nullptr: none)
+  int s2d_stride[3];  // strides (z, y, x) of the conv that will read the copy
   InXform xf;    // fused normalisation of the input (xf.scale == nullptr: none)
+  int xf_groups; // transform warp groups (divides `stages`)
   int xf_debug;  // profiling aid (BOA_B200_XF_DEBUG): 1 = transform warps only relay the barrier
   int halo;      // box = tile + halo per axis: 2 (3x3x3 stride 1), 1 (stride 2 on the s2d tensor), 0 (transposed)
   int stages;
@@ -89,7 +96,7 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < TAPS_MAX_STAGES; ++i) {
-      mbar_init(&full[i], xform ? TXF_GROUP_THREADS / 32 : 1);
+      mbar_init(&full[i], xform ? TXF_THREADS / 32 / p.xf_groups : 1);
       mbar_init(&empty[i], 1);
       mbar_init(&rawfull[i], 1);
     }
@@ -131,8 +138,9 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
           const uint32_t bbytes = (uint32_t)n_ops * NC * 32u;
           uint64_t* ready = xform ? &rawfull[st] : &full[st];
           mbar_arrive_expect_tx(ready, p.a_tx_bytes + bbytes);
-          tma_load_c8(sa, &tmapA, ready, p.tmap_merged, tx * TT_X + p.org, ty * TT_Y + p.org, tz * p.zt + p.org,
-                      b * p.in_groups_total + p.in_group_off + 2 * kc);
+          tma_load_c8(sa, &tmapA, ready, p.tmap_merged, tx * TT_X + p.org_x, ty * TT_Y + p.org_y, tz * p.zt + p.org_z,
+                      b * p.in_groups_total + p.in_group_off + __ldg(p.table + cls * TAB_STRIDE + TAB_GBASE) +
+                          2 * (kc - cls * p.chunks_per_class));
           bulk_load(sa + p.a_bytes,
                     reinterpret_cast<const uint8_t*>(p.bpacked) + (size_t)nt * p.b_nt_bytes + (size_t)b_off * 16u,
                     bbytes, ready);
@@ -184,20 +192,21 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
     // ===================================================================== operand transform (warps 8..15)
     reg_dealloc<TREGS_XF>();
     if (xform) {
-      const int grp = (threadIdx.x - 256) / TXF_GROUP_THREADS;
-      const int tid = (threadIdx.x - 256) % TXF_GROUP_THREADS;
+      const int gthreads = TXF_THREADS / p.xf_groups;
+      const int grp = (threadIdx.x - 256) / gthreads;
+      const int tid = (threadIdx.x - 256) % gthreads;
       uint32_t cnt = 0;  // ring stage counter over (tile, kc)
       for (int tile = blockIdx.x; tile < p.total_tiles; tile += gridDim.x) {
         int nt, b, tz, ty, tx;
         taps_decode_tile(tile, p, nt, b, tz, ty, tx);
         // box index i <-> tensor coordinate t * T + org + i: the in-volume part of the box
-        const int z0 = tz * p.zt + p.org, y0 = ty * TT_Y + p.org, x0 = tx * TT_X + p.org;
+        const int z0 = tz * p.zt + p.org_z, y0 = ty * TT_Y + p.org_y, x0 = tx * TT_X + p.org_x;
         const int zlo = z0 < 0 ? -z0 : 0, zhi = p.D - z0 < p.box_z ? p.D - z0 : p.box_z;
         const int ylo = y0 < 0 ? -y0 : 0, yhi = p.H - y0 < p.box_y ? p.H - y0 : p.box_y;
         const int xlo = x0 < 0 ? -x0 : 0, xhi = p.W - x0 < p.box_x ? p.W - x0 : p.box_x;
         for (int kc = 0; kc < p.kc_count; ++kc, ++cnt) {
           const int st = (int)(cnt % (uint32_t)nstage);
-          if (st % TXF_GROUPS != grp) continue;
+          if (st % p.xf_groups != grp) continue;
           const uint32_t ph = (cnt / (uint32_t)nstage) & 1u;
           // channels of this K chunk: the stride-2 gather walks the 8 phases of the space-to-depth tensor, each
           // holding every channel (chunk index inside the phase = kc % chunks_per_class)
@@ -210,10 +219,10 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
             uint8_t* sa = smem + (size_t)st * stage_bytes;
             const float* sc = p.xf.scale + (size_t)b * p.xf.channels + 16 * cc;
             const float* sh = p.xf.shift + (size_t)b * p.xf.channels + 16 * cc;
-            // box_z <= 6: z phases of 2, at most 3 planes per item
-            if (p.halo == 2) xform_stage<TT_X + 2, TT_Y + 2, TXF_GROUP_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
-            else if (p.halo == 1) xform_stage<TT_X + 1, TT_Y + 1, TXF_GROUP_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
-            else xform_stage<TT_X, TT_Y, TXF_GROUP_THREADS, 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid);
+            // z phases of 4, at most 3 planes per item (box_z <= 10)
+            if (p.halo == 2) xform_stage<TT_X + 2, TT_Y + 2, 4, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid, gthreads);
+            else if (p.halo == 1) xform_stage<TT_X + 1, TT_Y + 1, 4, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid, gthreads);
+            else xform_stage<TT_X, TT_Y, 4, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid, gthreads);
           }
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
           __syncwarp();
@@ -240,17 +249,17 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
 #pragma unroll
       for (int chunk = 0; chunk < NC / 32; ++chunk) {
         const int nbase = nt * NC + chunk * 32;  // first GEMM column of this 32-wide strip
-        if (p.kind != TAPS_TCONV2) {
+        if (p.kind != TAPS_TCONV) {
           const size_t zstride = (size_t)p.H * p.W, gstride = (size_t)p.D * zstride;
           uint4* dst = reinterpret_cast<uint4*>(p.out) +
                        ((((size_t)b * p.out_groups_total + p.out_group_off + (nbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
           conv_epilogue_strip(tlane + chunk * 32, NC, p.zt, p.bias + nbase, rowvalid, tz * p.zt, p.D, dst, zstride,
                               gstride, lane, b * p.Cout + nbase, run[chunk], p.stats,
-                              s2d_dst(p.s2d, b, p.Cout / 8, nbase >> 3, p.D, p.H, p.W, y, x));
+                              s2d_dst(p.s2d, p.s2d_stride, b, p.Cout / 8, nbase >> 3, p.D, p.H, p.W, y, x));
         } else {
-          // transposed conv: GEMM column n = (((pz*2+py) * Cout/8 + cg) * 2 + px) * 8 + e : the two x-phases of a
+          // transposed conv: GEMM column n = (((pz*tsy+py) * Cout/8 + cg) * 2 + px) * 8 + e : the two x-phases of a
           // channel group are neighbours on N, so a thread writes 32 contiguous bytes (xo = 2x, 2x+1) per group
-          const int Do = 2 * p.D, Ho = 2 * p.H, Wo = 2 * p.W;
+          const int Do = p.tsz * p.D, Ho = p.tsy * p.H, Wo = 2 * p.W;
           const int cgroups = p.Cout / 8;
           float bs[32];
           uint4* d[2];
@@ -263,12 +272,12 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
             const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
             for (int e = 0; e < 8; ++e) { bs[16 * jj + e] = bb[e]; bs[16 * jj + 8 + e] = bb[e]; }
-            const int zo = 2 * (tz * p.zt) + (pzpy >> 1), yo = 2 * y + (pzpy & 1);
+            const int zo = p.tsz * (tz * p.zt) + pzpy / p.tsy, yo = p.tsy * y + pzpy % p.tsy;
             d[jj] = reinterpret_cast<uint4*>(p.out) +
                     ((((size_t)b * p.out_groups_total + p.out_group_off + cg) * Do + zo) * Ho + yo) * Wo + 2 * x;
           }
           tconv_epilogue_strip(tlane + chunk * 32, NC, p.zt, bs, rowvalid, tz * p.zt, p.D, d[0], d[1],
-                               (size_t)2 * Ho * Wo);
+                               (size_t)p.tsz * Ho * Wo);
         }
       }
       tc_fence_before();
@@ -297,27 +306,47 @@ struct ConvTapsPlan {
 
 static inline uint32_t round_up(uint32_t v, uint32_t a) { return (v + a - 1) / a * a; }
 
-ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float* h_bias, int cin_w, int Cout,
-                                    const ActView& src, int B, const ConvIO& io, double* d_stats) {
+ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const TapsGeom& geo, const float* h_w, const float* h_bias,
+                                    int cin_w, int Cout, const ActView& src, int B, const ConvIO& io, double* d_stats) {
   const ActView& dst = io.out;
   const int cin_padded = (cin_w + 15) / 16 * 16;
-  const int Ntotal = kind == TAPS_TCONV2 ? 8 * Cout : Cout;
-  const int src_cin_groups = kind == TAPS_CONV3_S2 ? src.groups / 8 : src.groups;  // groups per phase for s2d
-  if (Cout % 8 || Ntotal % 64 || cin_padded / 8 > src_cin_groups || (kind == TAPS_CONV3_S2 && cin_w % 16)) {
-    set_error("conv_taps: unsupported channels kind=%d cin=%d cout=%d src groups=%d", (int)kind, cin_w, Cout,
-              src.groups);
+  const int* ks = geo.ks;
+  const int* st = geo.stride;
+  for (int a = 0; a < 3; ++a)
+    if ((ks[a] != 1 && ks[a] != 3 && kind == TAPS_CONV) || (st[a] != 1 && st[a] != 2)) {
+      set_error("conv_taps: kernel sizes must be 1 or 3 and strides 1 or 2");
+      return nullptr;
+    }
+  const int phases = kind == TAPS_CONV ? st[0] * st[1] * st[2] : 1;
+  const int Ntotal = kind == TAPS_TCONV ? st[0] * st[1] * st[2] * Cout : Cout;
+  const int src_cin_groups = src.groups / phases;  // groups per phase of a space-to-depth source
+  const bool sym = kind == TAPS_TCONV ? (st[2] == 2) : (ks[1] == ks[2] && st[1] == st[2]);
+  if (Cout % 8 || Ntotal % 32 || cin_padded / 8 > src_cin_groups || (phases > 1 && cin_w % 16) || !sym ||
+      src.groups % phases) {
+    set_error("conv_taps: unsupported shape kind=%d cin=%d cout=%d src groups=%d kernel %d%d%d stride %d%d%d", (int)kind,
+              cin_w, Cout, src.groups, ks[0], ks[1], ks[2], st[0], st[1], st[2]);
     return nullptr;
   }
   ConvTapsPlan* pl = new ConvTapsPlan();
-  const int NC = (kind != TAPS_CONV3_S1 && Ntotal % 128 == 0) ? 128 : 64;
+  const int NC = Ntotal % 64 ? 32 : ((Ntotal % 128 == 0 && (kind == TAPS_TCONV || phases > 1)) ? 128 : 64);
   pl->nc = NC;
   TapsParams& p = pl->prm;
   p.kind = (int)kind;
   p.zt = 256 / NC;  // two TMEM accumulator buffers of zt*NC <= 256 columns
   p.B = B; p.Ntotal = Ntotal; p.Cout = Cout; p.D = src.D; p.H = src.H; p.W = src.W;
-  const int halo = kind == TAPS_CONV3_S1 ? 2 : (kind == TAPS_CONV3_S2 ? 1 : 0);
-  p.org = kind == TAPS_TCONV2 ? 0 : -1;
-  p.box_x = TT_X + halo; p.box_y = TT_Y + halo; p.box_z = p.zt + halo;
+  // per axis (z, y, x): halo of the box and where it starts relative to the tile.  Kernel 3: one position before the
+  // tile; on a stride-2 axis the space-to-depth phases need one extra position, on a stride-1 axis two.
+  int halo[3], org[3];
+  for (int a = 0; a < 3; ++a) {
+    const bool k3 = kind == TAPS_CONV && ks[a] == 3;
+    halo[a] = k3 ? (st[a] == 2 ? 1 : 2) : 0;
+    org[a] = k3 ? -1 : 0;
+  }
+  p.org_z = org[0]; p.org_y = org[1]; p.org_x = org[2];
+  p.box_x = TT_X + halo[2]; p.box_y = TT_Y + halo[1]; p.box_z = p.zt + halo[0];
+  p.halo = halo[2];  // == halo[1]: the transform is instantiated per in-plane box size
+  p.tsz = kind == TAPS_TCONV ? st[0] : 1;
+  p.tsy = kind == TAPS_TCONV ? st[1] : 1;
   p.tiles_x = (src.W + TT_X - 1) / TT_X;
   p.tiles_y = (src.H + TT_Y - 1) / TT_Y;
   p.tiles_z = (src.D + p.zt - 1) / p.zt;
@@ -326,69 +355,77 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
   p.in_groups_total = src.groups_total; p.in_group_off = src.group_off;
   p.out = dst.base;
   p.out_groups_total = dst.groups_total; p.out_group_off = dst.group_off;
-  p.s2d = kind == TAPS_TCONV2 ? nullptr : io.s2d;
+  p.s2d = kind == TAPS_TCONV ? nullptr : io.s2d;
+  for (int a = 0; a < 3; ++a) p.s2d_stride[a] = io.s2d_stride[a];
   p.xf = io.xf;
   p.xf_debug = getenv("BOA_B200_XF_DEBUG") ? atoi(getenv("BOA_B200_XF_DEBUG")) : 0;
-  p.halo = halo;
   if (io.xf.scale && (io.xf.channels != cin_w || cin_w % 16 != 0)) {
     set_error("conv_taps: fused input normalisation needs Cin %% 16 == 0 (cin=%d, scale row %d)", cin_w, io.xf.channels);
     conv_taps_plan_destroy(pl);
     return nullptr;
   }
-  p.stats = kind == TAPS_TCONV2 ? nullptr : d_stats;
+  p.stats = kind == TAPS_TCONV ? nullptr : d_stats;
 
-  // ---- chunk table + packed weights
-  const int cpp = cin_padded / 16;                                   // K chunks per phase (or per tensor)
-  p.kc_count = kind == TAPS_CONV3_S2 ? 8 * cpp : cpp;
-  p.chunks_per_class = cpp;
-  p.n_classes = p.kc_count / cpp;  // 8 phases for the stride-2 gather, 1 otherwise
-  std::vector<int32_t> table((size_t)p.n_classes * TAB_STRIDE, 0);
+  // ---- chunk table + packed weights.  A class = one phase of the source that serves at least one tap.
+  const int cpp = cin_padded / 16;  // K chunks per phase (or per tensor)
+  const int k3 = ks[0] * ks[1] * ks[2];
   struct Op { int a_off, tap; };
-  std::vector<std::vector<Op>> ops(p.kc_count);
-  int max_ops = 0;
-  size_t total_ops = 0;
-  for (int kc = 0; kc < p.kc_count; ++kc) {
-    std::vector<Op>& o = ops[kc];
-    if (kind == TAPS_CONV3_S1) {
-      for (int t = 0; t < 27; ++t) {
-        const int dz = t / 9, dy = (t / 3) % 3, dx = t % 3;
-        o.push_back({(dz * p.box_y + dy) * p.box_x + dx, t});
+  struct Class { int gbase; std::vector<Op> ops; };
+  std::vector<Class> classes;
+  if (kind == TAPS_TCONV) {
+    classes.push_back({0, {{0, 0}}});
+  } else {
+    // per axis: (box offset, kernel tap) pairs a phase can serve
+    auto opts = [&](int a, int bit, int (&off)[3], int (&d)[3]) {
+      if (ks[a] == 1) {
+        if (st[a] == 2 && bit) return 0;  // a stride-2 axis with kernel 1 reads the even phase only
+        off[0] = 0; d[0] = 0;
+        return 1;
       }
-    } else if (kind == TAPS_CONV3_S2) {
-      const int phs = kc / cpp, pz = phs >> 2, py = (phs >> 1) & 1, px = phs & 1;
-      // per axis: even phase serves tap d=1 at box offset 1; odd phase serves d=0 at offset 0 and d=2 at offset 1
-      auto opts = [](int bit, int (&off)[2], int (&d)[2]) {
-        if (bit) { off[0] = 0; d[0] = 0; off[1] = 1; d[1] = 2; return 2; }
-        off[0] = 1; d[0] = 1; return 1;
-      };
-      int oz[2], dzv[2], oy[2], dyv[2], ox[2], dxv[2];
-      const int nz = opts(pz, oz, dzv), ny = opts(py, oy, dyv), nx = opts(px, ox, dxv);
+      if (st[a] == 1) { for (int i = 0; i < 3; ++i) { off[i] = i; d[i] = i; } return 3; }
+      if (bit) { off[0] = 0; d[0] = 0; off[1] = 1; d[1] = 2; return 2; }
+      off[0] = 1; d[0] = 1;
+      return 1;
+    };
+    for (int phs = 0; phs < phases; ++phs) {
+      const int px = phs % st[2], py = (phs / st[2]) % st[1], pz = phs / (st[2] * st[1]);
+      int oz[3], dzv[3], oy[3], dyv[3], ox[3], dxv[3];
+      const int nz = opts(0, pz, oz, dzv), ny = opts(1, py, oy, dyv), nx = opts(2, px, ox, dxv);
+      Class c;
+      c.gbase = phs * src_cin_groups;
       for (int a = 0; a < nz; ++a)
         for (int bq = 0; bq < ny; ++bq)
-          for (int c = 0; c < nx; ++c)
-            o.push_back({(oz[a] * p.box_y + oy[bq]) * p.box_x + ox[c], dzv[a] * 9 + dyv[bq] * 3 + dxv[c]});
-    } else {
-      o.push_back({0, 0});
+          for (int cx = 0; cx < nx; ++cx)
+            c.ops.push_back({(oz[a] * p.box_y + oy[bq]) * p.box_x + ox[cx], (dzv[a] * ks[1] + dyv[bq]) * ks[2] + dxv[cx]});
+      if (!c.ops.empty()) classes.push_back(c);
     }
-    if (kc % cpp == 0) {
-      const size_t cls = (size_t)(kc / cpp);
-      table[cls * TAB_STRIDE] = (int)o.size();
-      table[cls * TAB_STRIDE + 1] = (int)total_ops;
-      for (size_t i = 0; i < o.size(); ++i) table[cls * TAB_STRIDE + 2 + i] = o[i].a_off;
-    }
+  }
+  p.n_classes = (int)classes.size();
+  p.chunks_per_class = cpp;
+  p.kc_count = p.n_classes * cpp;
+  std::vector<int32_t> table((size_t)p.n_classes * TAB_STRIDE, 0);
+  int max_ops = 0;
+  size_t total_ops = 0;
+  for (int c = 0; c < p.n_classes; ++c) {
+    const std::vector<Op>& o = classes[c].ops;
+    table[(size_t)c * TAB_STRIDE] = (int)o.size();
+    table[(size_t)c * TAB_STRIDE + 1] = (int)total_ops;
+    for (size_t i = 0; i < o.size(); ++i) table[(size_t)c * TAB_STRIDE + 2 + i] = o[i].a_off;
+    table[(size_t)c * TAB_STRIDE + TAB_GBASE] = classes[c].gbase;
     max_ops = std::max(max_ops, (int)o.size());
-    total_ops += o.size();
+    total_ops += o.size() * cpp;
   }
   const size_t nt_halves = total_ops * NC * 16;  // [op][kchunk 2][NC rows][8]
   p.b_nt_bytes = (uint32_t)(nt_halves * 2);
   std::vector<__half> hb((size_t)p.n_ntiles * nt_halves);
+  const int nph = st[0] * st[1] * st[2];
   for (int nt = 0; nt < p.n_ntiles; ++nt) {
     size_t opi = 0;
     for (int kc = 0; kc < p.kc_count; ++kc)
-      for (const Op& op : ops[kc]) {
+      for (const Op& op : classes[kc / cpp].ops) {
         __half* blk = hb.data() + (size_t)nt * nt_halves + opi * NC * 16;
         ++opi;
-        const int cc = kind == TAPS_CONV3_S2 ? kc % cpp : kc;
+        const int cc = kc % cpp;
         for (int kch = 0; kch < 2; ++kch)
           for (int n = 0; n < NC; ++n)
             for (int e = 0; e < 8; ++e) {
@@ -396,12 +433,12 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
               const int ng = nt * NC + n;
               float v = 0.f;
               if (ci < cin_w) {
-                if (kind == TAPS_TCONV2) {
+                if (kind == TAPS_TCONV) {
                   const int px = (ng >> 3) & 1, cg = (ng >> 4) % (Cout / 8), pzpy = ng / (2 * Cout);
-                  const int phs = pzpy * 2 + px, co = cg * 8 + (ng & 7);
-                  v = h_w[((size_t)ci * Cout + co) * 8 + phs];
+                  const int pz = pzpy / st[1], py = pzpy % st[1], co = cg * 8 + (ng & 7);
+                  v = h_w[((size_t)ci * Cout + co) * nph + (pz * st[1] + py) * st[2] + px];
                 } else {
-                  v = h_w[((size_t)ng * cin_w + ci) * 27 + op.tap];
+                  v = h_w[((size_t)ng * cin_w + ci) * k3 + op.tap];
                 }
               }
               blk[((size_t)kch * NC + n) * 8 + e] = __float2half_rn(v);
@@ -437,12 +474,15 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float
     conv_taps_plan_destroy(pl);
     return nullptr;
   }
+  if (io.xf.scale && stages >= 4) stages = stages / 4 * 4;  // the transform groups share the ring slots evenly
   p.stages = stages;
+  p.xf_groups = stages % 4 == 0 ? 4 : (stages % 2 == 0 ? 2 : 1);
   p.tmap_merged = c8_tmap_merged() ? 1 : 0;
   pl->smem = (size_t)stages * stage + (3 * TAPS_MAX_STAGES + 8) * 8 + 8 * TAB_STRIDE * sizeof(int32_t);
   // the attribute is per kernel, not per plan: always opt in to the full 227 KB
   cudaError_t e = NC == 128 ? cudaFuncSetAttribute(conv_taps_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)
-                            : cudaFuncSetAttribute(conv_taps_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
+                  : NC == 64 ? cudaFuncSetAttribute(conv_taps_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM)
+                             : cudaFuncSetAttribute(conv_taps_kernel<32>, cudaFuncAttributeMaxDynamicSharedMemorySize, MAX_DYN_SMEM);
   if (e != cudaSuccess) {
     set_error("conv_taps: cannot opt in to %zu bytes of shared memory: %s", pl->smem, cudaGetErrorString(e));
     conv_taps_plan_destroy(pl);
@@ -469,8 +509,10 @@ int conv_taps_launch(ConvTapsPlan* pl, cudaStream_t s, int nb) {
   }
   if (pl->nc == 128)
     conv_taps_kernel<128><<<pl->grid, TAPS_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
-  else
+  else if (pl->nc == 64)
     conv_taps_kernel<64><<<pl->grid, TAPS_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
+  else
+    conv_taps_kernel<32><<<pl->grid, TAPS_THREADS, pl->smem, s>>>(pl->tmap, pl->prm);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }
