@@ -22,26 +22,34 @@ __device__ __forceinline__ void stats_flush(RunningStats& r, double* __restrict_
   r.s1 = 0.0; r.s2 = 0.0; r.key = -1;
 }
 
-// Optional second destination of a conv output: the space-to-depth copy [B][8 phases][G][D/2][H/2][W/2][8] that the
-// next stage's stride-2 conv reads (phase = (z&1)*4 + (y&1)*2 + (x&1)).  `base` is this thread's voxel (x, y) of the
-// strip's first channel group at z = 0; nullptr = no copy.
+// Optional second destination of a conv output: the space-to-depth copy [B][phases][G][D/sz][H/sy][W/sx][8] that the
+// next stage's strided conv reads (strides 1 or 2 per axis; phase = ((z%sz)*sy + y%sy)*sx + x%sx).  `base` is this
+// thread's voxel (x, y) of the strip's first channel group at z = 0; nullptr = no copy.
 struct S2dDst {
   uint4* base = nullptr;
-  size_t zpar_stride = 0;   // z odd: + 4 phases
-  size_t zhalf_stride = 0;  // per z >> 1
+  size_t zpar_stride = 0;   // z odd (sz == 2): + sy * sx phases
+  size_t zhalf_stride = 0;  // per z / sz
   size_t gstride = 0;       // per channel group
-  __device__ __forceinline__ uint4* at(int z) const { return base + (size_t)(z & 1) * zpar_stride + (size_t)(z >> 1) * zhalf_stride; }
+  int zshift = 0;           // sz - 1
+  __device__ __forceinline__ uint4* at(int z) const {
+    return base + (size_t)(z & zshift) * zpar_stride + (size_t)(z >> zshift) * zhalf_stride;
+  }
 };
 
-__device__ __forceinline__ S2dDst s2d_dst(__half* s2d, int b, int groups, int g0, int D, int H, int W, int y, int x) {
+__device__ __forceinline__ S2dDst s2d_dst(__half* s2d, const int (&st)[3], int b, int groups, int g0, int D, int H, int W,
+                                          int y, int x) {
   S2dDst d;
   if (!s2d) return d;
-  const size_t hv = (size_t)(D >> 1) * (H >> 1) * (W >> 1);
-  const int ph_xy = (y & 1) * 2 + (x & 1);
-  d.base = reinterpret_cast<uint4*>(s2d) + ((size_t)(b * 8 + ph_xy) * groups + g0) * hv + (size_t)(y >> 1) * (W >> 1) + (x >> 1);
-  d.zpar_stride = (size_t)4 * groups * hv;
-  d.zhalf_stride = (size_t)(H >> 1) * (W >> 1);
+  const int sz = st[0], sy = st[1], sx = st[2];
+  const int Hh = H / sy, Wh = W / sx;
+  const size_t hv = (size_t)(D / sz) * Hh * Wh;
+  const int ph_xy = (y % sy) * sx + (x % sx);
+  d.base = reinterpret_cast<uint4*>(s2d) + ((size_t)(b * sz * sy * sx + ph_xy) * groups + g0) * hv +
+           (size_t)(y / sy) * Wh + (x / sx);
+  d.zpar_stride = (size_t)sy * sx * groups * hv;
+  d.zhalf_stride = (size_t)Hh * Wh;
   d.gstride = hv;
+  d.zshift = sz - 1;
   return d;
 }
 

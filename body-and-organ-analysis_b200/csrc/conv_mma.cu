@@ -57,6 +57,7 @@ struct ConvMmaParams {
   int in_groups_total, in_group_off;
   int out_groups_total, out_group_off;  // the output view (a channel-group slice of a concat buffer, or dense)
   __half* s2d;                          // optional space-to-depth copy of the output (nullptr: none)
+  int s2d_stride[3];                    // strides (z, y, x) of the conv that will read the copy
   InXform xf;                           // fused normalisation of the input (xf.scale == nullptr: none)
   int xf_groups;                        // transform warp groups (divides `stages`)
   int xf_debug;                         // profiling aid (BOA_B200_XF_DEBUG): 1 = transform warps only relay the barrier
@@ -258,7 +259,7 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
                      ((((size_t)b * p.out_groups_total + p.out_group_off + (cbase >> 3)) * p.D + tz * p.zt) * p.H + y) * p.W + x;
         conv_epilogue_strip(tlane + chunk * 32, NC, p.zt, p.bias + cbase, rowvalid, tz * p.zt, p.D, dst, zstride, gstride,
                             lane, b * p.Cout + cbase, run[chunk], p.stats,
-                            s2d_dst(p.s2d, b, p.Cout / 8, cbase >> 3, p.D, p.H, p.W, y, x));
+                            s2d_dst(p.s2d, p.s2d_stride, b, p.Cout / 8, cbase >> 3, p.D, p.H, p.W, y, x));
       }
       tc_fence_before();
       __syncwarp();
@@ -319,9 +320,11 @@ struct ConvMmaPlan {
 };
 
 ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin_w, int cin_padded, int Cout,
-                                  const ActView& src, int B, const ConvIO& io, double* d_stats, bool taps_on_k) {
+                                  const ActView& src, int B, const ConvIO& io, double* d_stats, bool taps_on_k,
+                                  int kz) {
   // taps_on_k (first layer, Cin = 1): the source tensor carries the 9 in-plane neighbours of every voxel as its
-  // channels 0..8, h_w is [Cout][1][27]; only the dz taps remain as (folded) taps.
+  // channels 0..8, h_w is [Cout][1][kz * 9]; only the dz taps remain as (folded) taps.  kz == 1 ([1,3,3] kernels of
+  // anisotropic plans): the dz = 0 / 2 blocks are zero (wasted MMAs in a layer that is HBM bound anyway).
   const int ntaps = taps_on_k ? 1 : 9;
   if (taps_on_k) { cin_w = 9; cin_padded = 16; }
   if (cin_padded % 16 || Cout % 32 || cin_padded > src.groups * 8) {
@@ -347,12 +350,14 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
   p.in_groups_total = src.groups_total; p.in_group_off = src.group_off;
   p.out = io.out.base; p.out_groups_total = io.out.groups_total; p.out_group_off = io.out.group_off;
   p.s2d = io.s2d;
+  for (int a = 0; a < 3; ++a) p.s2d_stride[a] = io.s2d_stride[a];
   p.stats = d_stats;
   p.ntaps = ntaps;
   p.tmap_merged = c8_tmap_merged() ? 1 : 0;
   p.xf = io.xf;
   p.xf_debug = getenv("BOA_B200_XF_DEBUG") ? atoi(getenv("BOA_B200_XF_DEBUG")) : 0;
-  if (io.out.groups < Cout / 8 || (io.s2d && ((src.D | src.H | src.W) & 1)) ||
+  if (io.out.groups < Cout / 8 ||
+      (io.s2d && (src.D % io.s2d_stride[0] || src.H % io.s2d_stride[1] || src.W % io.s2d_stride[2])) ||
       (io.xf.scale && (taps_on_k || io.xf.channels != cin_w || cin_w % 16 != 0))) {
     set_error("conv_mma: bad output view / space-to-depth copy / input transform for cin=%d cout=%d", cin_w, Cout);
     conv_mma_plan_destroy(pl);
@@ -375,9 +380,12 @@ ConvMmaPlan* conv_mma_plan_create(const float* h_w, const float* h_bias, int cin
                 const int ci = kc * 16 + kch * 8 + e;
                 const int dz = 2 - j;
                 float v = 0.f;
-                if (ci < cin_w)
-                  v = taps_on_k ? h_w[(size_t)(nt * NC + co) * 27 + dz * 9 + (ci == 0 ? 4 : (ci <= 4 ? ci - 1 : ci))]
-                                : h_w[((size_t)(nt * NC + co) * cin_w + ci) * 27 + dz * 9 + dy * 3 + dx];
+                if (ci < cin_w) {
+                  const int tap9 = ci == 0 ? 4 : (ci <= 4 ? ci - 1 : ci);
+                  if (!taps_on_k) v = h_w[((size_t)(nt * NC + co) * cin_w + ci) * 27 + dz * 9 + dy * 3 + dx];
+                  else if (kz == 3) v = h_w[(size_t)(nt * NC + co) * 27 + dz * 9 + tap9];
+                  else v = dz == 1 ? h_w[(size_t)(nt * NC + co) * 9 + tap9] : 0.f;
+                }
                 blk[((size_t)kch * 3 * NC + j * NC + co) * 8 + e] = __float2half_rn(v);
               }
       }

@@ -443,10 +443,16 @@ static int build_lane(boa_net* net, int li) {
       if (!mid[s][0] || !mid[s][1] || !outb[s]) return BOA_ERR_CUDA;
     }
     cat[s] = s < n - 1 ? wsalloc<__half>(net, li, B * 2 * f * vox(s)) : nullptr;
-    const bool iso2 = s < n - 1 && is3(a.strides[s + 1], 2) && dims[s][0] % 2 == 0 && dims[s][1] % 2 == 0 &&
-                      dims[s][2] % 2 == 0;
-    s2d[s] = iso2 ? wsalloc<__half>(net, li, B * f * vox(s)) : nullptr;
-    if ((s < n - 1 && !cat[s]) || (iso2 && !s2d[s])) return BOA_ERR_CUDA;
+    // space-to-depth copy for the next stage's strided conv: any mix of strides 1 / 2 with equal in-plane strides
+    // (the unfused schedule's normalise pass only writes the isotropic stride-2 copy)
+    bool want_s2d = false;
+    if (s < n - 1) {
+      const int* ns = a.strides[s + 1];
+      want_s2d = !is3(ns, 1) && ns[1] == ns[2] && (fuse || is3(ns, 2));
+      for (int k = 0; k < 3; ++k) want_s2d = want_s2d && (ns[k] == 1 || ns[k] == 2) && dims[s][k] % ns[k] == 0;
+    }
+    s2d[s] = want_s2d ? wsalloc<__half>(net, li, B * f * vox(s)) : nullptr;
+    if ((s < n - 1 && !cat[s]) || (want_s2d && !s2d[s])) return BOA_ERR_CUDA;
     if (fuse && s < n - 1) {
       // combined scale / shift rows of the decoder concat [B][2f]: the transposed-conv half is final (identity, never
       // read: ident_groups), the skip half is written by the encoder conv's statistics kernel every forward
@@ -471,7 +477,8 @@ static int build_lane(boa_net* net, int li) {
 
   // first layer (Cin = 1, 3x3x3): on the tensor cores with the 9 in-plane taps moved onto K (K = 16, three folded
   // dz taps) when Cout % 32 == 0, else the direct FP32 kernel from a plain fp16 patch
-  const bool first33 = a.in_channels == 1 && is3(a.kernels[0], 3) && a.n_conv_enc[0] >= 1;
+  const bool first33 = a.in_channels == 1 && a.kernels[0][1] == 3 && a.kernels[0][2] == 3 &&
+                       (a.kernels[0][0] == 3 || a.kernels[0][0] == 1) && a.n_conv_enc[0] >= 1;
   // (the direct kernel writes a dense tensor: not usable when the first conv is also the last of its stage in the
   // fused schedule, where the output goes into the concat buffer)
   const bool first_dense = !(fuse && a.n_conv_enc[0] == 1 && n > 1);
@@ -484,7 +491,8 @@ static int build_lane(boa_net* net, int li) {
   // normalise pass writes there and the raw output goes to a ping-pong buffer).  want_s2d: the next stage's stride-2
   // conv wants a space-to-depth copy of the result.
   auto add_conv = [&](const std::string& prefix, const Feed& in, const ActView& in_s2d, int cin, int cout,
-                      const int* ks, const int* stride, int s_out, const ActView& final_dst, __half* want_s2d) -> int {
+                      const int* ks, const int* stride, int s_out, const ActView& final_dst, __half* want_s2d,
+                      const int* next_stride) -> int {
     ConvStep st;
     st.name = prefix;
     st.cin = cin; st.cout = cout;
@@ -524,14 +532,19 @@ static int build_lane(boa_net* net, int li) {
     ConvIO io;
     io.out = st.out;
     io.xf = in.xf;
+    if (next_stride)
+      for (int k = 0; k < 3; ++k) io.s2d_stride[k] = next_stride[k];
     const int cin_padded = (cin + 15) / 16 * 16;
+    bool k13 = ks[1] == ks[2] && stride[1] == stride[2];
+    for (int k = 0; k < 3; ++k) k13 = k13 && (ks[k] == 1 || ks[k] == 3) && (stride[k] == 1 || stride[k] == 2);
     // a transform in the tensor-core kernels works on whole K chunks of 16 channels
     const bool xf_ok = !in.xf.scale || cin % 16 == 0;
     if (first_plain) {
       st.kind = STEP_CONV_FIRST;
     } else if (first_nb9) {
       io.s2d = fuse ? want_s2d : nullptr;
-      st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, in.view, B, io, st.d_stats, true);
+      st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, in.view, B, io, st.d_stats, true,
+                                     ks[0]);
       if (!st.fold) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_FOLD;
     } else if (is3(ks, 3) && is3(stride, 1) && cout % 32 == 0 && cin_padded <= in.view.groups * 8 && xf_ok) {
@@ -539,12 +552,17 @@ static int build_lane(boa_net* net, int li) {
       st.fold = conv_mma_plan_create(wr.data(), bi->data.data(), cin, cin_padded, cout, in.view, B, io, st.d_stats);
       if (!st.fold) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_FOLD;
-    } else if (is3(ks, 3) && is3(stride, 2) && in_s2d.base && cin % 16 == 0 && cout % 64 == 0) {
+    } else if (k13 && cin % 16 == 0 && cout % 32 == 0 && xf_ok && (is3(stride, 1) || in_s2d.base)) {
+      // every other kernel / stride mix of {1,3} x {1,2} (equal in-plane): the tap-list kernel, on the plain tensor
+      // when all strides are 1, else on the space-to-depth copy the producer's epilogue (or pass) wrote
+      const ActView& tsrc = is3(stride, 1) ? in.view : in_s2d;
       io.s2d = fuse ? want_s2d : nullptr;
-      st.taps = conv_taps_plan_create(TAPS_CONV3_S2, wr.data(), bi->data.data(), cin, cout, in_s2d, B, io, st.d_stats);
+      TapsGeom geo;
+      for (int k = 0; k < 3; ++k) { geo.ks[k] = ks[k]; geo.stride[k] = stride[k]; }
+      st.taps = conv_taps_plan_create(TAPS_CONV, geo, wr.data(), bi->data.data(), cin, cout, tsrc, B, io, st.d_stats);
       if (!st.taps) return BOA_ERR_CUDA;
       st.kind = STEP_CONV_TAPS;
-      st.src = in_s2d;
+      st.src = tsrc;
     }
     if (fuse && (st.kind == STEP_CONV_FOLD || st.kind == STEP_CONV_TAPS)) st.out_s2d = want_s2d;
     first_plain = false;
@@ -582,7 +600,8 @@ static int build_lane(boa_net* net, int li) {
       __half* s2d_out = (last && s < n - 1) ? s2d[s] : nullptr;
       char name[64];
       snprintf(name, sizeof(name), "encoder.stages.%d.0.convs.%d", s, i);
-      if (int r = add_conv(name, cur, i == 0 ? cur_s2d : ActView(), cur_c, f, a.kernels[s], stride, s, dst, s2d_out))
+      if (int r = add_conv(name, cur, i == 0 ? cur_s2d : ActView(), cur_c, f, a.kernels[s], stride, s, dst, s2d_out,
+                           s < n - 1 ? a.strides[s + 1] : nullptr))
         return r;
       ConvStep& st = L.steps.back();
       if (fuse && last && s < n - 1) {  // skip producer: its scale / shift also fill the concat's combined table
@@ -593,8 +612,11 @@ static int build_lane(boa_net* net, int li) {
       cur_s2d = ActView();
       // the copy exists when a pass (unfused) or a tensor-core epilogue (fused) writes it
       if (s2d_out && (fuse ? st.out_s2d != nullptr : true)) {
-        cur_s2d.base = s2d_out; cur_s2d.groups_total = f; cur_s2d.group_off = 0; cur_s2d.groups = f;  // 8 * f/8
-        cur_s2d.D = dims[s][0] / 2; cur_s2d.H = dims[s][1] / 2; cur_s2d.W = dims[s][2] / 2;
+        const int* ns = a.strides[s + 1];
+        const int phases = ns[0] * ns[1] * ns[2];
+        cur_s2d.base = s2d_out; cur_s2d.groups_total = phases * f / 8; cur_s2d.group_off = 0;
+        cur_s2d.groups = phases * f / 8;
+        cur_s2d.D = dims[s][0] / ns[0]; cur_s2d.H = dims[s][1] / ns[1]; cur_s2d.W = dims[s][2] / ns[2];
       }
     }
   }
@@ -624,11 +646,14 @@ static int build_lane(boa_net* net, int li) {
     up.macs = (double)nph * cb * f * vox(s_below);
     macs += up.macs;
     up.kind = STEP_TCONV_SIMT;
-    if (is3(st3, 2) && cb % 16 == 0 && (8 * f) % 64 == 0) {
+    bool tc_ok = st3[2] == 2 && st3[1] == 2 && (st3[0] == 1 || st3[0] == 2) && cb % 16 == 0 && (nph * f) % 32 == 0;
+    if (tc_ok) {
       ConvIO io;
       io.out = up.out;
       io.xf = cur.xf;
-      up.taps = conv_taps_plan_create(TAPS_TCONV2, wr.data(), bi->data.data(), cb, f, cur.view, B, io, nullptr);
+      TapsGeom geo;
+      for (int k = 0; k < 3; ++k) { geo.ks[k] = st3[k]; geo.stride[k] = st3[k]; }
+      up.taps = conv_taps_plan_create(TAPS_TCONV, geo, wr.data(), bi->data.data(), cb, f, cur.view, B, io, nullptr);
       if (!up.taps) return BOA_ERR_CUDA;
       up.kind = STEP_TCONV_TAPS;
     }
@@ -647,7 +672,7 @@ static int build_lane(boa_net* net, int li) {
       if (fuse) { dst = view(raw[s][raw_flip & 1], f / 8, 0, f / 8, s); ++raw_flip; }
       else dst = last ? view(outb[s], f / 8, 0, f / 8, s) : view(mid[s][i & 1], f / 8, 0, f / 8, s);
       snprintf(name, sizeof(name), "decoder.stages.%d.convs.%d", j, i);
-      if (int r = add_conv(name, cur, ActView(), cur_c, f, a.kernels[s], one, s, dst, nullptr)) return r;
+      if (int r = add_conv(name, cur, ActView(), cur_c, f, a.kernels[s], one, s, dst, nullptr, nullptr)) return r;
       cur = feed_of_last(dst);
       cur_c = f;
     }

@@ -80,6 +80,7 @@ int launch_head(const ActView& src, int b, const float* d_w, const float* d_bias
 struct ConvIO {
   ActView out;
   __half* s2d = nullptr;
+  int s2d_stride[3] = {2, 2, 2};  // strides (z, y, x) of the conv that will read the copy: phases = product
   InXform xf;
 };
 
@@ -87,20 +88,24 @@ struct ConvIO {
 struct ConvMmaPlan;
 ConvMmaPlan* conv_mma_plan_create(const float* h_w /*[Cout][Cin_w][27] fp32*/, const float* h_bias, int cin_w,
                                   int cin_padded, int Cout, const ActView& src, int B, const ConvIO& io,
-                                  double* d_stats, bool taps_on_k = false);
+                                  double* d_stats, bool taps_on_k = false, int kz = 3);
 void conv_mma_plan_destroy(ConvMmaPlan* p);
 // nb: batch items to process (<= the B the plan was created with; the tensors keep their [B]-strided layout)
 int conv_mma_launch(ConvMmaPlan* p, cudaStream_t s, int nb = -1);
 
-// ---- tcgen05 implicit GEMM over an explicit tap list (conv_taps.cu): stride-2 convs on the space-to-depth copy,
-//      transposed convs (one tap, 8 output phases on N), plain 3x3x3.
+// ---- tcgen05 implicit GEMM over an explicit tap list (conv_taps.cu): strided convs on the space-to-depth copy,
+//      transposed convs (one tap, the output phases on N), stride-1 convs with any kernel in {1,3}^3.
 struct ConvTapsPlan;
-enum TapsKind { TAPS_CONV3_S1 = 0, TAPS_CONV3_S2 = 1, TAPS_TCONV2 = 2 };
-// TAPS_CONV3_S1: h_w [Cout][cin_w][27], src = activation view;       out = raw [B][Cout/8][D][H][W], stats.
-// TAPS_CONV3_S2: h_w [Cout][cin_w][27], src = s2d view (8*groups);   out = raw at src dims,           stats.
-// TAPS_TCONV2:   h_w [Cin][Cout][8],    src = activation view;       out = dst view at 2x dims (bias, no stats).
-ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const float* h_w, const float* h_bias, int cin_w, int Cout,
-                                    const ActView& src, int B, const ConvIO& io, double* d_stats);
+enum TapsKind { TAPS_CONV = 0, TAPS_TCONV = 2 };
+struct TapsGeom {  // per axis (z, y, x)
+  int ks[3];       // conv: kernel size 1 or 3 (in-plane sizes equal); transposed conv: unused (kernel = stride)
+  int stride[3];   // 1 or 2 (in-plane strides equal; transposed conv: x stride 2)
+};
+// TAPS_CONV:  h_w [Cout][cin_w][kz*ky*kx]; src = activation view (all strides 1) or the space-to-depth view of it
+//             ([phases * groups], dims divided by the strides); out = raw conv output at the source view's dims, stats.
+// TAPS_TCONV: h_w [Cin][Cout][sz*sy*sx];   src = activation view; out = dst view at (sz, sy, sx) x the dims (bias only).
+ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const TapsGeom& geo, const float* h_w, const float* h_bias,
+                                    int cin_w, int Cout, const ActView& src, int B, const ConvIO& io, double* d_stats);
 void conv_taps_plan_destroy(ConvTapsPlan* p);
 int conv_taps_launch(ConvTapsPlan* p, cudaStream_t s, int nb = -1);
 

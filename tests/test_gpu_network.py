@@ -71,6 +71,21 @@ def test_anisotropic_net_simt(cuda):
     _compare(arch, 5, 2, 2, TOL)
 
 
+def test_anisotropic_plans_run_on_the_tensor_cores(cuda):
+    """[1,3,3] kernels, [1,2,2] pools and a non-cubic patch - what nnU-Net plans for thick-slice data (the 5 mm
+    body-composition models, _external/body_composition_analysis/tasks.py:15-48) look like: every conv / transposed
+    conv must land on a tcgen05 kernel (no SIMT launches) and agree with the oracle."""
+    plans = zoo.default_plans((16, 64, 48), 32, 128, 3)
+    cfg = plans["configurations"]["3d_fullres"]
+    cfg["pool_op_kernel_sizes"] = [[1, 1, 1], [1, 2, 2], [2, 2, 2]]
+    cfg["conv_kernel_sizes"] = [[1, 3, 3], [1, 3, 3], [3, 3, 3]]
+    arch = arch_from_plans(plans, "3d_fullres", 1, 7)
+    out, kinds = _compare(arch, 23, 3, 2, TOL)
+    assert 2 not in kinds and 4 not in kinds and 5 not in kinds, f"SIMT kernels in the schedule: {kinds}"
+    d = np.abs(out[0] - out[1]).max() / np.abs(out[1]).max()
+    assert d < TOL
+
+
 def test_totalseg_geometry_one_patch(cuda):
     # the real TotalSegmentator geometry at a 64^3 patch (6 stages, 32..320 features): every layer shape class
     arch = _arch((64, 64, 64), 32, 320, 6, 25)
