@@ -292,9 +292,9 @@ conv3_fold_kernel(const __grid_constant__ CUtensorMap tmapA, const ConvMmaParams
                            (8 * g0 + 8 >= p.xf.channels ? 2 : 0);
           mbar_wait(&rawfull[st], ph);
           if (skip != 3 && p.xf_debug != 1)
-            xform_stage<XB, YB, 4, 3>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
+            xform_stage<XB, YB, 3>(ring + (size_t)st * stage_bytes, zb, zlo, zhi, ylo, yhi, xlo, xhi,
                                       p.xf.scale + (size_t)b * p.xf.channels + 16 * kc,
-                                      p.xf.shift + (size_t)b * p.xf.channels + 16 * kc, skip, p.xf.slope, tid, gthreads);
+                                      p.xf.shift + (size_t)b * p.xf.channels + 16 * kc, skip, p.xf.slope, tid, gthreads, 4);
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
           __syncwarp();
           if (lane == 0) mbar_arrive(&full[st]);

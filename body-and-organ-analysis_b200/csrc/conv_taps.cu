@@ -219,10 +219,12 @@ conv_taps_kernel(const __grid_constant__ CUtensorMap tmapA, const TapsParams p) 
             uint8_t* sa = smem + (size_t)st * stage_bytes;
             const float* sc = p.xf.scale + (size_t)b * p.xf.channels + 16 * cc;
             const float* sh = p.xf.shift + (size_t)b * p.xf.channels + 16 * cc;
-            // z phases of 4, at most 3 planes per item (box_z <= 10)
-            if (p.halo == 2) xform_stage<TT_X + 2, TT_Y + 2, 4, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid, gthreads);
-            else if (p.halo == 1) xform_stage<TT_X + 1, TT_Y + 1, 4, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid, gthreads);
-            else xform_stage<TT_X, TT_Y, 4, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid, gthreads);
+            // work items = (z phase, in-plane position) with at most 3 planes each: z phases of 2 for boxes of up to 6
+            // planes (NC = 64 / 128), of 4 for the 8..10-plane boxes of NC = 32
+            const int zs = p.box_z <= 6 ? 2 : 4;
+            if (p.halo == 2) xform_stage<TT_X + 2, TT_Y + 2, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid, gthreads, zs);
+            else if (p.halo == 1) xform_stage<TT_X + 1, TT_Y + 1, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid, gthreads, zs);
+            else xform_stage<TT_X, TT_Y, 3>(sa, p.box_z, zlo, zhi, ylo, yhi, xlo, xhi, sc, sh, skip, p.xf.slope, tid, gthreads, zs);
           }
           fence_proxy_async();  // generic-proxy stores -> visible to the tensor core's async-proxy reads
           __syncwarp();
@@ -474,7 +476,7 @@ ConvTapsPlan* conv_taps_plan_create(TapsKind kind, const TapsGeom& geo, const fl
     conv_taps_plan_destroy(pl);
     return nullptr;
   }
-  if (io.xf.scale && stages >= 4) stages = stages / 4 * 4;  // the transform groups share the ring slots evenly
+  if (io.xf.scale && stages >= 4 && !getenv("BOA_B200_TAPS_NOTRIM")) stages = stages / 4 * 4;  // the transform groups share the ring slots evenly
   p.stages = stages;
   p.xf_groups = stages % 4 == 0 ? 4 : (stages % 2 == 0 ? 2 : 1);
   p.tmap_merged = c8_tmap_merged() ? 1 : 0;

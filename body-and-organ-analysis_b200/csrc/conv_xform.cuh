@@ -46,12 +46,12 @@ __device__ __forceinline__ uint4 xform8(const uint4& raw, const float (&a)[8], c
 // One operand stage: 2 channel groups x [bz][BY][BX] positions x 16 bytes, in place.  Called by nt threads (tid).
 // [zlo,zhi) x [ylo,yhi) x [xlo,xhi): in-volume part of the box.  sc / sh: scale / shift of the 16 channels of this
 // K chunk for this batch item.  skip: bit g set = group g is final (or does not exist).
-// Work items are (z phase of ZS, in-plane position): a thread's (y, x) is fixed per item, so the bounds test and the
+// Work items are (z phase of zs = 2 or 4, in-plane position; at most MAXP planes per item): a thread's (y, x) is fixed per item, so the bounds test and the
 // index arithmetic happen once per item and the planes of an item are loaded together before they are transformed.
-template <int BX, int BY, int ZS, int MAXP>
+template <int BX, int BY, int MAXP>
 __device__ __forceinline__ void xform_stage(uint8_t* sa, int bz, int zlo, int zhi, int ylo, int yhi, int xlo, int xhi,
                                             const float* __restrict__ sc, const float* __restrict__ sh, int skip,
-                                            float slope, int tid, int nt) {
+                                            float slope, int tid, int nt, int zs) {
   constexpr int SL = BX * BY;
   const int per_group = bz * SL;
 #pragma unroll 1
@@ -66,18 +66,18 @@ __device__ __forceinline__ void xform_stage(uint8_t* sa, int bz, int zlo, int zh
     }
     uint4* t = reinterpret_cast<uint4*>(sa) + g * per_group;
 #pragma unroll 1
-    for (int it = tid; it < ZS * SL; it += nt) {
+    for (int it = tid; it < zs * SL; it += nt) {
       const int zp = it / SL, r = it - zp * SL, y = r / BX, x = r - y * BX;
       if (y < ylo || y >= yhi || x < xlo || x >= xhi) continue;
-      // planes zlo <= z < zhi with z % ZS == zp
-      int z = zlo + ((zp - zlo) % ZS + ZS) % ZS;
+      // planes zlo <= z < zhi with z % zs == zp (zs is a power of two)
+      const int z = zlo + ((zp - zlo) & (zs - 1));
       uint4 v[MAXP];
 #pragma unroll
       for (int k = 0; k < MAXP; ++k)
-        if (z + k * ZS < zhi) v[k] = t[(z + k * ZS) * SL + r];
+        if (z + k * zs < zhi) v[k] = t[(z + k * zs) * SL + r];
 #pragma unroll
       for (int k = 0; k < MAXP; ++k)
-        if (z + k * ZS < zhi) t[(z + k * ZS) * SL + r] = xform8(v[k], a, s, slope);
+        if (z + k * zs < zhi) t[(z + k * zs) * SL + r] = xform8(v[k], a, s, slope);
     }
   }
 }

@@ -483,7 +483,7 @@ static int build_lane(boa_net* net, int li) {
   // fused schedule, where the output goes into the concat buffer)
   const bool first_dense = !(fuse && a.n_conv_enc[0] == 1 && n > 1);
   net->input_mode = (first33 && a.features[0] % 32 == 0) ? 2
-                    : (first33 && first_dense && conv_first_supported(a.features[0]) ? 1 : 0);
+                    : (first33 && is3(a.kernels[0], 3) && first_dense && conv_first_supported(a.features[0]) ? 1 : 0);
   bool first_plain = net->input_mode == 1;
   bool first_nb9 = net->input_mode == 2;
   int raw_flip = 0;
