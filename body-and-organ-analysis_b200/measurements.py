@@ -88,9 +88,27 @@ def _masked_hist_dev(ct: torch.Tensor, mask: torch.Tensor, hu_lo: int, n_bins: i
     return hist[1]
 
 
-def _eroded_region_hist_dev(ct, labels, ids, minus_fat: bool, hu_lo: int, n_bins: int) -> torch.Tensor:
-    mask = passes.label_set_mask(labels, ids, ct, ADIPOSE_TISSUE[0], ADIPOSE_TISSUE[1], 2 if minus_fat else 0)
-    return _masked_hist_dev(ct, passes.erode_box(mask, 3, 2), hu_lo, n_bins)
+def _eroded_region_hist_dev(ct, labels, ids, minus_fat: bool, hu_lo: int, n_bins: int, slab=None) -> torch.Tensor:
+    """Histogram of the CT under erode_6(label set [minus fat]).  slab = (z0, z1): only the slices z0..z1 of the volume
+    contribute (multi-GPU: every rank takes its dim-0 slab and the tables are all-reduced); the erosion window reaches 3
+    slices back and 2 forward, so the mask is built on the slab plus that halo and the halo rows are dropped."""
+    if slab is None:
+        mask = passes.label_set_mask(labels, ids, ct, ADIPOSE_TISSUE[0], ADIPOSE_TISSUE[1], 2 if minus_fat else 0)
+        return _masked_hist_dev(ct, passes.erode_box(mask, 3, 2), hu_lo, n_bins)
+    z0, z1 = slab
+    lo, hi = max(0, z0 - 3), min(int(ct.shape[0]), z1 + 2)
+    cts, labs = ct[lo:hi], labels[lo:hi]
+    mask = passes.label_set_mask(labs, ids, cts, ADIPOSE_TISSUE[0], ADIPOSE_TISSUE[1], 2 if minus_fat else 0)
+    # kept rows z0..z1 look at z-3..z+2, i.e. never beyond [lo, hi) unless that is the image border itself, where
+    # erode_region's "outside counts as foreground" is exactly what erode_box does
+    er = passes.erode_box(mask, 3, 2)
+    return _masked_hist_dev(ct[z0:z1], er[z0 - lo:z1 - lo].contiguous(), hu_lo, n_bins)
+
+
+def _all_reduce_sum(t: torch.Tensor, dist_ctx) -> torch.Tensor:
+    import torch.distributed as dist
+    dist.all_reduce(t, op=dist.ReduceOp.SUM, group=dist_ctx.group)
+    return t
 
 
 class PendingMeasurements:
@@ -163,9 +181,12 @@ class PendingMeasurements:
 
 def enqueue_measurements(ct: torch.Tensor, segmentations: dict[str, torch.Tensor], spacing,
                          cnr_adjustment: bool = False, return_ct_pfav_mask: bool = False,
-                         hu_range: tuple[int, int] | None = None) -> PendingMeasurements:
+                         hu_range: tuple[int, int] | None = None, dist_ctx=None) -> PendingMeasurements:
     """Device half of compute_measurements (compute/measurements.py:244-343).  hu_range = (min, max) HU of the CT if
-    the caller knows it (the histograms then cover exactly that range); None: read it here (one host sync)."""
+    the caller knows it (the histograms then cover exactly that range); None: read it here (one host sync).
+    dist_ctx (every rank holds the whole CT and label map): each rank reduces its dim-0 slab and the integer tables are
+    all-reduced - exact, and every rank ends up with the same tables."""
+    from .geometry import shard_patches
     pend = PendingMeasurements(spacing, cnr_adjustment)
     if not segmentations:
         return pend
@@ -175,27 +196,33 @@ def enqueue_measurements(ct: torch.Tensor, segmentations: dict[str, torch.Tensor
         lo_t, hi_t = torch.aminmax(ct)
         hu_range = (int(lo_t), int(hi_t))
     hu_lo, n_bins = int(hu_range[0]), int(hu_range[1]) - int(hu_range[0]) + 1
+    sharded = dist_ctx is not None and dist_ctx.world_size > 1
+    slab = shard_patches(int(ct.shape[0]), dist_ctx.world_size, dist_ctx.rank) if sharded else None
+    red = (lambda t: _all_reduce_sum(t, dist_ctx)) if sharded else (lambda t: t)
     for model_name in sorted(segmentations, key=lambda m: m != "total"):
         labels = segmentations[model_name]
         if labels.shape != ct.shape:
             raise ValueError("The spacing of the image and of the segmentation should be the same")
         label_map = measurement_label_map(model_name)
         n_labels = max(label_map.values()) + 1
-        hist_dev, _ = passes.label_hu_hist(ct, labels, n_labels, hu_lo, n_bins)
-        hist_h = _to_host_async(hist_dev)
+        if sharded:
+            hist_dev, _ = passes.label_hu_hist(ct[slab[0]:slab[1]], labels[slab[0]:slab[1]], n_labels, hu_lo, n_bins)
+        else:
+            hist_dev, _ = passes.label_hu_hist(ct, labels, n_labels, hu_lo, n_bins)
+        hist_h = _to_host_async(red(hist_dev))
         aut_h, adj_h = None, {}
         if model_name == "total":
             ids = [label_map["autochthon_right"], label_map["autochthon_left"]]
             # the same histogram serves the autochthon reference (:42-58) and the CNR-adjusted "autochthon" entry
-            aut_h = _to_host_async(_eroded_region_hist_dev(ct, labels, ids, True, hu_lo, n_bins))
+            aut_h = _to_host_async(red(_eroded_region_hist_dev(ct, labels, ids, True, hu_lo, n_bins, slab).contiguous()))
             if return_ct_pfav_mask:
                 pend.pfav_mask = passes.label_set_mask(labels, [label_map[ll] for ll in LUNG_MASKS], ct,
                                                        ADIPOSE_TISSUE[0], ADIPOSE_TISSUE[1], 1)
         if cnr_adjustment and model_name in CNR_ADJUSTED_REGIONS:
             for region, label in label_map.items():
                 if region in CNR_ADJUSTED_REGIONS[model_name]:
-                    adj_h[region] = _to_host_async(_eroded_region_hist_dev(ct, labels, [label], "autochthon" in region,
-                                                                           hu_lo, n_bins))
+                    adj_h[region] = _to_host_async(red(_eroded_region_hist_dev(
+                        ct, labels, [label], "autochthon" in region, hu_lo, n_bins, slab).contiguous()))
         pend.models.append((model_name, label_map, hu_lo, hist_h, aut_h, adj_h))
     pend.event = torch.cuda.Event()
     pend.event.record()

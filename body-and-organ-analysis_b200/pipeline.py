@@ -382,7 +382,7 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         if total_measurements:
             with nvtx.range("boa/total_measurements"):
                 pending_total = enqueue_measurements(ct, {"total": res.total}, sx_sy_sz, cnr_adjustment,
-                                                     return_ct_pfav_mask=True, hu_range=hu_range)
+                                                     return_ct_pfav_mask=True, hu_range=hu_range, dist_ctx=dist_ctx)
             res.ct_pfav = pending_total.pfav_mask
             mark("total_measurements")
             if stager is not None:
@@ -417,14 +417,34 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
                 mark(f"{name}_postprocess")
             return out
 
-        if want_parts and "body_parts" in precomputed:
+        # >= 4 GPUs and both maps wanted: both networks first, then the two post-processings CONCURRENTLY - the labels of
+        # body_parts are dealt out to ranks 0 .. W-2 and the last rank runs the (sequential) body_regions passes
+        pair = (want_parts and want_regions and on_5mm and dist_ctx is not None
+                and dist_ctx.world_size >= int(os.environ.get("BOA_B200_PAIR_MIN_RANKS", "4"))
+                and "body_parts" not in precomputed and "body_regions" not in precomputed)
+        if pair:
+            from .postprocess import postprocess_pair_distributed
+            parts_raw = segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx, sp5)
+            mark("body_parts_net")
+            regions_raw = segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx, sp5)
+            mark("body_regions_net")
+            with nvtx.range("boa/postprocess/pair"):
+                parts_pp, regions_pp = postprocess_pair_distributed(parts_raw, regions_raw, weights, dist_ctx)
+                res.body_parts = upsample_labels_nearest(parts_pp, ct.shape[0])
+                res.body_regions = upsample_labels_nearest(regions_pp, ct.shape[0])
+            mark("bca_postprocess")
+            if stager is not None:
+                stager.stage("body_parts", res.body_parts)
+        elif want_parts and "body_parts" in precomputed:
             res.body_parts = precomputed["body_parts"].to(ct.device, torch.uint8).contiguous()
         elif want_parts:
             res.body_parts = finish(segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx, sp5),
                                     postprocess_part_segmentation, "body_parts")
             if stager is not None:
                 stager.stage("body_parts", res.body_parts)
-        if want_regions and "body_regions" in precomputed:
+        if pair:
+            pass
+        elif want_regions and "body_regions" in precomputed:
             res.body_regions = precomputed["body_regions"].to(ct.device, torch.uint8).contiguous()
         elif want_regions:
             res.body_regions = finish(segment_bca_net(ct5, zoo, "body_regions", fast_bca, dist_ctx, sp5),

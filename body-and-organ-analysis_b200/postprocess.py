@@ -79,8 +79,28 @@ def postprocess_region_segmentation(body_regions: torch.Tensor, weights: torch.T
     return seg
 
 
+def postprocess_pair_distributed(body_parts: torch.Tensor, body_regions: torch.Tensor, weights, dist_ctx):
+    """Both post-processings at once on >= 2 ranks: ranks 0 .. W-2 share the body_parts labels, rank W-1 runs the four
+    dependent body_regions passes; a MAX all-reduce combines the parts, a broadcast distributes the regions.  Same
+    results as running the two functions one after the other on every rank."""
+    import torch.distributed as dist
+    W, rank = dist_ctx.world_size, dist_ctx.rank
+    last = W - 1
+    if rank == last:
+        regions = postprocess_region_segmentation(body_regions, weights)
+        parts = torch.zeros_like(body_parts)
+    else:
+        regions = torch.empty_like(body_regions)
+        parts = postprocess_part_segmentation(body_parts, weights, label_share=(rank, W - 1))
+    dist.all_reduce(parts, op=dist.ReduceOp.MAX, group=dist_ctx.group)
+    src = last if dist_ctx.group is None else dist.get_global_rank(dist_ctx.group, last)
+    dist.broadcast(regions, src=src, group=dist_ctx.group)
+    return parts, regions
+
+
 def postprocess_part_segmentation(body_parts: torch.Tensor, weights: torch.Tensor | None = None,
-                                  threshold: int = SMALL_OBJECT_THRESHOLD, labels=None, dist_ctx=None) -> torch.Tensor:
+                                  threshold: int = SMALL_OBJECT_THRESHOLD, labels=None, dist_ctx=None,
+                                  label_share=None) -> torch.Tensor:
     """remove_small_labeled_objects (body_parts/postprocess.py:7-52): per label (ascending) fill the external contours
     of every slice, drop 26-connected objects of fewer than `threshold` voxels, close 26-connected holes of fewer than
     `threshold` voxels, paint the label (later labels overwrite earlier ones).
@@ -95,7 +115,9 @@ def postprocess_part_segmentation(body_parts: torch.Tensor, weights: torch.Tenso
         labels = [int(v) for v in np.nonzero(present)[0] if v > 0]  # np.unique(mask), labels > 0
     labels = sorted(labels)
     world = dist_ctx.world_size if dist_ctx is not None else 1
-    if world > 1:
+    if label_share is not None:      # (index, count): this caller's share, the caller combines the results
+        labels = labels[label_share[0]::label_share[1]]
+    elif world > 1:
         labels = labels[dist_ctx.rank::world]
     out = torch.zeros_like(body_parts)
     scratch = _Scratch(body_parts, need_border=True) if labels else None
@@ -107,7 +129,7 @@ def postprocess_part_segmentation(body_parts: torch.Tensor, weights: torch.Tenso
         _cc_filter(filled, (1,), True, MODE_26, OP_REMOVE_SMALL, threshold - 1, 1, weights, scratch)
         with torch.cuda.device(out.device):
             _lib.check(_lib.lib().boa_paint_label(_lib.ptr(filled), filled.numel(), label, _lib.ptr(out), _lib.stream_ptr()))
-    if world > 1:
+    if world > 1 and label_share is None:
         import torch.distributed as dist
         dist.all_reduce(out, op=dist.ReduceOp.MAX, group=dist_ctx.group)
     return out

@@ -47,6 +47,12 @@ def _worker(rank, world, port, out_dir):
     ct = torch.from_numpy(zoo.synthetic_ct((96, 64, 64), seed=5)).cuda()
     res = analyze_volume(ct, (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=True,
                          dist_ctx=DistContext(rank, world, None))
+    # the concurrent post-processing of the two body-composition maps (default from 4 ranks) on 2 ranks
+    os.environ["BOA_B200_PAIR_MIN_RANKS"] = "2"
+    res2 = analyze_volume(ct, (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=True,
+                          dist_ctx=DistContext(rank, world, None))
+    del os.environ["BOA_B200_PAIR_MIN_RANKS"]
+    same_pair = all(torch.equal(getattr(res, k), getattr(res2, k)) for k in ("body_parts", "body_regions", "tissues"))
     if rank == 0:
         ref = analyze_volume(ct, (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=True)
         import json
@@ -55,7 +61,8 @@ def _worker(rank, world, port, out_dir):
                     for k in ("total", "body_parts", "body_regions", "tissues")})
         with open(os.path.join(out_dir, "meas.json"), "w") as f:
             json.dump({"dist": [res.total_measurements, res.bca_measurements],
-                       "single": [ref.total_measurements, ref.bca_measurements]}, f)
+                       "single": [ref.total_measurements, ref.bca_measurements], "same_pair": bool(same_pair),
+                       "total_equal": bool(torch.equal(res.total, ref.total))}, f)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -84,3 +91,7 @@ def test_two_ranks_match_single_gpu(cuda, tmp_path):
     # the measurement dicts are functions of the label maps: same keys, and equal wherever the maps are equal
     assert m["dist"][0]["segmentations"]["total"].keys() == m["single"][0]["segmentations"]["total"].keys()
     assert m["dist"][1].keys() == m["single"][1].keys()
+    assert m["same_pair"], "concurrent post-processing of body_parts / body_regions differs from the sequential one"
+    if m["total_equal"]:  # sharded histograms, all-reduced: exact - same label map => same statistics
+        from test_oracle_golden import _close
+        _close(m["single"][0], m["dist"][0])
