@@ -67,6 +67,11 @@ _SIGS = {
     "boa_resample_z_cubic": (C.c_int, [_P, C.c_int, C.c_int, C.c_size_t, C.c_int, _P, _P, _P]),
     "boa_resample_z_nearest_u8": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_int, _P, _P]),
     "boa_resample_axis_cubic": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.c_int, _P, _P, C.c_int, _P]),
+    "boa_resample_axis_cubic_grid": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_int, C.c_size_t, C.c_int, _P, _P, C.c_int, _P]),
+    "boa_clip_slices_f32": (C.c_int, [_P, C.c_size_t, _P, C.c_size_t, C.c_int, _P, _P]),
+    "boa_resample_z_nearest_grid_f32": (C.c_int, [_P, C.c_int, C.c_size_t, C.c_int, _P, _P]),
+    "boa_finalize_argmax_resampled": (C.c_int, [_P, _P, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.c_int,
+                                                C.POINTER(C.c_uint8), C.c_int, _P, _P, _P]),
     "boa_resample_nearest_u8": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_int32), _P, _P]),
     "boa_median3x3_slices": (C.c_int, [_P, C.POINTER(C.c_int32), _P, _P]),
     "boa_cc_filter": (C.c_int, [_P, C.POINTER(C.c_int32), C.POINTER(C.c_uint8), C.c_int, C.c_int, C.c_int, C.c_int,

@@ -129,6 +129,60 @@ struct PeerSrc {
   }
 };
 
+// ResampledSrc: the network ran on a grid that nnU-Net's preprocessing resampled the volume to; the reference divides
+// the logits by the weight sum ON THAT GRID and resamples every channel back to the pre-resampling shape with order 1
+// before the argmax (_external/nnunetv2/inference/export_prediction.py:25-38 ->
+// resample_data_or_seg_to_shape(..., is_seg=False, order=1, order_z=0), default_resampling.py:117-203:
+// skimage.transform.resize(order=1, mode="edge") = scipy zoom with grid_mode coordinates (o + 0.5) * n_in / n_out - 0.5,
+// clamped; slice by slice with an order-0 pick along the anisotropic axis when separate_z).  Here the interpolation is
+// part of the argmax pass: value(c, voxel) = sum_k weight_k * (acc[c][p_k] / w[p_k]) over the 4 / 8 grid neighbours.
+// v0 indexes the OUTPUT grid; VEC == 1 only.
+struct ResampledSrc {
+  const float* acc;
+  const float* w;
+  int Zn, Yn, Xn, Zo, Yo, Xo;
+  int separate_z;
+  __device__ __forceinline__ static void axis(int o, int n_in, int n_out, int& i0, int& i1, double& t) {
+    double cc = ((double)o + 0.5) * ((double)n_in / (double)n_out) - 0.5;
+    cc = cc < 0.0 ? 0.0 : (cc > (double)(n_in - 1) ? (double)(n_in - 1) : cc);
+    const double fl = floor(cc);
+    i0 = (int)fl;
+    i1 = i0 + 1 < n_in ? i0 + 1 : n_in - 1;
+    t = cc - fl;
+  }
+  template <int VEC>
+  __device__ __forceinline__ void load(int c, size_t v0, float (&x)[VEC]) const {
+    static_assert(VEC == 1, "ResampledSrc is scalar");
+    const int xo = (int)(v0 % Xo), yo = (int)((v0 / Xo) % Yo), zo = (int)(v0 / ((size_t)Xo * Yo));
+    int x0, x1, y0, y1, z0, z1;
+    double tx, ty, tz;
+    axis(xo, Xn, Xo, x0, x1, tx);
+    axis(yo, Yn, Yo, y0, y1, ty);
+    if (separate_z) {  // map_coordinates(order=0): floor(scale * (k + 0.5) - 0.5 + 0.5)
+      int k = (int)floor(((double)Zn / (double)Zo) * ((double)zo + 0.5));
+      z0 = z1 = k < 0 ? 0 : (k >= Zn ? Zn - 1 : k);
+      tz = 0.0;
+    } else {
+      axis(zo, Zn, Zo, z0, z1, tz);
+    }
+    const size_t Vn = (size_t)Zn * Yn * Xn;
+    const float* a = acc + (size_t)c * Vn;
+    auto at = [&](int z, int y, int xx) -> double {
+      const size_t i = ((size_t)z * Yn + y) * Xn + xx;
+      return (double)__fdiv_rn(__ldg(a + i), __ldg(w + i));
+    };
+    const double v00 = at(z0, y0, x0) * (1.0 - tx) + at(z0, y0, x1) * tx;
+    const double v01 = at(z0, y1, x0) * (1.0 - tx) + at(z0, y1, x1) * tx;
+    double v = v00 * (1.0 - ty) + v01 * ty;
+    if (tz != 0.0) {
+      const double v10 = at(z1, y0, x0) * (1.0 - tx) + at(z1, y0, x1) * tx;
+      const double v11 = at(z1, y1, x0) * (1.0 - tx) + at(z1, y1, x1) * tx;
+      v = v * (1.0 - tz) + (v10 * (1.0 - ty) + v11 * ty) * tz;
+    }
+    x[0] = (float)v;
+  }
+};
+
 // predict_from_raw_data.py:620-625 (divide, isinf) ; label_handling.py:178 (argmax(0), first max wins) ;
 // totalsegmentator/nnunet.py:553-556 (part label -> global label, non-zero overwrite)
 template <int VEC, typename Src>
@@ -141,7 +195,7 @@ __device__ __forceinline__ void argmax_group(const Src& src, const float* __rest
     float4 t = __ldg(reinterpret_cast<const float4*>(wacc + v0));
     w[0] = t.x; w[1] = t.y; w[2] = t.z; w[3] = t.w;
   } else {
-    w[0] = __ldg(wacc + v0);
+    w[0] = wacc ? __ldg(wacc + v0) : 1.f;  // no weight sum: the source divides itself (ResampledSrc)
   }
 #pragma unroll
   for (int k = 0; k < VEC; ++k) { best[k] = 0.f; arg[k] = 0; }
@@ -585,6 +639,27 @@ extern "C" int boa_finalize_argmax(const float* d_logits_acc, const float* d_wei
   else
     finalize_argmax_scalar_kernel<LocalSrc><<<grid_for(V, 256, 8), 256, 0, s>>>(
         src, d_weight_acc, C, V, lut, overwrite_nonzero_only, d_label_inout, d_nonfinite);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+// Finalize on a different grid than the network's (nnU-Net resampled the volume to the plan's spacing): ResampledSrc.
+extern "C" int boa_finalize_argmax_resampled(const float* d_logits_acc, const float* d_weight_acc, int C,
+                                             const int32_t* net_shape, const int32_t* out_shape, int separate_z,
+                                             const uint8_t* h_lut, int overwrite_nonzero_only, uint8_t* d_label_inout,
+                                             int32_t* d_nonfinite, void* stream) {
+  BOA_REQUIRE(d_logits_acc && d_weight_acc && net_shape && out_shape && h_lut && d_label_inout && d_nonfinite,
+              "boa_finalize_argmax_resampled: null");
+  BOA_REQUIRE(C > 0 && C <= 256, "boa_finalize_argmax_resampled: C=%d out of range", C);
+  for (int k = 0; k < 3; ++k)
+    BOA_REQUIRE(net_shape[k] >= 1 && out_shape[k] >= 1, "boa_finalize_argmax_resampled: bad shape");
+  ResampledSrc src{d_logits_acc, d_weight_acc, net_shape[0], net_shape[1], net_shape[2],
+                   out_shape[0],  out_shape[1],  out_shape[2], separate_z ? 1 : 0};
+  Lut256 lut;
+  for (int c = 0; c < 256; ++c) lut.v[c] = c < C ? h_lut[c] : 0;
+  const size_t V = (size_t)out_shape[0] * out_shape[1] * out_shape[2];
+  finalize_argmax_scalar_kernel<ResampledSrc><<<grid_for(V, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      src, nullptr, C, V, lut, overwrite_nonzero_only, d_label_inout, d_nonfinite);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }

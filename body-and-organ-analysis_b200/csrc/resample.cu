@@ -140,19 +140,23 @@ spline_prefilter_axis_kernel(const T* __restrict__ in, size_t outer, int n_in, s
   }
 }
 
-// out_mode 0: fp64 (intermediate pass);  1: int16, truncated toward zero;  2: int32, truncated toward zero
+// out_mode 0: fp64 (intermediate pass);  1: int16, truncated toward zero;  2: int32, truncated toward zero;
+//          3: fp32.
+// grid_mode 0: scipy.ndimage.zoom's default coordinates  in = out * (n_in - 1) / (n_out - 1);
+//           1: grid_mode=True (what skimage.transform.resize passes)  in = (out + 0.5) * n_in / n_out - 0.5.
 __global__ void __launch_bounds__(256)
 spline_eval_axis_kernel(const double* __restrict__ c, size_t outer, int n_in, size_t inner, int n_out, void* __restrict__ out,
-                        int out_mode) {
+                        int out_mode, int grid_mode) {
   const size_t total = outer * (size_t)n_out * inner;
-  const double zoom = n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 1.0;
+  const double zoom = grid_mode ? (double)n_in / (double)n_out
+                                : (n_out > 1 ? (double)(n_in - 1) / (double)(n_out - 1) : 1.0);
   const int n = n_in + 2 * NPAD;
   const size_t stride = (size_t)gridDim.x * blockDim.x;
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
     const size_t i0 = i % inner;
     const int k = (int)((i / inner) % (size_t)n_out);
     const size_t o = i / (inner * (size_t)n_out);
-    const double cc = (double)k * zoom + (double)NPAD;
+    const double cc = (grid_mode ? ((double)k + 0.5) * zoom - 0.5 : (double)k * zoom) + (double)NPAD;
     const double fl = floor(cc);
     const double y = cc - fl, z = 1.0 - y;
     const double w1 = (y * y * (y - 2.0) * 3.0 + 4.0) / 6.0;
@@ -165,7 +169,8 @@ spline_eval_axis_kernel(const double* __restrict__ c, size_t outer, int n_in, si
                      w3 * line[(s + 3) * inner];
     if (out_mode == 0) static_cast<double*>(out)[i] = v;
     else if (out_mode == 1) static_cast<int16_t*>(out)[i] = (int16_t)(int)v;
-    else static_cast<int32_t*>(out)[i] = (int32_t)v;
+    else if (out_mode == 2) static_cast<int32_t*>(out)[i] = (int32_t)v;
+    else static_cast<float*>(out)[i] = (float)v;
   }
 }
 
@@ -239,7 +244,122 @@ extern "C" int boa_resample_axis_cubic(const void* d_in, int in_dtype, size_t ou
     spline_prefilter_axis_kernel<double><<<blocks, 256, 0, s>>>(static_cast<const double*>(d_in), outer, n_in, inner, d_scratch);
   BOA_CHECK_LAUNCH();
   spline_eval_axis_kernel<<<grid_for(outer * (size_t)n_out * inner, 256), 256, 0, s>>>(d_scratch, outer, n_in, inner, n_out,
-                                                                                    d_out, out_mode);
+                                                                                    d_out, out_mode, 0);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+// The same 1-D pass with grid_mode=True coordinates and an optional fp32 result (out_mode 3): one axis of
+// skimage.transform.resize(order=3, mode="edge", anti_aliasing=False) = scipy.ndimage.zoom(..., mode="nearest",
+// grid_mode=True), which nnU-Net's resample_data_or_seg calls for the image data
+// (_external/nnunetv2/preprocessing/resampling/default_resampling.py:117-203).
+extern "C" int boa_resample_axis_cubic_grid(const void* d_in, int in_dtype, size_t outer, int n_in, size_t inner,
+                                            int n_out, double* d_scratch, void* d_out, int out_mode, void* stream) {
+  BOA_REQUIRE(d_in && d_scratch && d_out, "boa_resample_axis_cubic_grid: null pointer");
+  BOA_REQUIRE(n_in >= 2 && n_out >= 1 && outer > 0 && inner > 0, "boa_resample_axis_cubic_grid: bad sizes");
+  BOA_REQUIRE(in_dtype == BOA_DT_F32 || in_dtype == BOA_DT_F64, "boa_resample_axis_cubic_grid: bad input dtype %d", in_dtype);
+  BOA_REQUIRE(out_mode == 0 || out_mode == 3, "boa_resample_axis_cubic_grid: bad output mode %d", out_mode);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const unsigned blocks = (unsigned)((outer * inner + 255) / 256);
+  if (in_dtype == BOA_DT_F32)
+    spline_prefilter_axis_kernel<float><<<blocks, 256, 0, s>>>(static_cast<const float*>(d_in), outer, n_in, inner, d_scratch);
+  else
+    spline_prefilter_axis_kernel<double><<<blocks, 256, 0, s>>>(static_cast<const double*>(d_in), outer, n_in, inner, d_scratch);
+  BOA_CHECK_LAUNCH();
+  spline_eval_axis_kernel<<<grid_for(outer * (size_t)n_out * inner, 256), 256, 0, s>>>(d_scratch, outer, n_in, inner, n_out,
+                                                                                    d_out, out_mode, 1);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+// skimage.transform.resize(..., clip=True) clips its result to the value range of ITS input - one 2-D slice when nnU-Net
+// resamples slice by slice (separate z), the whole volume otherwise.  d_ref: the input of the resize [n_slices][ref_n],
+// d_data: its output [n_slices][data_n], clipped in place; d_minmax: 2 * n_slices ints of scratch.
+namespace boa {
+__device__ __forceinline__ int float_order(float f) {  // monotone map float -> int (for atomicMin / atomicMax)
+  const int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float order_float(int i) { return __int_as_float(i >= 0 ? i : i ^ 0x7fffffff); }
+
+__global__ void __launch_bounds__(256)
+slice_minmax_kernel(const float* __restrict__ ref, size_t ref_n, int chunks, int* __restrict__ minmax) {
+  const int sl = blockIdx.x / chunks, ch = blockIdx.x % chunks;
+  const size_t per = (ref_n + chunks - 1) / chunks;
+  const size_t b = (size_t)ch * per, e = b + per < ref_n ? b + per : ref_n;
+  float lo = INFINITY, hi = -INFINITY;
+  for (size_t i = b + threadIdx.x; i < e; i += 256) {
+    const float v = __ldg(ref + (size_t)sl * ref_n + i);
+    lo = fminf(lo, v);
+    hi = fmaxf(hi, v);
+  }
+  for (int off = 16; off; off >>= 1) {
+    lo = fminf(lo, __shfl_xor_sync(0xffffffffu, lo, off));
+    hi = fmaxf(hi, __shfl_xor_sync(0xffffffffu, hi, off));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&minmax[2 * sl], float_order(lo));
+    atomicMax(&minmax[2 * sl + 1], float_order(hi));
+  }
+}
+
+__global__ void __launch_bounds__(256)
+clip_slices_kernel(float* __restrict__ data, size_t data_n, int n_slices, const int* __restrict__ minmax) {
+  const size_t total = (size_t)n_slices * data_n;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int sl = (int)(i / data_n);
+    const float lo = order_float(minmax[2 * sl]), hi = order_float(minmax[2 * sl + 1]);
+    data[i] = fminf(fmaxf(data[i], lo), hi);
+  }
+}
+
+__global__ void minmax_init_kernel(int* minmax, int n_slices) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n_slices) { minmax[2 * i] = 0x7fffffff; minmax[2 * i + 1] = (int)0x80000000; }
+}
+
+// Order-0 pick along dim 0 with grid coordinates: index = floor(scale * (k + 0.5)), scale = n_in / n_out - what
+// map_coordinates(order=0, mode="nearest") does with the coordinates scale * (k + 0.5) - 0.5
+// (default_resampling.py:176-192).
+__global__ void __launch_bounds__(256)
+nearest_z_grid_f32_kernel(const float* __restrict__ in, int z_in, size_t plane, int z_out, float* __restrict__ out) {
+  const size_t total = (size_t)z_out * plane;
+  const double scale = (double)z_in / (double)z_out;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += stride) {
+    const int o = (int)(i / plane);
+    int k = (int)floor(scale * ((double)o + 0.5) - 0.5 + 0.5);
+    k = k < 0 ? 0 : (k >= z_in ? z_in - 1 : k);
+    out[i] = in[(size_t)k * plane + i % plane];
+  }
+}
+}  // namespace boa
+
+extern "C" int boa_clip_slices_f32(const float* d_ref, size_t ref_slice_voxels, float* d_data, size_t data_slice_voxels,
+                                   int n_slices, int32_t* d_minmax, void* stream) {
+  BOA_REQUIRE(d_ref && d_data && d_minmax && n_slices > 0 && ref_slice_voxels > 0 && data_slice_voxels > 0,
+              "boa_clip_slices_f32: bad argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  minmax_init_kernel<<<(n_slices + 255) / 256, 256, 0, s>>>(d_minmax, n_slices);
+  BOA_CHECK_LAUNCH();
+  int chunks = (int)((ref_slice_voxels + 65535) / 65536);
+  const int cap = (sm_count() * 8 + n_slices - 1) / n_slices;
+  chunks = chunks > cap ? cap : chunks;
+  chunks = chunks < 1 ? 1 : chunks;
+  slice_minmax_kernel<<<(unsigned)(n_slices * chunks), 256, 0, s>>>(d_ref, ref_slice_voxels, chunks, d_minmax);
+  BOA_CHECK_LAUNCH();
+  clip_slices_kernel<<<grid_for((size_t)n_slices * data_slice_voxels, 256), 256, 0, s>>>(d_data, data_slice_voxels, n_slices,
+                                                                                        d_minmax);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
+extern "C" int boa_resample_z_nearest_grid_f32(const float* d_in, int z_in, size_t plane, int z_out, float* d_out,
+                                               void* stream) {
+  BOA_REQUIRE(d_in && d_out && z_in >= 1 && z_out >= 1 && plane > 0, "boa_resample_z_nearest_grid_f32: bad argument");
+  nearest_z_grid_f32_kernel<<<grid_for((size_t)z_out * plane, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_in, z_in, plane, z_out, d_out);
   BOA_CHECK_LAUNCH();
   return BOA_OK;
 }

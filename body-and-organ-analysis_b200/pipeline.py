@@ -120,27 +120,21 @@ def predict_labels_sharded(pred: nnUNetPredictor, data: torch.Tensor, lut=None, 
 
 
 def check_plan_geometry(spec, cropped_shape, spacing_zyx) -> None:
-    """DefaultPreprocessor.run_case_npy also applies plans.transpose_forward and resamples the cropped, normalised
-    volume to the configuration's spacing (default_preprocessor.py:57-90), and export_prediction resamples the logits
-    back before the argmax (export_prediction.py:25-34).  Both are identities on this path when the caller hands in a
-    volume whose grid is the plan's (`total`: TotalSegmentator resamples to 1.5 mm first).  Anything else would
-    silently run the network at the wrong scale, so it raises instead."""
+    """DefaultPreprocessor.run_case_npy applies plans.transpose_forward (only the identity is implemented: anything
+    else raises instead of silently producing a transposed result) and resamples the cropped, normalised volume to the
+    configuration's spacing (default_preprocessor.py:57-90).  Returns that target spacing (None: no spacing given, the
+    caller vouches for the grid)."""
     if list(spec.transpose_forward) != [0, 1, 2] or list(spec.transpose_backward) != [0, 1, 2]:
         raise NotImplementedError(
             f"plans.json asks for transpose_forward={list(spec.transpose_forward)} / transpose_backward="
             f"{list(spec.transpose_backward)}: only the identity is implemented (every BOA model is trained with it)")
     if spacing_zyx is None:
-        return
+        return None
     target = list(spec.spacing)
     if len(target) < 3:  # 2d configurations keep the slice spacing (default_preprocessor.py:72-75)
         target = [spacing_zyx[0]] + target
     # compute_new_shape (default_resampling.py:25-31); the reference resamples iff the shape changes (:139)
-    new_shape = [int(round(float(i) / float(j) * int(k))) for i, j, k in zip(spacing_zyx, target, cropped_shape)]
-    if new_shape != [int(v) for v in cropped_shape]:
-        raise NotImplementedError(
-            f"input grid {tuple(int(v) for v in cropped_shape)} @ {tuple(float(v) for v in spacing_zyx)} mm is not the "
-            f"plan's grid ({tuple(new_shape)} @ {tuple(target)} mm): nnU-Net's internal resampling to the "
-            "configuration spacing (and of the logits back) is not implemented")
+    return target
 
 
 def _preprocess(ct: torch.Tensor, spec, spacing_zyx=None, box=None) -> tuple[torch.Tensor, list]:
@@ -149,10 +143,15 @@ def _preprocess(ct: torch.Tensor, spec, spacing_zyx=None, box=None) -> tuple[tor
     if box is None:
         box = nonzero_bbox(ct)
     crop = ct[box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]].contiguous()
-    check_plan_geometry(spec, crop.shape, spacing_zyx)
+    target = check_plan_geometry(spec, crop.shape, spacing_zyx)
     p = spec.intensity
     norm = passes.ct_normalize(crop, float(p["percentile_00_5"]), float(p["percentile_99_5"]), float(p["mean"]),
                                float(p["std"]))
+    if target is not None:
+        # normalise first, then resample to the plan's spacing (default_preprocessor.py:76-90); identity when the
+        # shape does not change (`total`: TotalSegmentator resampled to 1.5 mm already)
+        from .resample import resample_to_plan_spacing
+        norm = resample_to_plan_spacing(norm, spacing_zyx, target)
     return norm[None], box
 
 
@@ -184,6 +183,8 @@ def _segment_task_peers(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spa
     preds = [zoo.get(tid, folds, step_size) for tid in task_ids]
     if any(int(s) < int(p) for pr in preds for s, p in zip(ct.shape, pr.patch_size)):
         return None
+    if any(_plan_shape(pr.spec, ct.shape, spacing_zyx) != tuple(ct.shape) for pr in preds):
+        return None  # nnU-Net's own resampling to the plan's spacing: general path
     rank, world = dist_ctx.rank, dist_ctx.world_size
     Y, X = int(ct.shape[1]), int(ct.shape[2])
     plans = []
@@ -221,6 +222,15 @@ def _segment_task_peers(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spa
     return out
 
 
+def _plan_shape(spec, cropped_shape, spacing_zyx) -> tuple:
+    """Shape of the network's grid for a cropped volume of this shape (compute_new_shape, default_resampling.py:25-31)."""
+    from .resample import nnunet_new_shape
+    target = check_plan_geometry(spec, cropped_shape, spacing_zyx)
+    if target is None:
+        return tuple(int(v) for v in cropped_shape)
+    return nnunet_new_shape(cropped_shape, spacing_zyx, target)
+
+
 def _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spacing_zyx=None) -> torch.Tensor:
     if dist_ctx is not None and dist_ctx.world_size > 1 and ct.is_cuda:
         ex = dist_ctx.peer_exchange(ct.device)
@@ -239,7 +249,26 @@ def _segment_task_whole(ct, zoo, task_ids, folds, step_size, luts, dist_ctx, spa
         sl = tuple(slice(b, e) for b, e in box)
         full = all(b == 0 and e == s for (b, e), s in zip(box, ct.shape))
         lut = luts[i] if luts is not None else None
-        if full:
+        cropped_shape = tuple(e - b for b, e in box)
+        if tuple(data.shape[1:]) != cropped_shape:
+            # the network runs on the plan's grid; the logits come back to the cropped grid (order 1) inside the argmax
+            # pass (export_prediction.py:25-38)
+            from .resample import nnunet_separate_z
+            if dist_ctx is not None and dist_ctx.world_size > 1:
+                raise NotImplementedError("multi-GPU prediction of a volume that nnU-Net resamples to the plan's "
+                                          "spacing is not implemented")
+            target = check_plan_geometry(pred.spec, cropped_shape, spacing_zyx)
+            sep, axis = nnunet_separate_z(target, spacing_zyx)  # current = plan spacing, new = original spacing
+            if sep and axis != 0:
+                raise NotImplementedError("separate-z resampling along an in-plane axis is not implemented")
+            lab = pred.predict_labels(data, lut, defer=flags, resample_to=cropped_shape, separate_z=sep)
+            view = out[sl]
+            if multi:
+                nz = lab != 0
+                view[nz] = lab[nz]
+            else:
+                view.copy_(lab)
+        elif full:
             predict_labels_sharded(pred, data, lut, out, overwrite_nonzero_only=multi, dist_ctx=dist_ctx, defer=flags)
         else:
             lab = predict_labels_sharded(pred, data, lut, dist_ctx=dist_ctx, defer=flags)

@@ -206,6 +206,24 @@ def finalize_argmax(acc: torch.Tensor, wsum: torch.Tensor, lut=None, label_inout
     return label_inout
 
 
+def finalize_argmax_resampled(acc: torch.Tensor, wsum: torch.Tensor, out_shape, separate_z: bool, lut=None,
+                              defer: list | None = None) -> torch.Tensor:
+    """finalize_argmax when the network ran on a grid nnU-Net resampled the volume to: logits / n are resampled with
+    order 1 to out_shape before the argmax (export_prediction.py:25-38), fused into the argmax pass."""
+    Cn = acc.shape[0]
+    out = torch.zeros(tuple(int(v) for v in out_shape), dtype=torch.uint8, device=acc.device)
+    lut_arr = (C.c_uint8 * Cn)(*(range(Cn) if lut is None else [int(v) for v in lut]))
+    bad = torch.zeros(1, dtype=torch.int32, device=acc.device)
+    _lib.check(_lib.lib().boa_finalize_argmax_resampled(_lib.ptr(acc), _lib.ptr(wsum), Cn, _lib.i32x3(wsum.shape),
+                                                        _lib.i32x3(out_shape), int(separate_z), lut_arr, 0,
+                                                        _lib.ptr(out), _lib.ptr(bad), _lib.stream_ptr()))
+    if defer is not None:
+        defer.append(bad)
+    elif int(bad.item()) != 0:
+        raise RuntimeError(INF_MESSAGE)
+    return out
+
+
 class nnUNetPredictor:
     def __init__(self, tile_step_size: float = 0.5, use_gaussian: bool = True, use_mirroring: bool = True,
                  perform_everything_on_device: bool = True, device=None, verbose: bool = False,
@@ -316,13 +334,28 @@ class nnUNetPredictor:
 
     @torch.inference_mode()
     def predict_labels(self, input_image: torch.Tensor, lut=None, label_inout: torch.Tensor | None = None,
-                       overwrite_nonzero_only: bool = False, defer: list | None = None) -> torch.Tensor:
-        """[c,x,y,z] -> uint8 label map [x,y,z] on the device; logits never leave HBM."""
+                       overwrite_nonzero_only: bool = False, defer: list | None = None, resample_to=None,
+                       separate_z: bool = False) -> torch.Tensor:
+        """[c,x,y,z] -> uint8 label map [x,y,z] on the device; logits never leave HBM.
+        resample_to: shape of the volume BEFORE nnU-Net's preprocessing resampled it to the plan's spacing - the label
+        map is produced on that grid (logits resampled with order 1 inside the argmax pass)."""
         with torch.cuda.device(self.device_index):
             vol, origins, unpad = self._prepare(input_image)
             acc = self.accumulate(vol, origins)
             w = weight_sum(vol.shape, self.patch_size, origins, self.gaussian(), self.gaussian_kind)
             padded = any(s.start != 0 or s.stop != d for s, d in zip(unpad, vol.shape))
+            if resample_to is not None and tuple(resample_to) != tuple(input_image.shape[1:]):
+                if padded:  # un-pad first (predict_from_raw_data.py:679), then resample
+                    acc = acc[(slice(None), *unpad)].contiguous()
+                    w = w[unpad].contiguous()
+                lab = finalize_argmax_resampled(acc, w, resample_to, separate_z, lut, defer=defer)
+                if label_inout is None:
+                    return lab
+                if overwrite_nonzero_only:
+                    label_inout[lab != 0] = lab[lab != 0]
+                else:
+                    label_inout.copy_(lab)
+                return label_inout
             if padded:
                 lab = finalize_argmax(acc, w, lut, defer=defer)[unpad].contiguous()
                 if label_inout is None:

@@ -101,3 +101,87 @@ def resample_labels_nearest(labels: torch.Tensor, out_shape) -> torch.Tensor:
         _lib.check(_lib.lib().boa_resample_nearest_u8(_lib.ptr(labels), _lib.i32x3(labels.shape), _lib.i32x3(out_shape),
                                                       _lib.ptr(out), _lib.stream_ptr()))
     return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# nnU-Net's own resampling between the image grid and the plan's spacing
+# (_external/nnunetv2/preprocessing/preprocessors/default_preprocessor.py:57-90 on the way in,
+#  _external/nnunetv2/inference/export_prediction.py:25-38 on the way out;
+#  resample_data_or_seg_to_shape / determine_do_sep_z_and_axis / compute_new_shape:
+#  _external/nnunetv2/preprocessing/resampling/default_resampling.py:14-203, ANISO_THRESHOLD = 3 in configuration.py)
+ANISO_THRESHOLD = 3.0
+
+
+def nnunet_new_shape(shape, old_spacing, new_spacing) -> tuple:
+    """compute_new_shape (default_resampling.py:25-31)."""
+    return tuple(int(round(float(i) / float(j) * int(k))) for i, j, k in zip(old_spacing, new_spacing, shape))
+
+
+def nnunet_separate_z(current_spacing, new_spacing):
+    """determine_do_sep_z_and_axis(force_separate_z=None, ...) (default_resampling.py:34-67): (do_separate_z, axis)."""
+    def aniso(sp):
+        return (max(sp) / min(sp)) > ANISO_THRESHOLD
+
+    def lowres_axis(sp):
+        sp = np.asarray(sp, dtype=np.float64)
+        return np.where(sp.max() / sp == 1)[0]
+
+    if aniso(current_spacing):
+        axis = lowres_axis(current_spacing)
+    elif aniso(new_spacing):
+        axis = lowres_axis(new_spacing)
+    else:
+        return False, None
+    if len(axis) != 1:  # (0.24, 1.25, 1.25)-like spacings: no separate treatment of the out-of-plane axis
+        return False, None
+    return True, int(axis[0])
+
+
+def _cubic_grid_axis(cur: torch.Tensor, axis: int, n_out: int, last: bool) -> torch.Tensor:
+    shape = list(cur.shape)
+    outer = int(np.prod(shape[:axis], dtype=np.int64))
+    inner = int(np.prod(shape[axis + 1:], dtype=np.int64))
+    n_in = shape[axis]
+    if n_in < 2:
+        raise ValueError("an axis of length 1 cannot be resampled")
+    scratch = torch.empty((outer * (n_in + 24) * inner,), dtype=torch.float64, device=cur.device)
+    shape[axis] = n_out
+    nxt = torch.empty(shape, dtype=torch.float32 if last else torch.float64, device=cur.device)
+    dt = _lib.BOA_DT_F32 if cur.dtype == torch.float32 else _lib.BOA_DT_F64
+    _lib.check(_lib.lib().boa_resample_axis_cubic_grid(_lib.ptr(cur), dt, outer, n_in, inner, n_out, _lib.ptr(scratch),
+                                                       _lib.ptr(nxt), 3 if last else 0, _lib.stream_ptr()))
+    return nxt
+
+
+def resample_to_plan_spacing(data: torch.Tensor, current_spacing, new_spacing) -> torch.Tensor:
+    """resampling_fn_data of the plans = resample_data_or_seg_to_shape(data, new_shape, current, new, is_seg=False,
+    order=3, order_z=0, force_separate_z=None): the NORMALISED fp32 volume [z,y,x] -> fp32 volume on the plan's grid.
+    skimage.transform.resize(order=3, mode="edge", anti_aliasing=False, clip=True) is scipy's cubic zoom with
+    grid_mode coordinates, clipped to the value range of its input - per slice when the anisotropic axis is resampled
+    separately (order 0 along it), over the whole volume otherwise."""
+    if not (data.is_cuda and data.is_contiguous() and data.dim() == 3 and data.dtype == torch.float32):
+        raise ValueError("resample_to_plan_spacing needs a contiguous fp32 [z,y,x] CUDA tensor")
+    new_shape = nnunet_new_shape(data.shape, current_spacing, new_spacing)
+    if tuple(new_shape) == tuple(data.shape):
+        return data  # default_resampling.py:139: "no resampling necessary"
+    sep, axis = nnunet_separate_z(current_spacing, new_spacing)
+    if sep and axis != 0:
+        raise NotImplementedError("separate-z resampling along an in-plane axis is not implemented (slices are dim 0)")
+    L = _lib.lib()
+    with torch.cuda.device(data.device):
+        axes = [a for a in ((1, 2) if sep else (0, 1, 2)) if new_shape[a] != data.shape[a]]
+        cur = data
+        for k, a in enumerate(axes):
+            cur = _cubic_grid_axis(cur, a, new_shape[a], last=k == len(axes) - 1)
+        if axes:
+            n_slices = int(data.shape[0]) if sep else 1
+            mm = torch.empty(2 * n_slices, dtype=torch.int32, device=data.device)
+            _lib.check(L.boa_clip_slices_f32(_lib.ptr(data), data.numel() // n_slices, _lib.ptr(cur),
+                                             cur.numel() // n_slices, n_slices, _lib.ptr(mm), _lib.stream_ptr()))
+        if sep and new_shape[0] != cur.shape[0]:
+            out = torch.empty((new_shape[0], cur.shape[1], cur.shape[2]), dtype=torch.float32, device=data.device)
+            _lib.check(L.boa_resample_z_nearest_grid_f32(_lib.ptr(cur), int(cur.shape[0]),
+                                                         int(cur.shape[1] * cur.shape[2]), int(new_shape[0]),
+                                                         _lib.ptr(out), _lib.stream_ptr()))
+            cur = out
+    return cur

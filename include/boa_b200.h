@@ -191,6 +191,24 @@ int boa_resample_axis_cubic(const void* d_in, int in_dtype, size_t outer, int n_
 /* Order-0 zoom of a uint8 label map [z][y][x] from in_shape to out_shape (host int32[3] each). */
 int boa_resample_nearest_u8(const uint8_t* d_in, const int32_t* in_shape, const int32_t* out_shape, uint8_t* d_out,
                             void* stream);
+/* One axis of skimage.transform.resize(order=3, mode="edge", anti_aliasing=False) = scipy.ndimage.zoom(order=3,
+ * mode="nearest", grid_mode=True): what nnU-Net's DefaultPreprocessor resamples the NORMALISED image with
+ * (_external/nnunetv2/preprocessing/resampling/default_resampling.py:117-203, default_preprocessor.py:57-90).  Same
+ * addressing as boa_resample_axis_cubic; in_dtype fp32 / fp64; out_mode 0 = fp64 (intermediate pass), 3 = fp32. */
+int boa_resample_axis_cubic_grid(const void* d_in, int in_dtype, size_t outer, int n_in, size_t inner, int n_out,
+                                 double* d_scratch, void* d_out, int out_mode, void* stream);
+/* resize(..., clip=True): clip d_data [n_slices][data_slice_voxels] in place to the value range of the matching slice
+ * of the resize's input d_ref [n_slices][ref_slice_voxels] (n_slices = 1: whole volume).  d_minmax: 2 * n_slices ints. */
+int boa_clip_slices_f32(const float* d_ref, size_t ref_slice_voxels, float* d_data, size_t data_slice_voxels,
+                        int n_slices, int32_t* d_minmax, void* stream);
+/* Order-0 pick along dim 0 with grid coordinates (order_z = 0 of the separate-z branch, default_resampling.py:176-192). */
+int boa_resample_z_nearest_grid_f32(const float* d_in, int z_in, size_t plane, int z_out, float* d_out, void* stream);
+/* boa_finalize_argmax when the network ran on a resampled grid: every class channel of logits / n is resampled with
+ * order 1 from net_shape to out_shape before the argmax (export_prediction.py:25-38; separate_z: order-0 pick along
+ * dim 0, bilinear in plane).  d_logits_acc [C][net_shape], d_weight_acc [net_shape], d_label_inout [out_shape]. */
+int boa_finalize_argmax_resampled(const float* d_logits_acc, const float* d_weight_acc, int C, const int32_t* net_shape,
+                                  const int32_t* out_shape, int separate_z, const uint8_t* h_lut,
+                                  int overwrite_nonzero_only, uint8_t* d_label_inout, int32_t* d_nonfinite, void* stream);
 
 /* In-plane 3x3 median of every z-slice, boundary mode "reflect": scipy.ndimage.median_filter(image, size=[1,3,3]) of
  * subclassify_tissues(median_filtering=True) (_external/body_composition_analysis/tissue/subclassification.py:20-36,

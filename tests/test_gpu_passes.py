@@ -245,3 +245,45 @@ def test_median3x3_slices_vs_scipy(cuda, shape):
     from boa_b200 import bca
     tis = bca.subclassify_tissues(_dev(ct), _dev(regions), median_filtering=True).cpu().numpy()
     assert np.array_equal(tis, op.subclassify_tissues(ndimage.median_filter(ct, size=[1, 3, 3]), regions))
+
+
+@pytest.mark.parametrize("shape,cur,new", [((12, 40, 36), (5.0, 0.9, 0.9), (5.0, 1.5, 1.5)),     # separate z, 2-D cubic per slice
+                                           ((10, 30, 44), (6.0, 1.0, 1.0), (5.0, 0.8, 0.8)),     # separate z + order-0 pick along z
+                                           ((20, 24, 28), (1.0, 0.8, 0.8), (1.5, 1.5, 1.5)),     # 3-D cubic
+                                           ((9, 33, 31), (5.0, 1.5, 1.5), (5.0, 1.5, 1.5))])      # identity
+def test_resample_to_plan_spacing_vs_oracle(cuda, shape, cur, new):
+    """nnU-Net's own resampling of the normalised volume to the plan's spacing (default_preprocessor.py:57-90)."""
+    from boa_b200.resample import nnunet_new_shape, resample_to_plan_spacing
+    from oracle import resampling as orr
+    rng = np.random.default_rng(6)
+    data = rng.standard_normal(shape).astype(np.float32)
+    data[:, :5] = -2.2  # a flat border: cubic overshoot at its edge is what the clip acts on
+    ref = orr.resample_data(data[None], orr.compute_new_shape(shape, cur, new), cur, new, order=3)[0]
+    got = resample_to_plan_spacing(_dev(data), cur, new).cpu().numpy()
+    assert got.shape == ref.shape == nnunet_new_shape(shape, cur, new)
+    assert np.allclose(got, ref, rtol=0, atol=2e-6), np.abs(got - ref).max()
+
+
+@pytest.mark.parametrize("net_shape,out_shape,cur,new", [((8, 20, 24), (8, 33, 40), (5.0, 1.5, 1.5), (5.0, 0.9, 0.9)),
+                                                         ((10, 18, 22), (12, 30, 37), (6.0, 1.5, 1.5), (5.0, 0.9, 0.9)),
+                                                         ((12, 14, 16), (18, 26, 30), (1.5, 1.5, 1.5), (1.0, 0.8, 0.8))])
+def test_finalize_argmax_resampled_vs_oracle(cuda, net_shape, out_shape, cur, new):
+    """Logits / n resampled with order 1 to the pre-resampling shape, then argmax (export_prediction.py:25-38)."""
+    from boa_b200.predictor import finalize_argmax_resampled
+    from boa_b200.resample import nnunet_separate_z
+    from oracle import resampling as orr
+    rng = np.random.default_rng(8)
+    C = 5
+    w = rng.uniform(0.5, 10.0, size=net_shape).astype(np.float32)
+    logits = (rng.standard_normal((C, *net_shape)) * 3).astype(np.float32)
+    acc = (logits * w).astype(np.float32)
+    q = acc / w  # what the reference resamples
+    ref = orr.logits_to_segmentation(q, out_shape, cur, new)
+    sep, axis = nnunet_separate_z(cur, new)
+    assert (sep, axis) == orr.determine_do_sep_z_and_axis(cur, new)
+    got = finalize_argmax_resampled(_dev(acc), _dev(w), out_shape, sep).cpu().numpy()
+    r = orr.resample_data(q.astype(np.float64), out_shape, cur, new, order=1)
+    top2 = np.sort(r, axis=0)[-2:]
+    safe = (top2[1] - top2[0]) > 1e-4  # fp32 quotients vs the oracle's fp64 interpolation
+    assert got.shape == ref.shape
+    assert np.array_equal(got[safe], ref[safe]) and (got == ref).mean() > 0.9999

@@ -155,3 +155,27 @@ def test_total_on_a_volume_that_is_not_at_1_5_mm(cuda, small_zoo):
     ref_meas.pop("_ct_pfav_mask")
     from test_oracle_golden import _close
     _close(ref_meas, res.total_measurements)
+
+
+def test_volume_off_the_plans_grid_is_resampled_like_nnunet(cuda, small_zoo):
+    """A 5 mm volume whose in-plane spacing is not the plan's (every real CT for the body-composition nets, which are
+    only resampled in thickness before nnU-Net sees them): nnU-Net's preprocessing resamples the NORMALISED volume to
+    the plan's spacing (order 3, slice by slice - separate z) and the export resamples the logits back (order 1) before
+    the argmax (default_preprocessor.py:57-90, export_prediction.py:25-38).  Against the oracle's restatement."""
+    from boa_b200.pipeline import segment_bca_net
+    from oracle import resampling as orr
+    specs, mz = small_zoo
+    spec = specs[543]
+    ct5 = zoo.synthetic_ct((36, 72, 80), seed=8)
+    sp = (5.0, 0.9, 0.9)                      # plan: (5.0, 1.5, 1.5)
+    lab = segment_bca_net(torch.from_numpy(ct5).cuda(), mz, "body_parts", fast=True, spacing_zyx=sp).cpu().numpy()
+    assert lab.shape == ct5.shape
+    norm = op.ct_normalize(ct5, spec.intensity)[None]
+    new_shape = orr.compute_new_shape(ct5.shape, sp, spec.spacing)
+    assert new_shape == (36, 43, 48)
+    data = orr.resample_data(norm, new_shape, sp, spec.spacing, order=3).astype(np.float32)
+    logits = predict_sliding_window_return_logits(spec.arch, [spec.fold_weights[0]], data, 0.5, emulate_fp16=True)
+    ref = orr.logits_to_segmentation(logits, ct5.shape, spec.spacing, sp)
+    agree = (lab == ref).mean()
+    print(f"body_parts on a (5.0, 0.9, 0.9) mm volume: agreement with the oracle {agree:.5f}")
+    assert agree > 0.99

@@ -178,16 +178,21 @@ def test_triple_split_ranges_stitch_like_the_reference():
     assert needs_triple_split((154, 512, 512), False, force_split=True)
 
 
-def test_non_identity_transpose_and_foreign_spacing_raise():
+def test_plan_geometry_transpose_raises_and_resampling_decisions_match_the_oracle():
     from boa_b200.pipeline import check_plan_geometry
     from boa_b200.plans import ModelSpec
+    from boa_b200.resample import nnunet_new_shape, nnunet_separate_z
+    from oracle import resampling as orr
     spec = ModelSpec(arch={}, intensity={}, labels={}, transpose_forward=[0, 2, 1], transpose_backward=[0, 2, 1],
                      spacing=[1.5] * 3, configuration="3d_fullres")
     with pytest.raises(NotImplementedError, match="transpose_forward"):
         check_plan_geometry(spec, (64, 64, 64), None)
     spec.transpose_forward = spec.transpose_backward = [0, 1, 2]
-    check_plan_geometry(spec, (64, 64, 64), (1.5, 1.5, 1.5))
-    check_plan_geometry(spec, (64, 64, 64), None)
-    spec.spacing = [5.0, 0.8, 0.8]
-    with pytest.raises(NotImplementedError, match="plan's grid"):
-        check_plan_geometry(spec, (64, 512, 512), (5.0, 0.7, 0.7))
+    assert check_plan_geometry(spec, (64, 64, 64), None) is None
+    assert check_plan_geometry(spec, (64, 64, 64), (1.0, 1.0, 1.0)) == [1.5, 1.5, 1.5]
+    # compute_new_shape / determine_do_sep_z_and_axis (default_resampling.py:14-67) against the oracle's restatement
+    for shape, cur, new in (((64, 512, 512), (5.0, 0.7, 0.7), (5.0, 0.8, 0.8)), ((30, 100, 90), (6.0, 1.0, 1.0), (5.0, 0.8, 0.8)),
+                            ((80, 90, 100), (1.0, 0.8, 0.8), (1.5, 1.5, 1.5)), ((40, 50, 60), (0.24, 1.25, 1.25), (1.0, 1.0, 1.0)),
+                            ((40, 50, 60), (1.0, 1.0, 4.0), (1.0, 1.0, 1.0))):
+        assert nnunet_new_shape(shape, cur, new) == orr.compute_new_shape(shape, cur, new)
+        assert nnunet_separate_z(cur, new) == orr.determine_do_sep_z_and_axis(cur, new)
