@@ -6,7 +6,7 @@
   generate_secondary_findings (volumes) / create_json   (builder.py:163-361,397-444,520-598)
 The volumes are touched once by boa_tissue_subclassify and four boa_slice_label_stats passes; everything the report
 needs is then a function of the small per-slice tables [Z, L] (integer counts and HU sums), evaluated on the host.
-Plots / PDF and the breast-implant connected-component finding are out of scope.
+Plots / PDF are out of scope; the breast-implant finding labels the (small) implant mask on the host.
 """
 from __future__ import annotations
 
@@ -174,7 +174,52 @@ def _pretty_volume(value: float) -> str:
     return f"{value / 1000:.3f} L" if value >= 1000 else f"{value:.2f} mL"
 
 
-def secondary_findings(t: SliceTables, examined: AggregatableBodyPart, ml_per_voxel: float) -> list[str]:
+def breast_implant_finding(body_regions, ml_per_voxel: float) -> str | None:
+    """builder.py:363-395: 26-connected components of the BREAST_IMPLANT label larger than 10 ml, ordered by the integer
+    part of their centroid along the last array axis; one or two of them make a sentence (side = centroid against the
+    middle of array axis 1, as the reference compares them), more are an error.  The label is rare and small: only
+    its bounding box travels to the host, where scipy labels it (skimage.measure.label / regionprops in the reference)."""
+    from scipy import ndimage
+    R = BODY_REGION["BREAST_IMPLANT"]
+    if hasattr(body_regions, "is_cuda"):
+        mask_d = body_regions == R
+        if not bool(mask_d.any()):
+            return None
+        box = []
+        for ax in range(3):
+            idx = torch.nonzero(mask_d.any(dim=tuple(a for a in range(3) if a != ax))).flatten()
+            box.append((int(idx[0]), int(idx[-1]) + 1))
+        mask = mask_d[box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]].cpu().numpy()
+        off, mid_index = [b[0] for b in box], int(body_regions.shape[1]) // 2
+    else:
+        mask = np.asarray(body_regions) == R
+        if not mask.any():
+            return None
+        off, mid_index = [0, 0, 0], mask.shape[1] // 2
+    lab, n = ndimage.label(mask, structure=np.ones((3, 3, 3)))
+    props = []
+    for i in range(1, n + 1):
+        idx = np.nonzero(lab == i)
+        volume = len(idx[0]) * ml_per_voxel
+        if volume > 10:
+            props.append((float(np.mean(idx[2])) + off[2], volume))
+    props.sort(key=lambda p: int(p[0]))
+    found = [("right" if x < mid_index else "left", v) for x, v in props]
+    if len(found) == 1:
+        return (f"Patient has a single breast implant on the {found[0][0]} side with volume of "
+                f"{_pretty_volume(found[0][1])}")
+    if len(found) == 2:
+        return (f"Patient has two breast implants with volume of {_pretty_volume(found[0][1])} ({found[0][0]}) and "
+                f"{_pretty_volume(found[1][1])} ({found[1][0]})")
+    if len(found) > 2:
+        import logging
+        logging.getLogger(__name__).error("More than two breast implant segments found")
+    return None
+
+
+def secondary_findings(t: SliceTables, examined: AggregatableBodyPart, ml_per_voxel: float,
+                       body_regions=None) -> list[str]:
+    """generate_secondary_findings (builder.py:309-395).  body_regions (the label map): also look for breast implants."""
     R = BODY_REGION
     tot = t.region_counts.sum(axis=0)
     out = []
@@ -186,6 +231,10 @@ def secondary_findings(t: SliceTables, examined: AggregatableBodyPart, ml_per_vo
         v = (tot[R["MEDIASTINUM"]] + tot[R["PERICARDIUM"]]) * ml_per_voxel
         out.append(f"Volume of mediastinum is {_pretty_volume(v)}")
         out.append(f"Volume enclosed by the pericardial sack is {_pretty_volume(tot[R['PERICARDIUM']] * ml_per_voxel)}")
+        if body_regions is not None and tot[R["BREAST_IMPLANT"]] > 0:
+            sentence = breast_implant_finding(body_regions, ml_per_voxel)
+            if sentence:
+                out.append(sentence)
     return out
 
 

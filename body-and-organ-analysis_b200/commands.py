@@ -55,8 +55,7 @@ def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_f
     models = set(models)
     todo = models - IMPLEMENTED_MODELS
     if todo:
-        raise NotImplementedError(f"models {sorted(todo)} are outside the accelerated hot path (total, bca, "
-                                  "body_regions, body_parts)")
+        raise NotImplementedError(f"models {sorted(todo)} are not implemented (licence-only TotalSegmentator tasks)")
     dev_str, _, gpu_id = device.partition(":")
     if dev_str != "gpu":
         raise RuntimeError(f"device '{device}': boa_b200 has no CPU/MPS implementation, use -d gpu[:id]")
@@ -75,7 +74,8 @@ def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_f
     # existing total-measurements.json is kept (compute/inference.py:82-84,95-105; infer/infer.py:59-61)
     precomputed, keep_total_json = {}, False
     if not recompute:
-        for name in ("total", "body_parts", "body_regions"):
+        from .labels import CROP_TASKS
+        for name in ("total", "body_parts", "body_regions", *[m for m in CROP_TASKS if m in models]):
             f = out_dir / f"{name}.nii.gz"
             if f.is_file():
                 logger.info("Loading already computed %s...", name)
@@ -104,6 +104,9 @@ def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_f
             write("ct_pfav", res.ct_pfav)
             with (out_dir / "total-measurements.json").open("w") as f:
                 json.dump(res.total_measurements, f, indent=2)
+    for name, lab in res.extra.items():
+        if name not in precomputed:
+            write(name, lab, class_map(name))
     if res.body_parts is not None and "body_parts" not in precomputed:
         write("body_parts", res.body_parts, class_map("body_parts"))
     if res.body_regions is not None and "body_regions" not in precomputed:
@@ -115,6 +118,10 @@ def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_f
         if res.vertebrae:
             with (out_dir / "vertebrae.json").open("w") as f:
                 json.dump(res.vertebrae, f, indent=2)
+    if res.l3_axes_mm is not None and res.l3_axes_mm[0] is not None:
+        stats["l3_major_axis_cm"], stats["l3_minor_axis_cm"] = res.l3_axes_mm[0] / 10, res.l3_axes_mm[1] / 10
+    if res.other_findings:
+        stats["other_findings"] = " | ".join(res.other_findings)
     stats["total_time"] = time.time() - start
     stats.update({f"gpu_{k}_seconds": v for k, v in res.timings.items()})
     with (out_dir / "debug_information.txt").open("w") as f:

@@ -24,9 +24,10 @@ ALL_MODELS = frozenset({"bca", "body_parts", "body_regions", "cerebral_bleed", "
                         "lung_vessels", "pleural_pericard_effusion", "total"})
 LICENSE_MODELS = frozenset({"heartchambers_highres"})
 AVAILABLE_MODELS = ALL_MODELS | LICENSE_MODELS
-# What this framework computes (the hot path of BASELINE.json).  The remaining tasks are further nnU-Net models behind
-# crop pre-passes; asking for them raises NotImplementedError in commands.analyze_ct.
-IMPLEMENTED_MODELS = frozenset({"total", "bca", "body_regions", "body_parts"})
+# What this framework computes: the hot path of BASELINE.json and the tasks behind a crop pre-pass (SURVEY.md 8f rank 3,
+# labels.CROP_TASKS) - i.e. everything `--models all` selects.  The licence-only model raises NotImplementedError in
+# commands.analyze_ct.
+IMPLEMENTED_MODELS = frozenset(ALL_MODELS)
 
 _TRUE_WORDS = ("1", "true")
 _PLACEHOLDERS = ("", "todo")

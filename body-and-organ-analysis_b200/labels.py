@@ -12,6 +12,21 @@ TOTAL_TASK_IDS = [291, 292, 293, 294, 295]           # totalsegmentator/python_a
 TOTAL_FAST_TASK_ID = 297                              # --fast-total: one 3 mm model, all 117 classes (python_api.py:169-175)
 BODY_REGIONS_TASK_ID, BODY_PARTS_TASK_ID = 542, 543  # body_composition_analysis/tasks.py:15-48
 
+# Tasks behind a crop pre-pass (totalsegmentator/python_api.py:236-330,673-736): a rough 6 mm `total` segmentation
+# (model 298) gives the bounding box of the listed structures (+ 20 mm, :726), the task's own network then runs on the
+# cropped volume at its native spacing.  task -> (dataset id, folds (None = every fold in the folder), crop structures)
+CROP_PREPASS_TASK_ID = 298
+_LUNG_LOBES = ["lung_upper_lobe_left", "lung_lower_lobe_left", "lung_upper_lobe_right", "lung_middle_lobe_right",
+               "lung_lower_lobe_right"]
+CROP_TASKS = {
+    "lung_vessels": (258, [0], _LUNG_LOBES),
+    "cerebral_bleed": (150, [0], ["brain"]),
+    "hip_implant": (260, [0], ["femur_left", "femur_right", "hip_left", "hip_right"]),
+    "pleural_pericard_effusion": (315, None, _LUNG_LOBES),
+    "liver_vessels": (8, [0], ["liver"]),
+}
+CROP_ADDON_MM = 20.0
+
 # body_composition_analysis/body_regions/definition.py, body_parts/definition.py, tissue/definition.py
 BODY_REGION = {"SUBCUTANEOUS_TISSUE": 1, "MUSCLE": 2, "ABDOMINAL_CAVITY": 3, "THORACIC_CAVITY": 4, "BONE": 5,
                "GLANDS": 6, "PERICARDIUM": 7, "BREAST_IMPLANT": 8, "MEDIASTINUM": 9, "BRAIN": 10, "NERVOUS_SYSTEM": 11}

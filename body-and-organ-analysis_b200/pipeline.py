@@ -23,7 +23,8 @@ from torch.cuda import nvtx  # NVTX ranges around the stages (visible in nsys / 
 
 from . import bca, passes
 from .dist import DistContext, exchange_slabs, gather_label_slabs, plan_shards
-from .labels import BODY_PARTS_TASK_ID, BODY_REGIONS_TASK_ID, TOTAL_FAST_TASK_ID, TOTAL_TASK_IDS, part_luts
+from .labels import (BODY_PARTS_TASK_ID, BODY_REGIONS_TASK_ID, CROP_ADDON_MM, CROP_PREPASS_TASK_ID, CROP_TASKS,
+                     TOTAL_FAST_TASK_ID, TOTAL_TASK_IDS, class_map, part_luts)
 from .measurements import compute_measurements_on_device, enqueue_measurements
 from .plans import find_model_folder, load_model_folder
 from .predictor import finalize_argmax, nnUNetPredictor, raise_if_nonfinite, weight_sum
@@ -31,7 +32,9 @@ from .predictor import finalize_argmax, nnUNetPredictor, raise_if_nonfinite, wei
 TRAINERS = {**{t: "nnUNetTrainerNoMirroring" for t in TOTAL_TASK_IDS},
             TOTAL_FAST_TASK_ID: "nnUNetTrainer_4000epochs_NoMirroring",
             BODY_REGIONS_TASK_ID: "nnUNetTrainerNoMirroring",
-            BODY_PARTS_TASK_ID: "nnUNetTrainer_1500epochs_NoMirroring"}
+            BODY_PARTS_TASK_ID: "nnUNetTrainer_1500epochs_NoMirroring",
+            CROP_PREPASS_TASK_ID: "nnUNetTrainer_4000epochs_NoMirroring",
+            **{tid: "nnUNetTrainer" for tid, _, _ in CROP_TASKS.values()}}
 
 
 class ModelZoo:
@@ -56,7 +59,8 @@ class ModelZoo:
         return zoo
 
     def get(self, task_id: int, folds, step_size: float) -> nnUNetPredictor:
-        key = (task_id, tuple(folds), step_size)
+        """folds None = every fold of the model (nnU-Net's auto-detection, predict_from_raw_data.py:131-140)."""
+        key = (task_id, None if folds is None else tuple(folds), step_size)
         if key not in self._cache:
             p = nnUNetPredictor(tile_step_size=step_size, use_gaussian=True, use_mirroring=False,
                                 perform_everything_on_device=True, device=self.device, max_batch=self.max_batch,
@@ -64,7 +68,8 @@ class ModelZoo:
             if getattr(self, "_specs", None) is not None:
                 import copy
                 spec = copy.copy(self._specs[task_id])
-                spec.fold_weights = [self._specs[task_id].fold_weights[int(f)] for f in folds]
+                if folds is not None:
+                    spec.fold_weights = [self._specs[task_id].fold_weights[int(f)] for f in folds]
                 p.manual_initialization(spec)
             else:
                 p.initialize_from_trained_model_folder(find_model_folder(self.root, task_id, TRAINERS[task_id]), folds)
@@ -296,6 +301,48 @@ def segment_total_fast(ct_3mm: torch.Tensor, zoo: ModelZoo, dist_ctx: DistContex
     return segment_task(ct_3mm, zoo, [TOTAL_FAST_TASK_ID], [0], 0.5, None, dist_ctx, spacing_zyx=spacing_zyx)
 
 
+def rough_total_6mm(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo) -> torch.Tensor:
+    """The rough organ segmentation of the crop pre-pass (totalsegmentator/python_api.py:673-712): the volume at 6 mm,
+    model 298 (`total` classes, fold 0, step 0.5), labels back on the input grid (order 0)."""
+    from .resample import resample_labels_nearest, resample_volume_cubic
+    ct6 = resample_volume_cubic(ct, spacing_zyx, 6.0)
+    seg6 = segment_task(ct6, zoo, [CROP_PREPASS_TASK_ID], [0], 0.5, None, None, spacing_zyx=(6.0, 6.0, 6.0))
+    return resample_labels_nearest(seg6, ct.shape)
+
+
+def crop_box_from_rois(rough: torch.Tensor, roi_names, spacing_zyx):
+    """crop_to_mask / get_bbox_from_mask (totalsegmentator/cropping.py:11-37,75-103): bounding box of the listed `total`
+    structures in the rough segmentation, grown by 20 mm (python_api.py:726) per axis, clipped to the volume.  None: the
+    structures are absent (the reference then returns an empty segmentation, nnunet.py:428-445)."""
+    inv = {v: k for k, v in class_map("total").items()}
+    mask = passes.label_set_mask(rough, [inv[r] for r in roi_names])
+    box = []
+    for ax in range(3):
+        other = tuple(a for a in range(3) if a != ax)
+        idx = torch.nonzero(mask.any(dim=other)).flatten()
+        if idx.numel() == 0:
+            return None
+        addon = int(CROP_ADDON_MM / float(spacing_zyx[ax]))  # mm -> voxels, truncated (cropping.py:99)
+        box.append((max(0, int(idx[0]) - addon), min(int(rough.shape[ax]), int(idx[-1]) + 1 + addon)))
+    return box
+
+
+def segment_crop_task(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, task: str, rough: torch.Tensor) -> torch.Tensor:
+    """One task behind the crop pre-pass (lung_vessels, cerebral_bleed, hip_implant, pleural_pericard_effusion,
+    liver_vessels; python_api.py:236-330): its network runs on the cropped volume at the volume's NATIVE spacing
+    (`resample=None`), i.e. nnU-Net's own preprocessing resamples to the plan's spacing and the logits come back with
+    order 1 (_segment_task_whole); the labels are put back into a zero volume (undo_crop, cropping.py:127-133)."""
+    task_id, folds, rois = CROP_TASKS[task]
+    out = torch.zeros(ct.shape, dtype=torch.uint8, device=ct.device)
+    box = crop_box_from_rois(rough, rois, spacing_zyx)
+    if box is None:
+        return out
+    sl = tuple(slice(b, e) for b, e in box)
+    crop = ct[sl].contiguous()
+    out[sl] = segment_task(crop, zoo, [task_id], folds, 0.5, None, None, spacing_zyx=tuple(float(v) for v in spacing_zyx))
+    return out
+
+
 FORCE_SPLIT_THRESHOLD = 400  # slices at 5 mm (commands.py:155-170 -> compute/inference.py:109-128)
 
 
@@ -314,6 +361,9 @@ class VolumeResult:
     body_regions: torch.Tensor | None = None
     tissues: torch.Tensor | None = None
     ct_pfav: torch.Tensor | None = None
+    extra: dict = field(default_factory=dict)   # crop-pre-pass tasks: name -> uint8 label map
+    other_findings: list | None = None          # generate_secondary_findings sentences (builder.py:309-395)
+    l3_axes_mm: tuple | None = None             # (major, minor) body axis at L3 (compute/ts_metrics.py:32-61)
     total_measurements: dict | None = None
     bca_measurements: dict | None = None
     vertebrae: dict | None = None
@@ -371,6 +421,8 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
     models = set(models)
     if "bca" in models:
         models.add("total")  # compute/config.py:54-55
+    if models & set(CROP_TASKS):
+        models.add("total")  # compute_measurements needs it (autochthon reference) and the CLI always runs it first
     pending_total = None
     # HU range of the CT: sizes the per-label histograms exactly; read once here, before any network is enqueued (the
     # only device -> host read ahead of the label maps)
@@ -405,12 +457,23 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
             stager.stage("total", res.total)
         sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
 
+        # tasks behind the crop pre-pass (`--models all`): one rough 6 mm segmentation serves all of them
+        crop_tasks = [m for m in sorted(models) if m in CROP_TASKS]
+        if crop_tasks:
+            rough = rough_total_6mm(ct, spacing_zyx, zoo)
+            for m in crop_tasks:
+                res.extra[m] = precomputed[m].to(ct.device, torch.uint8).contiguous() if m in precomputed else \
+                    segment_crop_task(ct, spacing_zyx, zoo, m, rough)
+                if stager is not None:
+                    stager.stage(m, res.extra[m])
+            del rough
+            mark("crop_tasks")
         # `total-measurements.json` needs only the CT and the `total` label map: its device passes are enqueued here and
         # the small tables travel to pinned host memory; the ~300 per-name statistics (host numpy) are evaluated at the
         # end, after the body-composition networks are enqueued, i.e. while the GPU is busy.
         if total_measurements:
             with nvtx.range("boa/total_measurements"):
-                pending_total = enqueue_measurements(ct, {"total": res.total}, sx_sy_sz, cnr_adjustment,
+                pending_total = enqueue_measurements(ct, {"total": res.total, **res.extra}, sx_sy_sz, cnr_adjustment,
                                                      return_ct_pfav_mask=True, hu_range=hu_range, dist_ctx=dist_ctx)
             res.ct_pfav = pending_total.pfav_mask
             mark("total_measurements")
@@ -491,8 +554,19 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         if stager is not None:
             stager.stage("tissues", res.tissues)
         sx_sy_sz = (spacing_zyx[2], spacing_zyx[1], spacing_zyx[0])
-        res.bca_measurements, res.vertebrae, _ = bca.build_bca_measurements(
+        res.bca_measurements, res.vertebrae, tables = bca.build_bca_measurements(
             ct, res.tissues, res.body_parts, res.body_regions, res.total, sx_sy_sz)
+        examined = bca.body_part_from_regions(tables, float(sx_sy_sz[2]))
+        res.other_findings = bca.secondary_findings(tables, examined, float(np.prod(sx_sy_sz) / 1000.0),
+                                                    body_regions=res.body_regions)
+        if res.total is not None and tables.total_counts is not None:
+            from .labels import class_map as _cm
+            from .ts_metrics import axes_of_slice
+            l3 = {v: k for k, v in _cm("total").items()}["vertebrae_L3"]
+            present = np.nonzero(tables.total_counts[:, l3] > 0)[0]
+            if present.size:  # one 2-D slice of the body mask goes to the host
+                z = int(np.median(present))
+                res.l3_axes_mm = axes_of_slice((res.body_parts[z] == 1).cpu().numpy(), (sx_sy_sz[0], sx_sy_sz[1]))
         nvtx.range_pop()
         mark("bca_measurements")
     torch.cuda.synchronize()

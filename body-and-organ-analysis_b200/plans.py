@@ -22,6 +22,7 @@ class ModelSpec:
     configuration: str
     fold_weights: list = field(default_factory=list)   # list of state dicts (name -> tensor)
     folder: str = ""
+    allowed_mirroring_axes: object = None              # `inference_allowed_mirroring_axes` of the checkpoint
 
 
 def arch_from_plans(plans: dict, configuration: str, num_input_channels: int, num_classes: int) -> dict:
@@ -91,17 +92,22 @@ def load_model_folder(model_training_output_dir: str, use_folds, checkpoint_name
         dataset_json = json.load(f)
     with open(os.path.join(model_training_output_dir, "plans.json")) as f:
         plans = json.load(f)
+    if use_folds is None:  # auto-detect (predict_from_raw_data.py:75,131-140): every fold_k with the checkpoint
+        use_folds = sorted(int(d[5:]) for d in os.listdir(model_training_output_dir)
+                           if d.startswith("fold_") and d[5:].isdigit()
+                           and os.path.isfile(os.path.join(model_training_output_dir, d, checkpoint_name)))
     if isinstance(use_folds, (str, int)):
         use_folds = [use_folds]
-    weights, configuration = [], None
+    weights, configuration, mirror = [], None, None
     for fold in use_folds:
         fold = int(fold) if fold != "all" else fold
         ckpt = torch.load(os.path.join(model_training_output_dir, f"fold_{fold}", checkpoint_name),
                           map_location="cpu", weights_only=False)
         configuration = ckpt["init_args"]["configuration"]
-        if ckpt.get("inference_allowed_mirroring_axes") is not None:
-            # the BOA path only uses *NoMirroring trainers (totalsegmentator/python_api.py:183-189)
-            raise NotImplementedError("test-time mirroring is not implemented (checkpoint allows mirroring axes)")
+        # checkpoints of the plain nnUNetTrainer allow mirroring; the reference predicts with tta=False everywhere on
+        # this path (totalsegmentator/python_api.py:708,746,752 -> disable_tta), so the axes are only recorded: the
+        # predictor refuses use_mirroring=True instead of silently skipping it
+        mirror = ckpt.get("inference_allowed_mirroring_axes")
         weights.append({k: v for k, v in ckpt["network_weights"].items()})
     labels = dataset_json["labels"]
     if any(isinstance(v, (list, tuple)) for v in labels.values()):
@@ -114,7 +120,8 @@ def load_model_folder(model_training_output_dir: str, use_folds, checkpoint_name
     return ModelSpec(arch=arch, intensity=props, labels=labels, transpose_forward=plans["transpose_forward"],
                      transpose_backward=plans["transpose_backward"],
                      spacing=plans["configurations"][configuration].get("spacing", [1, 1, 1]),
-                     configuration=configuration, fold_weights=weights, folder=model_training_output_dir)
+                     configuration=configuration, fold_weights=weights, folder=model_training_output_dir,
+                     allowed_mirroring_axes=mirror)
 
 
 def find_model_folder(results_root: str, dataset_id: int, trainer: str, plans: str = "nnUNetPlans",

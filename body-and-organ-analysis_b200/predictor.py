@@ -250,8 +250,11 @@ class nnUNetPredictor:
 
     def manual_initialization(self, spec: ModelSpec) -> None:
         if self.use_mirroring:
-            # the checkpoints of this path disallow mirroring (nnUNetTrainerNoMirroring): the reference then runs
-            # without TTA (predict_from_raw_data.py:542-557), and so do we; nothing else is implemented.
+            # checkpoints of the *NoMirroring trainers disallow mirroring: the reference then runs without TTA
+            # (predict_from_raw_data.py:542-557) and so do we.  Mirroring a checkpoint that allows it is not implemented.
+            if getattr(spec, "allowed_mirroring_axes", None):
+                raise NotImplementedError("test-time mirroring is not implemented: construct the predictor with "
+                                          "use_mirroring=False (what the reference does on this path, tta=False)")
             self.use_mirroring = False
         self.spec = spec
         donor = self._donor.networks[0] if (self._donor is not None and self._donor.networks) else None

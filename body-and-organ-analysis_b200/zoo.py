@@ -24,9 +24,21 @@ DATASETS = {
     294: ("Dataset294_TotalSegmentator_part4_muscles_1559subj", "nnUNetTrainerNoMirroring", 24),
     295: ("Dataset295_TotalSegmentator_part5_ribs_1559subj", "nnUNetTrainerNoMirroring", 27),
     297: ("Dataset297_TotalSegmentator_total_3mm_1559subj", "nnUNetTrainer_4000epochs_NoMirroring", 118),
+    298: ("Dataset298_TotalSegmentator_total_6mm_1559subj", "nnUNetTrainer_4000epochs_NoMirroring", 118),
+    258: ("Dataset258_lung_vessels_248subj", "nnUNetTrainer", 3),
+    150: ("Dataset150_icb_v0", "nnUNetTrainer", 2),
+    260: ("Dataset260_hip_implant_71subj", "nnUNetTrainer", 2),
+    315: ("Dataset315_thoraxCT", "nnUNetTrainer", 4),
+    8: ("Dataset008_HepaticVessel", "nnUNetTrainer", 3),
     542: ("Dataset542_BodyRegions", "nnUNetTrainerNoMirroring", 12),
     543: ("Dataset543_BodyParts", "nnUNetTrainer_1500epochs_NoMirroring", 7),
 }
+
+
+# plan spacing of the synthetic models: the 3 mm / 6 mm `total` models, and the crop-task models at a spacing that is
+# NOT the test volumes' (their networks run at native resolution, so nnU-Net's own resampling is exercised)
+_SPACING = {297: (3.0, 3.0, 3.0), 298: (6.0, 6.0, 6.0), 258: (1.0, 1.0, 1.0), 150: (1.0, 1.0, 1.0), 260: (1.25, 1.25, 1.25),
+            315: (2.0, 2.0, 2.0), 8: (1.0, 1.0, 1.0)}
 
 
 def default_plans(patch=(128, 128, 128), base=32, max_features=320, n_stages=6, spacing=(1.5, 1.5, 1.5),
@@ -131,7 +143,7 @@ def write_zoo(root: str, patch=(128, 128, 128), base=32, max_features=320, n_sta
     for did, (name, trainer, ncls) in DATASETS.items():
         if datasets is not None and did not in datasets:
             continue
-        spacing = (3.0, 3.0, 3.0) if did == 297 else ((1.5, 1.5, 1.5) if did < 500 else (5.0, 1.5, 1.5))
+        spacing = _SPACING.get(did, (1.5, 1.5, 1.5) if did < 500 else (5.0, 1.5, 1.5))
         plans = default_plans(patch, base, max_features, n_stages, spacing, name)
         folds = (0,) if did < 500 else tuple(bca_folds)
         out[did] = write_model(root, did, plans, ncls, folds, seed)
@@ -175,7 +187,7 @@ def synthetic_specs(patch=(128, 128, 128), base=32, max_features=320, n_stages=6
     for did, (name, trainer, ncls) in DATASETS.items():
         if datasets is not None and did not in datasets:
             continue
-        spacing = (3.0, 3.0, 3.0) if did == 297 else ((1.5, 1.5, 1.5) if did < 500 else (5.0, 1.5, 1.5))
+        spacing = _SPACING.get(did, (1.5, 1.5, 1.5) if did < 500 else (5.0, 1.5, 1.5))
         plans = default_plans(patch, base, max_features, n_stages, spacing, name)
         arch = arch_from_plans(plans, "3d_fullres", 1, ncls)
         nf = 1 if did < 500 else bca_folds

@@ -62,7 +62,7 @@ def test_cpu_device_is_refused(tmp_path):
     with pytest.raises(RuntimeError, match="no CPU"):
         analyze_ct(tmp_path / "x.nii.gz", tmp_path, models={"total"}, device="cpu")
     with pytest.raises(NotImplementedError):
-        analyze_ct(tmp_path / "x.nii.gz", tmp_path, models={"lung_vessels"}, device="gpu")
+        analyze_ct(tmp_path / "x.nii.gz", tmp_path, models={"heartchambers_highres"}, device="gpu")  # licence-only
 
 
 def test_nifti_roundtrip_and_orientation(tmp_path):

@@ -162,3 +162,37 @@ def test_postprocess_on_the_5mm_grid_with_slice_weights_equals_the_full_grid():
         ref = fn(full, **kw)
         got = fn(low, weights=w, **kw)[src]
         assert np.array_equal(got, ref), key
+
+
+def test_breast_implant_finding_and_l3_axes_against_the_reference():
+    """Golden vectors from the reference's own generate_secondary_findings / find_axes
+    (tests/golden/make_golden_findings.py)."""
+    from boa_b200 import bca as pbca
+    from boa_b200 import ts_metrics
+    gold = json.load(open(os.path.join(G, "findings.json")))
+    for case in gold["implants"]:
+        regions = np.load(os.path.join(G, f"implants_{case['n']}.npz"))["regions"]
+        t = pbca.slice_tables_from_arrays(regions.shape[0], np.zeros((regions.shape[0], 8), dtype=np.int64),
+                                          np.zeros((regions.shape[0], 8), dtype=np.int64),
+                                          np.zeros((regions.shape[0], 8), dtype=np.int64),
+                                          np.zeros((regions.shape[0], 8), dtype=np.int64),
+                                          np.stack([(regions == r).sum(axis=(1, 2)) for r in range(12)], axis=1))
+        got = pbca.secondary_findings(t, pbca.AggregatableBodyPart.THORAX, float(np.prod(case["spacing"]) / 1000.0),
+                                      body_regions=regions)
+        assert got == case["findings"], (case["n"], got)
+    for k, ax in enumerate(gold["axes"]):
+        sl = np.load(os.path.join(G, f"axes_{k}.npz"))["slice"]
+        pts = ts_metrics.find_axes(sl)
+        assert [list(map(float, p)) for p in pts] == ax["points"]
+        major, minor = ts_metrics.axes_of_slice(sl, ax["spacing"])
+        assert abs(major - ax["major_mm"]) < 1e-9 and abs(minor - ax["minor_mm"]) < 1e-9
+    # the wrapper: middle slice of the L3 range, body mask = body_parts == 1
+    sl = np.load(os.path.join(G, "axes_0.npz"))["slice"]
+    total = np.zeros((9, *sl.shape), dtype=np.uint8)
+    parts = np.zeros_like(total)
+    total[3:6, 10:20, 10:20] = 29   # any label standing in for vertebrae_L3
+    parts[4] = sl
+    parts[3] = 1
+    assert ts_metrics.major_minor_axis(total, parts, gold["axes"][0]["spacing"], l3_label=29) == \
+        (gold["axes"][0]["major_mm"], gold["axes"][0]["minor_mm"])
+    assert ts_metrics.major_minor_axis(np.zeros_like(total), parts, (1, 1), l3_label=29) == (None, None)
