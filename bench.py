@@ -56,12 +56,17 @@ def count_forwards(a) -> dict:
     from boa_b200.geometry import sliding_window_origins
     from boa_b200.resample import resampled_depth
 
+    from boa_b200.config import resolve_models
+
+    ms = resolve_models(a.models, strict=True)
     P = (a.patch,) * 3
     shape = [max(s, a.patch) for s in a.shape]
-    n_total = len(sliding_window_origins(shape, P, 0.8)) * 5 if "total" in a.models or "bca" in a.models else 0
+    n_total = len(sliding_window_origins(shape, P, 0.8)) * 5 if "total" in ms else 0
     z5 = max(resampled_depth(a.shape[0], 1.5, 5.0), a.patch)
     folds = 1 if a.fast_bca else 5
-    n_bca = len(sliding_window_origins([z5, shape[1], shape[2]], P, 0.5)) * folds * 2 if "bca" in a.models else 0
+    n_bca = len(sliding_window_origins([z5, shape[1], shape[2]], P, 0.5)) * folds * 2 if "bca" in ms else 0
+    # (the crop-pre-pass tasks of `--models all` add one 6 mm forward set and one cropped forward set each; their patch
+    # count depends on the rough segmentation, so they are not part of the FLOP accounting)
     return {"total": n_total, "bca": n_bca}
 
 
@@ -369,8 +374,12 @@ def run_ours(a):
     from boa_b200 import _lib, zoo
     from boa_b200.pipeline import ModelZoo, analyze_from_host, analyze_volume
 
-    models = tuple(a.models.split("+"))
-    datasets = [291, 292, 293, 294, 295] + ([542, 543] if "bca" in models else [])
+    from boa_b200.config import resolve_models
+    from boa_b200.labels import CROP_PREPASS_TASK_ID, CROP_TASKS
+    models = tuple(sorted(resolve_models(a.models, strict=True)))  # "all" = every model that needs no licence
+    crop = [m for m in models if m in CROP_TASKS]
+    datasets = [291, 292, 293, 294, 295] + ([542, 543] if "bca" in models else []) + \
+               ([CROP_PREPASS_TASK_ID] + [CROP_TASKS[m][0] for m in crop] if crop else [])
     specs = zoo.synthetic_specs((a.patch,) * 3, 32, 320, 6, bca_folds=1 if a.fast_bca else 5, datasets=datasets)
     mz = ModelZoo.from_specs(specs, device=dev, max_batch=a.batch)
     ct_np = zoo.synthetic_ct(tuple(a.shape), seed=3 + (rank if throughput else 0))

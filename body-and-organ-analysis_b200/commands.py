@@ -69,7 +69,7 @@ def analyze_ct(input_folder: Path, processed_output_folder: Path, excel_output_f
     stats = {"num_voxels": int(ct_np.size), "num_slices": int(ct_np.shape[0])}
     zoo = zoo or ModelZoo(weights_root, device=dev)
     t0 = time.time()
-    ct = torch.from_numpy(ct_np).pin_memory().to(dev, non_blocking=True)
+    ct = torch.from_numpy(np.array(ct_np, copy=True)).pin_memory().to(dev, non_blocking=True)
     # recompute=False: label maps that already exist in the output folder are loaded instead of computed, and an
     # existing total-measurements.json is kept (compute/inference.py:82-84,95-105; infer/infer.py:59-61)
     precomputed, keep_total_json = {}, False

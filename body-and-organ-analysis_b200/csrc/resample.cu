@@ -14,6 +14,13 @@ namespace boa {
 
 constexpr int NPAD = 12;
 
+// The reference keeps the resampled CT as int32 (resampling.py:213-214); here it is int16, so a spline overshoot beyond
+// the int16 range saturates instead of wrapping around in sign.
+__device__ __forceinline__ int16_t trunc_sat_i16(double v) {
+  const int t = (int)v;
+  return (int16_t)(t < -32768 ? -32768 : (t > 32767 ? 32767 : t));
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256)
 spline_prefilter_z_kernel(const T* __restrict__ in, int z_in, size_t plane, double* __restrict__ c) {
@@ -71,7 +78,7 @@ spline_eval_z_kernel(const double* __restrict__ c, int z_in, size_t plane, int z
     const size_t s = (size_t)((int)fl - 1);
     const double v = w0 * c[s * plane + col] + w1 * c[(s + 1) * plane + col] + w2 * c[(s + 2) * plane + col] +
                      w3 * c[(s + 3) * plane + col];
-    out[i] = (int16_t)(int)v;  // truncation toward zero, as astype(np.int32)
+    out[i] = trunc_sat_i16(v);  // truncation toward zero, as astype(np.int32); saturated instead of wrapped
   }
 }
 
@@ -168,7 +175,7 @@ spline_eval_axis_kernel(const double* __restrict__ c, size_t outer, int n_in, si
     const double v = w0 * line[s * inner] + w1 * line[(s + 1) * inner] + w2 * line[(s + 2) * inner] +
                      w3 * line[(s + 3) * inner];
     if (out_mode == 0) static_cast<double*>(out)[i] = v;
-    else if (out_mode == 1) static_cast<int16_t*>(out)[i] = (int16_t)(int)v;
+    else if (out_mode == 1) static_cast<int16_t*>(out)[i] = trunc_sat_i16(v);
     else if (out_mode == 2) static_cast<int32_t*>(out)[i] = (int32_t)v;
     else static_cast<float*>(out)[i] = (float)v;
   }
