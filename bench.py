@@ -565,6 +565,9 @@ def run_ours(a):
 
 
 if __name__ == "__main__":
+    if os.environ.get("BOA_BENCH_WATCHDOG"):  # dump every thread's stack and exit if the run takes longer than this
+        import faulthandler
+        faulthandler.dump_traceback_later(float(os.environ["BOA_BENCH_WATCHDOG"]), exit=True)
     args = parse()
     if args.impl == "reference":
         run_reference(args)

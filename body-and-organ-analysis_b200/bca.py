@@ -177,19 +177,30 @@ def _pretty_volume(value: float) -> str:
 def breast_implant_finding(body_regions, ml_per_voxel: float) -> str | None:
     """builder.py:363-395: 26-connected components of the BREAST_IMPLANT label larger than 10 ml, ordered by the integer
     part of their centroid along the last array axis; one or two of them make a sentence (side = centroid against the
-    middle of array axis 1, as the reference compares them), more are an error.  The label is rare and small: only
-    its bounding box travels to the host, where scipy labels it (skimage.measure.label / regionprops in the reference)."""
+    middle of array axis 1, as the reference compares them), more are an error.
+    On the device the components of at most 10 ml are removed first (boa_cc_filter, the same criterion), so that only the
+    bounding box of real implants - usually nothing - travels to the host, where scipy labels it
+    (skimage.measure.label / regionprops in the reference) and the statistics are two bincounts."""
     from scipy import ndimage
     R = BODY_REGION["BREAST_IMPLANT"]
+    # largest voxel count whose volume is NOT above 10 ml, with the reference's float comparison
+    small = int(10.0 / ml_per_voxel)
+    while (small + 1) * ml_per_voxel <= 10:
+        small += 1
+    while small > 0 and small * ml_per_voxel > 10:
+        small -= 1
     if hasattr(body_regions, "is_cuda"):
-        mask_d = body_regions == R
+        from . import passes
+        from .postprocess import MODE_26, OP_REMOVE_SMALL, _cc_filter, _Scratch
+        mask_d = passes.label_set_mask(body_regions, [R])
+        _cc_filter(mask_d, (1,), False, MODE_26, OP_REMOVE_SMALL, small, 0, None, _Scratch(mask_d, need_border=False))
         if not bool(mask_d.any()):
             return None
         box = []
         for ax in range(3):
             idx = torch.nonzero(mask_d.any(dim=tuple(a for a in range(3) if a != ax))).flatten()
             box.append((int(idx[0]), int(idx[-1]) + 1))
-        mask = mask_d[box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]].cpu().numpy()
+        mask = mask_d[box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]].cpu().numpy() != 0
         off, mid_index = [b[0] for b in box], int(body_regions.shape[1]) // 2
     else:
         mask = np.asarray(body_regions) == R
@@ -197,12 +208,12 @@ def breast_implant_finding(body_regions, ml_per_voxel: float) -> str | None:
             return None
         off, mid_index = [0, 0, 0], mask.shape[1] // 2
     lab, n = ndimage.label(mask, structure=np.ones((3, 3, 3)))
-    props = []
-    for i in range(1, n + 1):
-        idx = np.nonzero(lab == i)
-        volume = len(idx[0]) * ml_per_voxel
-        if volume > 10:
-            props.append((float(np.mean(idx[2])) + off[2], volume))
+    flat = lab.ravel()
+    area = np.bincount(flat, minlength=n + 1)
+    xs = np.broadcast_to(np.arange(mask.shape[2], dtype=np.float64), mask.shape).ravel()
+    xsum = np.bincount(flat, weights=xs, minlength=n + 1)
+    props = [(xsum[i] / area[i] + off[2], area[i] * ml_per_voxel) for i in range(1, n + 1)
+             if area[i] * ml_per_voxel > 10]
     props.sort(key=lambda p: int(p[0]))
     found = [("right" if x < mid_index else "left", v) for x, v in props]
     if len(found) == 1:
@@ -231,7 +242,7 @@ def secondary_findings(t: SliceTables, examined: AggregatableBodyPart, ml_per_vo
         v = (tot[R["MEDIASTINUM"]] + tot[R["PERICARDIUM"]]) * ml_per_voxel
         out.append(f"Volume of mediastinum is {_pretty_volume(v)}")
         out.append(f"Volume enclosed by the pericardial sack is {_pretty_volume(tot[R['PERICARDIUM']] * ml_per_voxel)}")
-        if body_regions is not None and tot[R["BREAST_IMPLANT"]] > 0:
+        if body_regions is not None and tot[R["BREAST_IMPLANT"]] * ml_per_voxel > 10:  # else no component can be
             sentence = breast_implant_finding(body_regions, ml_per_voxel)
             if sentence:
                 out.append(sentence)

@@ -179,3 +179,26 @@ def test_volume_off_the_plans_grid_is_resampled_like_nnunet(cuda, small_zoo):
     agree = (lab == ref).mean()
     print(f"body_parts on a (5.0, 0.9, 0.9) mm volume: agreement with the oracle {agree:.5f}")
     assert agree > 0.99
+
+
+@pytest.mark.gpu
+def test_breast_implant_finding_device_path_equals_host_path(cuda):
+    """The device pre-filter (components <= 10 ml removed by boa_cc_filter, bounding box to the host) gives the sentence
+    of the plain host evaluation, also on a label map full of speckle (where a per-component host loop never ends)."""
+    import time
+    from boa_b200 import bca
+    R = bca.BODY_REGION["BREAST_IMPLANT"]
+    rng = np.random.default_rng(3)
+    ml = 0.9 * 0.9 * 1.5 / 1000.0
+    for n_blobs in (0, 1, 2, 3):
+        reg = rng.integers(0, 12, size=(96, 160, 192)).astype(np.uint8)
+        reg[reg == R] = 0
+        reg[rng.random(reg.shape) < 0.02] = R            # speckle: tens of thousands of tiny components
+        for c in [(40, 50, 40), (44, 52, 150), (70, 120, 96)][:n_blobs]:
+            z, y, x = np.ogrid[:96, :160, :192]
+            reg[(z - c[0]) ** 2 + (y - c[1]) ** 2 + (x - c[2]) ** 2 < 17 ** 2] = R
+        t0 = time.perf_counter()
+        dev = bca.breast_implant_finding(torch.from_numpy(reg).to(cuda), ml)
+        assert time.perf_counter() - t0 < 20
+        assert dev == bca.breast_implant_finding(reg, ml)
+        assert (dev is not None) == (n_blobs in (1, 2))
