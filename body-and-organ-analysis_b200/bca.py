@@ -178,10 +178,10 @@ def breast_implant_finding(body_regions, ml_per_voxel: float) -> str | None:
     """builder.py:363-395: 26-connected components of the BREAST_IMPLANT label larger than 10 ml, ordered by the integer
     part of their centroid along the last array axis; one or two of them make a sentence (side = centroid against the
     middle of array axis 1, as the reference compares them), more are an error.
-    On the device the components of at most 10 ml are removed first (boa_cc_filter, the same criterion), so that only the
-    bounding box of real implants - usually nothing - travels to the host, where scipy labels it
-    (skimage.measure.label / regionprops in the reference) and the statistics are two bincounts."""
-    from scipy import ndimage
+    On the device nothing but the few numbers of the sentence goes to the host: boa_cc_filter labels the components
+    (root = first voxel in raster order, the order skimage numbers them in) and counts their voxels; the components
+    above 10 ml - normally none, at most two - get their centroid from a per-column count of their voxels.  The host
+    path (numpy label map) is scipy.ndimage.label + two bincounts."""
     R = BODY_REGION["BREAST_IMPLANT"]
     # largest voxel count whose volume is NOT above 10 ml, with the reference's float comparison
     small = int(10.0 / ml_per_voxel)
@@ -189,31 +189,34 @@ def breast_implant_finding(body_regions, ml_per_voxel: float) -> str | None:
         small += 1
     while small > 0 and small * ml_per_voxel > 10:
         small -= 1
-    if hasattr(body_regions, "is_cuda"):
+    mid_index = int(body_regions.shape[1]) // 2
+    if getattr(body_regions, "is_cuda", False):
         from . import passes
         from .postprocess import MODE_26, OP_REMOVE_SMALL, _cc_filter, _Scratch
         mask_d = passes.label_set_mask(body_regions, [R])
-        _cc_filter(mask_d, (1,), False, MODE_26, OP_REMOVE_SMALL, small, 0, None, _Scratch(mask_d, need_border=False))
-        if not bool(mask_d.any()):
-            return None
-        box = []
-        for ax in range(3):
-            idx = torch.nonzero(mask_d.any(dim=tuple(a for a in range(3) if a != ax))).flatten()
-            box.append((int(idx[0]), int(idx[-1]) + 1))
-        mask = mask_d[box[0][0]:box[0][1], box[1][0]:box[1][1], box[2][0]:box[2][1]].cpu().numpy() != 0
-        off, mid_index = [b[0] for b in box], int(body_regions.shape[1]) // 2
+        scratch = _Scratch(mask_d, need_border=False)
+        _cc_filter(mask_d, (1,), False, MODE_26, OP_REMOVE_SMALL, small, 0, None, scratch)
+        roots = torch.nonzero(scratch.sizes > small).flatten()[:3].tolist()  # sizes are non-zero at roots only
+        props = []
+        if len(roots) <= 2:
+            cols = torch.arange(mask_d.shape[2], dtype=torch.float64, device=mask_d.device)
+            for r in roots:
+                per_col = (scratch.labels.view(mask_d.shape) == r).sum(dim=(0, 1)).to(torch.float64)
+                area = float(per_col.sum())
+                props.append((float((per_col * cols).sum()) / area, area * ml_per_voxel))
+        else:
+            props = [(0.0, 0.0)] * 3
     else:
+        from scipy import ndimage
         mask = np.asarray(body_regions) == R
         if not mask.any():
             return None
-        off, mid_index = [0, 0, 0], mask.shape[1] // 2
-    lab, n = ndimage.label(mask, structure=np.ones((3, 3, 3)))
-    flat = lab.ravel()
-    area = np.bincount(flat, minlength=n + 1)
-    xs = np.broadcast_to(np.arange(mask.shape[2], dtype=np.float64), mask.shape).ravel()
-    xsum = np.bincount(flat, weights=xs, minlength=n + 1)
-    props = [(xsum[i] / area[i] + off[2], area[i] * ml_per_voxel) for i in range(1, n + 1)
-             if area[i] * ml_per_voxel > 10]
+        lab, n = ndimage.label(mask, structure=np.ones((3, 3, 3)))
+        flat = lab.ravel()
+        area = np.bincount(flat, minlength=n + 1)
+        xs = np.broadcast_to(np.arange(mask.shape[2], dtype=np.float64), mask.shape).ravel()
+        xsum = np.bincount(flat, weights=xs, minlength=n + 1)
+        props = [(xsum[i] / area[i], area[i] * ml_per_voxel) for i in range(1, n + 1) if area[i] * ml_per_voxel > 10]
     props.sort(key=lambda p: int(p[0]))
     found = [("right" if x < mid_index else "left", v) for x, v in props]
     if len(found) == 1:
