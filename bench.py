@@ -559,6 +559,7 @@ def run_ours(a):
             "stage_seconds": res.timings if res is not None else None,
         }
         print(json.dumps(line))
+    barrier()  # the other ranks wait for rank 0's single-GPU legs before the group goes away
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

@@ -11,7 +11,7 @@
 
 namespace boa {
 
-constexpr int MAX_BATCH = 16;
+constexpr int MAX_BATCH = 32;
 
 struct ActView {  // a C8 tensor, possibly a channel-group slice of a wider buffer
   __half* base = nullptr;  // start of the whole buffer
