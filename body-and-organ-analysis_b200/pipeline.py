@@ -575,20 +575,28 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
     return res
 
 
-def analyze_from_host(ct_host: torch.Tensor, spacing_zyx, zoo: ModelZoo, device=None, **kw) -> dict:
+def analyze_from_host(ct_host: torch.Tensor, spacing_zyx, zoo: ModelZoo, device=None, maps_on_all_ranks: bool = False,
+                      **kw) -> dict:
     """The call a user of the Python API makes for one CT held in (pinned) host memory: H2D of the int16 volume,
     all networks and passes on the device, D2H of the uint8 label maps (pinned staging buffers owned by the zoo,
     copied on a side stream while later networks run); returns host tensors + measurement dicts.  The host tensors
-    are views of the staging buffers: copy them if they must outlive the next call on the same zoo."""
+    are views of the staging buffers: copy them if they must outlive the next call on the same zoo.
+    With a dist_ctx (one volume on N GPUs) the job has ONE caller: rank 0 receives the label maps, the other ranks
+    only the measurement dicts (their maps stay None unless maps_on_all_ranks) - N copies of 0.67 GB into the same
+    host memory cost 49 ms of a 375 ms step at 8 GPUs."""
     dev = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device())
+    dist_ctx = kw.get("dist_ctx")
+    deliver = maps_on_all_ranks or dist_ctx is None or dist_ctx.rank == 0
     stager = getattr(zoo, "_stager", None)
-    if stager is None or stager.device != dev:
+    if deliver and (stager is None or stager.device != dev):
         stager = zoo._stager = HostStager(dev)
     ct = ct_host.to(dev, non_blocking=True)
-    res = analyze_volume(ct, spacing_zyx, zoo, stager=stager, **kw)
+    res = analyze_volume(ct, spacing_zyx, zoo, stager=stager if deliver else None, **kw)
     out = {"total_measurements": res.total_measurements, "bca_measurements": res.bca_measurements,
            "vertebrae": res.vertebrae, "timings": res.timings}
-    host = stager.collect()
+    host = stager.collect() if deliver else {}
     for name in ("total", "body_parts", "body_regions", "tissues", "ct_pfav"):
         out[name] = host.get(name)
+    if not deliver:
+        torch.cuda.current_stream(dev).synchronize()  # the call returns when this rank's share of the volume is done
     return out

@@ -53,6 +53,15 @@ def _worker(rank, world, port, out_dir):
                           dist_ctx=DistContext(rank, world, None))
     del os.environ["BOA_B200_PAIR_MIN_RANKS"]
     same_pair = all(torch.equal(getattr(res, k), getattr(res2, k)) for k in ("body_parts", "body_regions", "tissues"))
+    # host API on N ranks: one caller (rank 0) receives the label maps, every rank the measurement dicts
+    from boa_b200.pipeline import analyze_from_host
+    host = analyze_from_host(ct.cpu().pin_memory(), (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=True,
+                             dist_ctx=DistContext(rank, world, None))
+    host_ok = host["total_measurements"] == res.total_measurements and (
+        all(torch.equal(host[k], getattr(res, k).cpu()) for k in ("total", "body_parts", "body_regions", "tissues"))
+        if rank == 0 else all(host[k] is None for k in ("total", "body_parts", "body_regions", "tissues")))
+    flag = torch.tensor([int(host_ok)], device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if rank == 0:
         ref = analyze_volume(ct, (1.5, 1.5, 1.5), mz, models=("total", "bca"), fast_bca=True)
         import json
@@ -62,6 +71,7 @@ def _worker(rank, world, port, out_dir):
         with open(os.path.join(out_dir, "meas.json"), "w") as f:
             json.dump({"dist": [res.total_measurements, res.bca_measurements],
                        "single": [ref.total_measurements, ref.bca_measurements], "same_pair": bool(same_pair),
+                       "host_api_ok": bool(flag.item()),
                        "total_equal": bool(torch.equal(res.total, ref.total))}, f)
     dist.barrier()
     dist.destroy_process_group()
@@ -91,6 +101,7 @@ def test_two_ranks_match_single_gpu(cuda, tmp_path):
     # the measurement dicts are functions of the label maps: same keys, and equal wherever the maps are equal
     assert m["dist"][0]["segmentations"]["total"].keys() == m["single"][0]["segmentations"]["total"].keys()
     assert m["dist"][1].keys() == m["single"][1].keys()
+    assert m["host_api_ok"], "analyze_from_host on 2 ranks: maps on rank 0 only, measurements everywhere"
     assert m["same_pair"], "concurrent post-processing of body_parts / body_regions differs from the sequential one"
     if m["total_equal"]:  # sharded histograms, all-reduced: exact - same label map => same statistics
         from test_oracle_golden import _close
