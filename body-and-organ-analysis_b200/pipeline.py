@@ -423,7 +423,7 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         models.add("total")  # compute/config.py:54-55
     if models & set(CROP_TASKS):
         models.add("total")  # compute_measurements needs it (autochthon reference) and the CLI always runs it first
-    pending_total = None
+    pending_total = pending_l3 = None
     # HU range of the CT: sizes the per-label histograms exactly; read once here, before any network is enqueued (the
     # only device -> host read ahead of the label maps)
     lo_t, hi_t = torch.aminmax(ct)
@@ -496,6 +496,13 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         on_5mm = postprocess and ct5.shape[0] <= ct.shape[0]
         weights = slice_weights(ct5.shape[0], ct.shape[0], ct.device) if on_5mm else None
 
+        def l3_axes():
+            # body cross-section at L3 (compute/ts_metrics.py:32-61): needs `total` and the final body_parts map
+            if "bca" not in models or res.total is None:
+                return None
+            from .ts_metrics import PendingL3Axes
+            return PendingL3Axes(res.total, res.body_parts, (spacing_zyx[2], spacing_zyx[1]))
+
         def finish(net_out, fn, name):
             mark(f"{name}_net")
             with nvtx.range(f"boa/postprocess/{name}"):
@@ -527,13 +534,16 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
             mark("bca_postprocess")
             if stager is not None:
                 stager.stage("body_parts", res.body_parts)
+            pending_l3 = l3_axes()
         elif want_parts and "body_parts" in precomputed:
             res.body_parts = precomputed["body_parts"].to(ct.device, torch.uint8).contiguous()
+            pending_l3 = l3_axes()
         elif want_parts:
             res.body_parts = finish(segment_bca_net(ct5, zoo, "body_parts", fast_bca, dist_ctx, sp5),
                                     postprocess_part_segmentation, "body_parts")
             if stager is not None:
                 stager.stage("body_parts", res.body_parts)
+            pending_l3 = l3_axes()  # its host part runs while the body_regions networks are on the device
         if pair:
             pass
         elif want_regions and "body_regions" in precomputed:
@@ -559,14 +569,8 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         examined = bca.body_part_from_regions(tables, float(sx_sy_sz[2]))
         res.other_findings = bca.secondary_findings(tables, examined, float(np.prod(sx_sy_sz) / 1000.0),
                                                     body_regions=res.body_regions)
-        if res.total is not None and tables.total_counts is not None:
-            from .labels import class_map as _cm
-            from .ts_metrics import axes_of_slice
-            l3 = {v: k for k, v in _cm("total").items()}["vertebrae_L3"]
-            present = np.nonzero(tables.total_counts[:, l3] > 0)[0]
-            if present.size:  # one 2-D slice of the body mask goes to the host
-                z = int(np.median(present))
-                res.l3_axes_mm = axes_of_slice((res.body_parts[z] == 1).cpu().numpy(), (sx_sy_sz[0], sx_sy_sz[1]))
+        if pending_l3 is not None:
+            res.l3_axes_mm = pending_l3.finish()
         nvtx.range_pop()
         mark("bca_measurements")
     torch.cuda.synchronize()

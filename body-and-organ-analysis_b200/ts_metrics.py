@@ -75,3 +75,50 @@ def major_minor_axis(total, body_parts, spacing_xy, l3_label: int | None = None)
         z = int(np.median(present))
         sl = body_parts[z] == 1
     return axes_of_slice(sl, spacing_xy)
+
+
+_PINNED: dict = {}
+
+
+class PendingL3Axes:
+    """major_minor_axis for device label maps without a stall of the launch queue and off the critical path: the middle
+    L3 slice index is computed on the device (median of the slice indices that contain the label, int() as the
+    reference: floor of the mean of the two middle ones), the body mask of that slice is copied to pinned host memory
+    asynchronously, and a host thread evaluates the geometry (OpenCV / qhull release the GIL) while the caller keeps
+    enqueuing the networks that follow.  finish() joins it."""
+
+    def __init__(self, total, body_parts, spacing_xy, l3_label: int | None = None):
+        import threading
+
+        import torch
+        from .labels import class_map
+        if l3_label is None:
+            l3_label = {v: k for k, v in class_map("total").items()}["vertebrae_L3"]
+        self.spacing_xy, self.result = spacing_xy, (None, None)
+        present = (total == l3_label).flatten(1).any(dim=1)
+        rank = present.cumsum(0)
+        n = rank[-1]
+        lo = torch.argmax(((rank == (n - 1) // 2 + 1) & present).to(torch.uint8))
+        hi = torch.argmax(((rank == n // 2 + 1) & present).to(torch.uint8))
+        z = (lo + hi) // 2
+        mask = body_parts.index_select(0, z.view(1))[0] == 1
+        key = (str(total.device), tuple(mask.shape))
+        if key not in _PINNED:
+            _PINNED[key] = (torch.empty(mask.shape, dtype=torch.bool, pin_memory=True),
+                            torch.empty(1, dtype=torch.int64, pin_memory=True))
+        self._mask, self._n = _PINNED[key]
+        self._mask.copy_(mask, non_blocking=True)
+        self._n.copy_(n.view(1), non_blocking=True)
+        self._event = torch.cuda.Event()
+        self._event.record(torch.cuda.current_stream(total.device))
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
+
+    def _run(self):
+        self._event.synchronize()
+        if int(self._n[0]) > 0:
+            self.result = axes_of_slice(self._mask.numpy(), self.spacing_xy)
+
+    def finish(self):
+        self._thread.join()
+        return self.result

@@ -202,3 +202,22 @@ def test_breast_implant_finding_device_path_equals_host_path(cuda):
         assert time.perf_counter() - t0 < 20
         assert dev == bca.breast_implant_finding(reg, ml)
         assert (dev is not None) == (n_blobs in (1, 2))
+
+
+@pytest.mark.gpu
+def test_pending_l3_axes_equals_the_synchronous_evaluation(cuda):
+    """PendingL3Axes (slice index on the device, host geometry in a thread) == ts_metrics.major_minor_axis on numpy maps,
+    for an odd and an even number of L3 slices and for a volume without L3."""
+    from boa_b200.labels import class_map
+    from boa_b200.ts_metrics import PendingL3Axes, major_minor_axis
+    l3 = {v: k for k, v in class_map("total").items()}["vertebrae_L3"]
+    z, y, x = np.ogrid[:40, :96, :128]
+    for slices in ((11, 12, 13, 17, 20), (9, 14, 15, 30), ()):
+        total = np.zeros((40, 96, 128), np.uint8)
+        for s in slices:
+            total[s, 40:50, 60:70] = l3
+        parts = (((y - 48) / (30.0 + 0.3 * z)) ** 2 + ((x - 64) / (50.0 - 0.5 * z)) ** 2 < 1).astype(np.uint8)
+        want = major_minor_axis(total, parts, (0.8, 0.7))
+        got = PendingL3Axes(torch.from_numpy(total).to(cuda), torch.from_numpy(parts).to(cuda), (0.8, 0.7)).finish()
+        assert got == want, (slices, got, want)
+        assert (want[0] is None) == (len(slices) == 0)
