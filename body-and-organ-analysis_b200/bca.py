@@ -174,14 +174,16 @@ def _pretty_volume(value: float) -> str:
     return f"{value / 1000:.3f} L" if value >= 1000 else f"{value:.2f} mL"
 
 
-def breast_implant_finding(body_regions, ml_per_voxel: float) -> str | None:
+def breast_implant_finding(body_regions, ml_per_voxel: float, slice_weights=None) -> str | None:
     """builder.py:363-395: 26-connected components of the BREAST_IMPLANT label larger than 10 ml, ordered by the integer
     part of their centroid along the last array axis; one or two of them make a sentence (side = centroid against the
     middle of array axis 1, as the reference compares them), more are an error.
     On the device nothing but the few numbers of the sentence goes to the host: boa_cc_filter labels the components
     (root = first voxel in raster order, the order skimage numbers them in) and counts their voxels; the components
-    above 10 ml - normally none, at most two - get their centroid from a per-column count of their voxels.  The host
-    path (numpy label map) is scipy.ndimage.label + two bincounts."""
+    above 10 ml - normally none, at most two - get their centroid from a per-column count of their voxels.
+    slice_weights (device path): the map is the 5 mm-grid map and slice z stands for slice_weights[z] replicated slices
+    of the input grid (postprocess.slice_weights) - components map one to one, voxel counts and column counts are
+    weighted, 3.3x less labelling work.  The host path (numpy label map) is scipy.ndimage.label + two bincounts."""
     R = BODY_REGION["BREAST_IMPLANT"]
     # largest voxel count whose volume is NOT above 10 ml, with the reference's float comparison
     small = int(10.0 / ml_per_voxel)
@@ -195,13 +197,16 @@ def breast_implant_finding(body_regions, ml_per_voxel: float) -> str | None:
         from .postprocess import MODE_26, OP_REMOVE_SMALL, _cc_filter, _Scratch
         mask_d = passes.label_set_mask(body_regions, [R])
         scratch = _Scratch(mask_d, need_border=False)
-        _cc_filter(mask_d, (1,), False, MODE_26, OP_REMOVE_SMALL, small, 0, None, scratch)
+        _cc_filter(mask_d, (1,), False, MODE_26, OP_REMOVE_SMALL, small, 0, slice_weights, scratch)
         roots = torch.nonzero(scratch.sizes > small).flatten()[:3].tolist()  # sizes are non-zero at roots only
         props = []
         if len(roots) <= 2:
             cols = torch.arange(mask_d.shape[2], dtype=torch.float64, device=mask_d.device)
             for r in roots:
-                per_col = (scratch.labels.view(mask_d.shape) == r).sum(dim=(0, 1)).to(torch.float64)
+                per_col = (scratch.labels.view(mask_d.shape) == r).sum(dim=1).to(torch.float64)  # [z, x]
+                if slice_weights is not None:
+                    per_col = per_col * slice_weights.view(-1, 1)
+                per_col = per_col.sum(dim=0)
                 area = float(per_col.sum())
                 props.append((float((per_col * cols).sum()) / area, area * ml_per_voxel))
         else:
@@ -232,8 +237,9 @@ def breast_implant_finding(body_regions, ml_per_voxel: float) -> str | None:
 
 
 def secondary_findings(t: SliceTables, examined: AggregatableBodyPart, ml_per_voxel: float,
-                       body_regions=None) -> list[str]:
-    """generate_secondary_findings (builder.py:309-395).  body_regions (the label map): also look for breast implants."""
+                       body_regions=None, slice_weights=None) -> list[str]:
+    """generate_secondary_findings (builder.py:309-395).  body_regions (the label map, or the 5 mm-grid map with its
+    slice weights): also look for breast implants."""
     R = BODY_REGION
     tot = t.region_counts.sum(axis=0)
     out = []
@@ -246,7 +252,7 @@ def secondary_findings(t: SliceTables, examined: AggregatableBodyPart, ml_per_vo
         out.append(f"Volume of mediastinum is {_pretty_volume(v)}")
         out.append(f"Volume enclosed by the pericardial sack is {_pretty_volume(tot[R['PERICARDIUM']] * ml_per_voxel)}")
         if body_regions is not None and tot[R["BREAST_IMPLANT"]] * ml_per_voxel > 10:  # else no component can be
-            sentence = breast_implant_finding(body_regions, ml_per_voxel)
+            sentence = breast_implant_finding(body_regions, ml_per_voxel, slice_weights)
             if sentence:
                 out.append(sentence)
     return out

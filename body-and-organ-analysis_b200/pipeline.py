@@ -496,6 +496,8 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         on_5mm = postprocess and ct5.shape[0] <= ct.shape[0]
         weights = slice_weights(ct5.shape[0], ct.shape[0], ct.device) if on_5mm else None
 
+        grid5 = {}  # post-processed maps on the 5 mm grid (each slice stands for weights[z] slices of the input grid)
+
         def l3_axes():
             # body cross-section at L3 (compute/ts_metrics.py:32-61): needs `total` and the final body_parts map
             if "bca" not in models or res.total is None:
@@ -509,6 +511,7 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
                 kw_d = {"dist_ctx": dist_ctx} if fn is postprocess_part_segmentation else {}
                 if on_5mm:
                     net_out = fn(net_out, weights, **kw_d)
+                    grid5[name] = net_out
                 out = upsample_labels_nearest(net_out, ct.shape[0])
                 if postprocess and not on_5mm:
                     out = fn(out, None, **kw_d)
@@ -531,6 +534,7 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
                 parts_pp, regions_pp = postprocess_pair_distributed(parts_raw, regions_raw, weights, dist_ctx)
                 res.body_parts = upsample_labels_nearest(parts_pp, ct.shape[0])
                 res.body_regions = upsample_labels_nearest(regions_pp, ct.shape[0])
+                grid5["body_regions"] = regions_pp
             mark("bca_postprocess")
             if stager is not None:
                 stager.stage("body_parts", res.body_parts)
@@ -567,8 +571,12 @@ def analyze_volume(ct: torch.Tensor, spacing_zyx, zoo: ModelZoo, models=("total"
         res.bca_measurements, res.vertebrae, tables = bca.build_bca_measurements(
             ct, res.tissues, res.body_parts, res.body_regions, res.total, sx_sy_sz)
         examined = bca.body_part_from_regions(tables, float(sx_sy_sz[2]))
-        res.other_findings = bca.secondary_findings(tables, examined, float(np.prod(sx_sy_sz) / 1000.0),
-                                                    body_regions=res.body_regions)
+        # breast implants: components of the region map, labelled on the 5 mm grid when that map exists
+        regions5 = grid5.get("body_regions")
+        res.other_findings = bca.secondary_findings(
+            tables, examined, float(np.prod(sx_sy_sz) / 1000.0),
+            body_regions=regions5 if regions5 is not None else res.body_regions,
+            slice_weights=weights if regions5 is not None else None)
         if pending_l3 is not None:
             res.l3_axes_mm = pending_l3.finish()
         nvtx.range_pop()

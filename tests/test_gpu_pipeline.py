@@ -202,6 +202,13 @@ def test_breast_implant_finding_device_path_equals_host_path(cuda):
         assert time.perf_counter() - t0 < 20
         assert dev == bca.breast_implant_finding(reg, ml)
         assert (dev is not None) == (n_blobs in (1, 2))
+        # the same on the 5 mm grid: every slice stands for weights[z] replicated slices of the input grid
+        from boa_b200.postprocess import slice_weights
+        from boa_b200.resample import upsample_labels_nearest
+        reg5 = torch.from_numpy(reg[::3].copy()).to(cuda)
+        full = upsample_labels_nearest(reg5, 96)
+        w = slice_weights(reg5.shape[0], 96, cuda)
+        assert bca.breast_implant_finding(reg5, ml, w) == bca.breast_implant_finding(full.cpu().numpy(), ml)
 
 
 @pytest.mark.gpu
