@@ -515,7 +515,7 @@ def run_ours(a):
     iso_flop = sum(2.0 * macs * a.batch for (_, kind, macs) in desc if kind == 0)
     traffic = None
     try:  # dram bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-        with open(os.path.join(ROOT, "profiles", "r01_fold_traffic.json")) as f:
+        with open(os.path.join(ROOT, "profiles", "r02_fold_traffic.json")) as f:
             traffic = float(json.load(f)["bytes_per_launch"])
     except Exception:
         pass
