@@ -9,7 +9,10 @@ from __future__ import annotations
 
 import gzip
 import json
+import os
 import struct
+import zlib
+from concurrent.futures import ThreadPoolExecutor
 from dataclasses import dataclass
 
 import numpy as np
@@ -120,11 +123,33 @@ def save(path, data_zyx: np.ndarray, affine: np.ndarray, label_map: dict | None 
     struct.pack_into("<4f", h, 296, *affine[1])
     struct.pack_into("<4f", h, 312, *affine[2])
     h[344:348] = b"n+1\0"
+    head = bytes(h) + struct.pack("4B", 1 if ext else 0, 0, 0, 0) + ext
+    threads = int(os.environ.get("BOA_B200_GZIP_THREADS", str(min(8, os.cpu_count() or 1))))
+    if str(path).endswith(".gz") and threads > 1 and data.nbytes > _GZIP_CHUNK:
+        _write_gzip_members(path, head, memoryview(data).cast("B"), threads)
+        return
     with _open(path, "wb") as f:
-        f.write(bytes(h))
-        f.write(struct.pack("4B", 1 if ext else 0, 0, 0, 0))
-        f.write(ext)
+        f.write(head)
         f.write(data.tobytes())
+
+
+_GZIP_CHUNK = 4 << 20
+
+
+def _write_gzip_members(path, head: bytes, body: memoryview, threads: int) -> None:
+    """Parallel deflate: the byte stream is cut into 4 MB chunks, every chunk is deflated on its own
+    thread (zlib releases the GIL) into a complete gzip MEMBER, and the members are written back to back.  A
+    concatenation of members is a valid gzip file (RFC 1952 2.2) that gzip / zlib's gzread / nibabel / ITK read as one
+    stream; level 1 as nibabel.  Costs < 0.1 % of file size against a single stream (one 18-byte frame + a cold
+    dictionary per 4 MB)."""
+    def member(lo: int) -> bytes:
+        c = zlib.compressobj(1, zlib.DEFLATED, 31)
+        chunk = body[lo:lo + _GZIP_CHUNK]
+        return c.compress(head + bytes(chunk) if lo == 0 else chunk) + c.flush()
+
+    with open(path, "wb") as f, ThreadPoolExecutor(max_workers=threads) as ex:
+        for blob in ex.map(member, range(0, len(body), _GZIP_CHUNK)):
+            f.write(blob)
 
 
 # ---- orientation (nib.as_closest_canonical / undo, totalsegmentator/alignment.py:8-54)

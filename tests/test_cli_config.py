@@ -82,3 +82,21 @@ def test_nifti_roundtrip_and_orientation(tmp_path):
     u8 = (d % 7).astype(np.uint8)
     nifti.save(tmp_path / "b.nii", u8, np.eye(4))
     assert np.array_equal(nifti.load(tmp_path / "b.nii").data, u8)
+
+
+def test_nifti_parallel_deflate_is_one_valid_gzip_stream(tmp_path, monkeypatch):
+    """Volumes above one chunk are written as concatenated gzip members deflated on several threads: the decompressed
+    stream is byte-identical to the single-stream file, and the label extension survives."""
+    import gzip
+    rng = np.random.default_rng(1)
+    d = rng.integers(0, 30, size=(40, 300, 400)).astype(np.int16)  # 9.6 MB: three chunks
+    aff = np.diag([0.8, 0.8, 2.5, 1.0])
+    monkeypatch.setenv("BOA_B200_GZIP_THREADS", "1")
+    nifti.save(tmp_path / "one.nii.gz", d, aff, {1: "spleen"})
+    monkeypatch.setenv("BOA_B200_GZIP_THREADS", "4")
+    nifti.save(tmp_path / "many.nii.gz", d, aff, {1: "spleen"})
+    one, many = (tmp_path / "one.nii.gz").read_bytes(), (tmp_path / "many.nii.gz").read_bytes()
+    assert many.count(b"\x1f\x8b\x08") >= 3 and one != many
+    assert gzip.decompress(one) == gzip.decompress(many)
+    im = nifti.load(tmp_path / "many.nii.gz")
+    assert np.array_equal(im.data, d) and np.allclose(im.affine, aff)
