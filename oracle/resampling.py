@@ -9,7 +9,10 @@ Restates, on numpy / scipy:
 `skimage.transform.resize(image, shape, order, mode="edge", anti_aliasing=False)` is not installable here; per its
 source (scikit-image 0.26, transform/_warps.py: resize -> ndi.zoom(image, zoom, order=order, mode="nearest",
 grid_mode=True) followed by _clip_warp_output: np.clip to the input's [min, max]) it is restated on scipy.
-Parity of this file: UNPINNED by skimage itself (not importable); pinned to scipy.ndimage.zoom.
+Parity of this file: compute_new_shape, determine_do_sep_z_and_axis and resample_data are PINNED to outputs of the
+reference's own default_resampling.py run in the development container (tests/golden/make_golden_resampling.py ->
+tests/golden/resampling.{json,npz}, bit-equal); only `resize` itself is unpinned by skimage (not importable) and
+rests on its source as quoted above.
 """
 from __future__ import annotations
 

@@ -287,3 +287,28 @@ def test_finalize_argmax_resampled_vs_oracle(cuda, net_shape, out_shape, cur, ne
     safe = (top2[1] - top2[0]) > 1e-4  # fp32 quotients vs the oracle's fp64 interpolation
     assert got.shape == ref.shape
     assert np.array_equal(got[safe], ref[safe]) and (got == ref).mean() > 0.9999
+
+
+def test_nnunet_resampling_against_the_reference_vectors(cuda):
+    """The device resampling to the plan's spacing and the resampled argmax against outputs of the reference's own
+    resample_data_or_seg_to_shape (tests/golden/make_golden_resampling.py)."""
+    import os
+    from boa_b200.predictor import finalize_argmax_resampled
+    from boa_b200.resample import nnunet_separate_z, resample_to_plan_spacing
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "resampling.npz"))
+    for name in sorted(k[:-3] for k in z.files if k.endswith("_in")):
+        meta = z[name + "_meta"]
+        cur, new, order = tuple(float(v) for v in meta[:3]), tuple(float(v) for v in meta[3:6]), int(meta[6])
+        data, ref = z[name + "_in"], z[name + "_out"]
+        if order == 3:   # DefaultPreprocessor: every channel of the normalised image
+            for c in range(data.shape[0]):
+                got = resample_to_plan_spacing(_dev(data[c]), cur, new).cpu().numpy()
+                assert got.shape == ref[c].shape, name
+                assert np.allclose(got, ref[c], rtol=0, atol=2e-6), (name, np.abs(got - ref[c]).max())
+        else:            # export: logits back to the pre-resampling shape, argmax
+            sep, _ = nnunet_separate_z(cur, new)
+            w = np.ones(data.shape[1:], np.float32)
+            got = finalize_argmax_resampled(_dev(data), _dev(w), ref.shape[1:], sep).cpu().numpy()
+            want = ref.argmax(0).astype(np.uint8)
+            safe = np.abs(ref[0].astype(np.float64) - ref[1]) > 1e-4
+            assert np.array_equal(got[safe], want[safe]) and (got == want).mean() > 0.999, name

@@ -196,3 +196,32 @@ def test_breast_implant_finding_and_l3_axes_against_the_reference():
     assert ts_metrics.major_minor_axis(total, parts, gold["axes"][0]["spacing"], l3_label=29) == \
         (gold["axes"][0]["major_mm"], gold["axes"][0]["minor_mm"])
     assert ts_metrics.major_minor_axis(np.zeros_like(total), parts, (1, 1), l3_label=29) == (None, None)
+
+
+def test_nnunet_resampling_decisions_and_volumes_match_the_reference():
+    """compute_new_shape / determine_do_sep_z_and_axis / resample_data_or_seg_to_shape of the reference
+    (tests/golden/make_golden_resampling.py ran default_resampling.py itself) against the oracle restatement and the
+    product's host logic."""
+    from boa_b200.resample import nnunet_new_shape, nnunet_separate_z
+    from oracle import resampling as orr
+    with open(os.path.join(G, "resampling.json")) as f:
+        g = json.load(f)
+    assert g["aniso_threshold"] == orr.ANISO_THRESHOLD
+    n_sep = 0
+    for d in g["decisions"]:
+        want = (d["separate_z"], d["axis"])
+        assert orr.determine_do_sep_z_and_axis(d["current"], d["new"]) == want, d
+        assert tuple(nnunet_separate_z(d["current"], d["new"])) == want, d
+        n_sep += d["separate_z"]
+        for shape, new_shape in zip(g["shapes"], d["new_shapes"]):
+            assert list(orr.compute_new_shape(shape, d["current"], d["new"])) == new_shape
+            assert list(nnunet_new_shape(shape, d["current"], d["new"])) == new_shape
+    assert 0 < n_sep < len(g["decisions"])
+    z = np.load(os.path.join(G, "resampling.npz"))
+    for name in sorted(k[:-3] for k in z.files if k.endswith("_in")):
+        meta = z[name + "_meta"]
+        cur, new, order = tuple(meta[:3]), tuple(meta[3:6]), int(meta[6])
+        ref = z[name + "_out"]
+        got = orr.resample_data(z[name + "_in"], ref.shape[1:], cur, new, order=order)
+        assert got.shape == ref.shape and got.dtype == ref.dtype, name
+        assert np.array_equal(got, ref), (name, np.abs(got - ref).max())
