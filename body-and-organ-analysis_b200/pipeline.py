@@ -316,14 +316,24 @@ def crop_box_from_rois(rough: torch.Tensor, roi_names, spacing_zyx):
     structures are absent (the reference then returns an empty segmentation, nnunet.py:428-445)."""
     inv = {v: k for k, v in class_map("total").items()}
     mask = passes.label_set_mask(rough, [inv[r] for r in roi_names])
-    box = []
+    extents = []
     for ax in range(3):
         other = tuple(a for a in range(3) if a != ax)
         idx = torch.nonzero(mask.any(dim=other)).flatten()
         if idx.numel() == 0:
             return None
-        addon = int(CROP_ADDON_MM / float(spacing_zyx[ax]))  # mm -> voxels, truncated (cropping.py:99)
-        box.append((max(0, int(idx[0]) - addon), min(int(rough.shape[ax]), int(idx[-1]) + 1 + addon)))
+        extents.append((int(idx[0]), int(idx[-1])))
+    return grow_crop_box(extents, rough.shape, spacing_zyx)
+
+
+def grow_crop_box(extents, shape, spacing_zyx, addon_mm: float = CROP_ADDON_MM):
+    """[(first, last)] index of the mask per axis -> [(lo, hi)] per axis: get_bbox_from_mask with the addon of crop_to_mask
+    (cropping.py:11-37,97-99): mm -> voxels by truncation of `addon / zoom` with the zoom as the float32 the NIfTI header
+    holds (20 mm / 0.8 mm is 24 voxels there, not 25), clipped to the volume."""
+    box = []
+    for ax, (first, last) in enumerate(extents):
+        addon = int(np.float64(addon_mm) / np.float32(spacing_zyx[ax]))
+        box.append((max(0, first - addon), min(int(shape[ax]), last + 1 + addon)))
     return box
 
 

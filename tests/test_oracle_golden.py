@@ -225,3 +225,16 @@ def test_nnunet_resampling_decisions_and_volumes_match_the_reference():
         got = orr.resample_data(z[name + "_in"], ref.shape[1:], cur, new, order=order)
         assert got.shape == ref.shape and got.dtype == ref.dtype, name
         assert np.array_equal(got, ref), (name, np.abs(got - ref).max())
+
+
+def test_crop_box_matches_the_reference_bbox():
+    """The crop pre-pass box (bounding box of the ROI mask + 20 mm, cropping.py) against the reference's
+    get_bbox_from_mask, incl. the float32 zoom that makes 20 mm / 0.8 mm 24 voxels."""
+    from boa_b200.pipeline import grow_crop_box
+    with open(os.path.join(G, "crop.json")) as f:
+        cases = json.load(f)
+    assert len(cases) >= 20
+    for c in cases:
+        got = grow_crop_box([tuple(fl) for fl in c["first_last"]], c["shape"], c["zooms"])
+        assert [list(b) for b in got] == c["bbox"], c
+    assert grow_crop_box([(30, 40)], (100,), (0.8,)) == [(6, 65)]
