@@ -312,3 +312,29 @@ def test_nnunet_resampling_against_the_reference_vectors(cuda):
             want = ref.argmax(0).astype(np.uint8)
             safe = np.abs(ref[0].astype(np.float64) - ref[1]) > 1e-4
             assert np.array_equal(got[safe], want[safe]) and (got == want).mean() > 0.999, name
+
+
+def test_change_spacing_against_the_reference_vectors(cuda):
+    """resample_volume_cubic / resample_thickness / resample_labels_nearest against outputs of the reference's own
+    change_spacing (tests/golden/make_golden_change_spacing.py).  Order 0 is bit-exact; order 3 agrees except (by one)
+    where the fp64 spline value is numerically an integer and the truncation to int is decided by rounding noise."""
+    from scipy import ndimage
+    from boa_b200.resample import resample_labels_nearest, resample_thickness, resample_volume_cubic
+    z = np.load(os.path.join(G, "change_spacing.npz"))
+    names = sorted(k[:-3] for k in z.files if k.endswith("_ct"))
+    assert len(names) == 4
+    for name in names:
+        ct, sp, tg, ref = z[name + "_ct"], z[name + "_spacing_zyx"], z[name + "_target_zyx"], z[name + "_resampled"]
+        if name.startswith("thickness"):
+            got = resample_thickness(_dev(ct), float(sp[0]), float(tg[0])).cpu().numpy()
+        else:
+            got = resample_volume_cubic(_dev(ct), tuple(float(v) for v in sp), float(tg[0])).cpu().numpy()
+        assert got.shape == ref.shape and got.dtype == np.int16, name
+        zoom = [np.float64(np.float32(s)) / np.float64(np.float32(t)) for s, t in zip(sp, tg)]
+        spline = ndimage.zoom(ct.astype(np.float64), zoom, order=3, mode="nearest")
+        diff = np.abs(got.astype(np.int64) - ref)
+        assert diff.max() <= 1, (name, diff.max())
+        inner = np.abs(spline - np.rint(spline)) > 1e-6
+        assert inner.mean() > 0.4 and np.array_equal(got[inner], ref[inner]), name
+        back = resample_labels_nearest(_dev(z[name + "_labels"]), ct.shape).cpu().numpy()
+        assert np.array_equal(back, z[name + "_labels_back"]), name

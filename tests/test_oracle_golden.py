@@ -238,3 +238,36 @@ def test_crop_box_matches_the_reference_bbox():
         got = grow_crop_box([tuple(fl) for fl in c["first_last"]], c["shape"], c["zooms"])
         assert [list(b) for b in got] == c["bbox"], c
     assert grow_crop_box([(30, 40)], (100,), (0.8,)) == [(6, 65)]
+
+
+def _change_spacing_cases():
+    z = np.load(os.path.join(G, "change_spacing.npz"))
+    for name in sorted(k[:-3] for k in z.files if k.endswith("_ct")):
+        yield name, {k[len(name) + 1:]: z[k] for k in z.files if k.startswith(name + "_")}
+
+
+def test_change_spacing_shapes_and_scipy_restatement_match_the_reference():
+    """Outputs of the reference's change_spacing (tests/golden/make_golden_change_spacing.py): the product's shape
+    arithmetic (float32 header zooms) and the scipy call the GPU tests compare the kernels with reproduce them exactly."""
+    from scipy import ndimage
+    from boa_b200.resample import resampled_depth, zoomed_shape
+    n = 0
+    for name, c in _change_spacing_cases():
+        ct, sp, tg, ref = c["ct"], c["spacing_zyx"], c["target_zyx"], c["resampled"]
+        if name.startswith("thickness"):
+            assert resampled_depth(ct.shape[0], sp[0], tg[0]) == ref.shape[0] and ref.shape[1:] == ct.shape[1:]
+        else:
+            assert zoomed_shape(ct.shape, sp, float(tg[0])) == ref.shape, name
+        zoom = [np.float64(np.float32(s)) / np.float64(np.float32(t)) for s, t in zip(sp, tg)]
+        # in the reference's own memory order ([x, y, z]) the restated call is the reference's call: bit-equal
+        xyz = ndimage.zoom(ct.transpose(2, 1, 0).astype(np.float64), zoom[::-1], order=3, mode="nearest")
+        assert np.array_equal(xyz.astype(np.int32).transpose(2, 1, 0), ref), name
+        # evaluated on the [z, y, x] array (what the GPU tests do) the separable passes run in another order: the spline
+        # values agree to ~1e-11, so the truncated integers differ (by one) only where the value is numerically an integer
+        zyx = ndimage.zoom(ct.astype(np.float64), zoom, order=3, mode="nearest")
+        diff = np.abs(zyx.astype(np.int32) - ref)
+        assert diff.max() <= 1 and np.all(np.abs(zyx - np.rint(zyx))[diff != 0] < 1e-6), name
+        back = ndimage.zoom(c["labels"], np.array(ct.shape) / np.array(ref.shape), order=0, mode="nearest")
+        assert np.array_equal(back, c["labels_back"]), name
+        n += 1
+    assert n == 4
