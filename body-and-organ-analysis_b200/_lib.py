@@ -58,6 +58,7 @@ _SIGS = {
     "boa_accumulate_weights": (C.c_int, [C.POINTER(C.c_int32), C.c_int, C.POINTER(C.c_int32), _P, _P,
                                          C.POINTER(C.c_int32), _P]),
     "boa_finalize_argmax": (C.c_int, [_P, _P, C.c_int, C.c_size_t, C.POINTER(C.c_uint8), C.c_int, _P, _P, _P]),
+    "boa_normalize_logits": (C.c_int, [_P, _P, C.c_int, C.c_size_t, C.c_float, _P, _P]),
     "boa_tissue_subclassify": (C.c_int, [_P, C.c_int, _P, C.c_size_t, _P, _P]),
     "boa_slice_label_stats": (C.c_int, [_P, _P, C.c_int, _P, C.c_int, C.c_int, C.c_size_t, C.c_int, _P, _P, _P]),
     "boa_label_hu_hist": (C.c_int, [_P, C.c_int, _P, C.c_size_t, C.c_int, C.c_int, C.c_int, _P, _P, _P]),

@@ -643,6 +643,36 @@ extern "C" int boa_finalize_argmax(const float* d_logits_acc, const float* d_wei
   return BOA_OK;
 }
 
+// `predicted_logits /= n_predictions` + the isinf check of the logits-returning entry
+// (predict_from_raw_data.py:620-625; the fold mean of predict_logits_from_preprocessed_data :494-500 as one divisor):
+// acc[c][v] = acc[c][v] / (w[v] * folds), IEEE division, non-finite quotients counted.
+__global__ void __launch_bounds__(256)
+normalize_logits_kernel(float* __restrict__ acc, const float* __restrict__ w, int C, size_t V, float folds,
+                        int32_t* __restrict__ nonfinite) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  int bad = 0;
+  for (size_t v = (size_t)blockIdx.x * blockDim.x + threadIdx.x; v < V; v += stride) {
+    const float d = __fmul_rn(w[v], folds);
+    for (int c = 0; c < C; ++c) {
+      const float q = __fdiv_rn(acc[(size_t)c * V + v], d);
+      acc[(size_t)c * V + v] = q;
+      bad |= !isfinite(q);
+    }
+  }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicAdd(nonfinite, 1);
+}
+
+extern "C" int boa_normalize_logits(float* d_logits_acc, const float* d_weight_acc, int C, size_t V, float folds,
+                                    int32_t* d_nonfinite, void* stream) {
+  BOA_REQUIRE(d_logits_acc && d_weight_acc && d_nonfinite, "boa_normalize_logits: null");
+  BOA_REQUIRE(C > 0 && folds > 0.0f, "boa_normalize_logits: C=%d folds=%f", C, (double)folds);
+  if (V == 0) return BOA_OK;
+  normalize_logits_kernel<<<grid_for(V, 256, 8), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      d_logits_acc, d_weight_acc, C, V, folds, d_nonfinite);
+  BOA_CHECK_LAUNCH();
+  return BOA_OK;
+}
+
 // Finalize on a different grid than the network's (nnU-Net resampled the volume to the plan's spacing): ResampledSrc.
 extern "C" int boa_finalize_argmax_resampled(const float* d_logits_acc, const float* d_weight_acc, int C,
                                              const int32_t* net_shape, const int32_t* out_shape, int separate_z,

@@ -324,11 +324,10 @@ class nnUNetPredictor:
             vol, origins, unpad = self._prepare(input_image)
             acc = self.accumulate(vol, origins)
             w = weight_sum(vol.shape, self.patch_size, origins, self.gaussian(), self.gaussian_kind)
-            acc /= w * float(len(self.networks))
-            if not torch.isfinite(acc).all():
-                raise RuntimeError("Encountered inf in predicted array. Aborting... If this problem persists, reduce "
-                                   "value_scaling_factor in compute_gaussian or increase the dtype of "
-                                   "predicted_logits to fp32")
+            bad = torch.zeros(1, dtype=torch.int32, device=self.device)
+            _lib.check(_lib.lib().boa_normalize_logits(_lib.ptr(acc), _lib.ptr(w), self.num_classes, w.numel(),
+                                                       float(len(self.networks)), _lib.ptr(bad), _lib.stream_ptr()))
+            raise_if_nonfinite([bad])
             return acc[(slice(None), *unpad)]
 
     @torch.inference_mode()

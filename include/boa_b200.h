@@ -139,6 +139,13 @@ int boa_accumulate_weights(const int32_t* h_origins, int n_patches, const int32_
 int boa_finalize_argmax(const float* d_logits_acc, const float* d_weight_acc, int C, size_t V, const uint8_t* h_lut,
                         int overwrite_nonzero_only, uint8_t* d_label_inout, int32_t* d_nonfinite, void* stream);
 
+/* The same division and check WITHOUT the argmax, for the entry that returns logits
+ * (predict_sliding_window_return_logits, predict_from_raw_data.py:620-625, and the fold mean of
+ * predict_logits_from_preprocessed_data :494-500): d_logits_acc[c][v] /= d_weight_acc[v] * folds in place.
+ * d_nonfinite: int32 counter incremented when a quotient is not finite (caller zeroes it). */
+int boa_normalize_logits(float* d_logits_acc, const float* d_weight_acc, int C, size_t V, float folds,
+                         int32_t* d_nonfinite, void* stream);
+
 /* subclassify_tissues numerics: tissue id from (HU, body region) with inclusive HU bounds
  * (_external/body_composition_analysis/tissue/subclassification.py:38-53, tissue/definition.py:6-30). */
 int boa_tissue_subclassify(const void* d_ct, int ct_dtype, const uint8_t* d_regions, size_t n, uint8_t* d_tissues,

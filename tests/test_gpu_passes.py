@@ -338,3 +338,24 @@ def test_change_spacing_against_the_reference_vectors(cuda):
         assert inner.mean() > 0.4 and np.array_equal(got[inner], ref[inner]), name
         back = resample_labels_nearest(_dev(z[name + "_labels"]), ct.shape).cpu().numpy()
         assert np.array_equal(back, z[name + "_labels_back"]), name
+
+
+def test_normalize_logits_equals_ieee_division_and_flags_nonfinite(cuda):
+    """boa_normalize_logits: acc[c][v] / (w[v] * folds) bit-equal to the fp32 division torch does, counter set by inf."""
+    import ctypes as C
+    from boa_b200 import _lib
+    rng = np.random.default_rng(2)
+    for V, Cn, folds in ((1000, 5, 1), (4099, 3, 5)):
+        acc = (rng.standard_normal((Cn, V)) * 50).astype(np.float32)
+        w = rng.uniform(1e-3, 40.0, size=V).astype(np.float32)
+        a, wd = _dev(acc), _dev(w)
+        want = (a / (wd * float(folds))).cpu().numpy()
+        bad = torch.zeros(1, dtype=torch.int32, device="cuda")
+        _lib.check(_lib.lib().boa_normalize_logits(_lib.ptr(a), _lib.ptr(wd), Cn, V, float(folds), _lib.ptr(bad),
+                                                   _lib.stream_ptr()))
+        assert np.array_equal(a.cpu().numpy(), want) and int(bad) == 0
+        acc[1, 7] = np.inf
+        a = _dev(acc)
+        _lib.check(_lib.lib().boa_normalize_logits(_lib.ptr(a), _lib.ptr(wd), Cn, V, float(folds), _lib.ptr(bad),
+                                                   _lib.stream_ptr()))
+        assert int(bad) > 0
